@@ -1,0 +1,179 @@
+"""numpy restatement of the CFD_Julia vortex-merger hot path (second, independent oracle).
+
+TEST INFRASTRUCTURE, NOT THE PRODUCT: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.
+
+It follows the same reference lines as oracle/vm_oracle.c (Common.jl:97-182,208-237,
+vm.jl:12-90, tgv.jl:82-90, fft_p.jl:8-42) but uses numpy's pocketfft instead of the C file's
+radix-2 FFT, so the two oracles cross-check each other's FFT and index conventions.
+Arrays are Fortran-ordered (column-major, like Julia); "ghosted" = shape (nx+2, ny+2).
+
+Parity pin: order.jl:13 (five fft_p.jl L2 errors) -- see tests/test_oracle.py.  Beyond that
+pin and the analytic Taylor-Green solution the reference's outputs are unrecorded and Julia
+is not installed here: "parity unpinned".
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# 13_Poisson_Solver_FFT_Spectral/specrtral_vs_FDM/order.jl:13 -- the only recorded reference outputs
+ORDER_JL_FFT_FDM = {
+    32: .0015607100315532957,
+    64: .0005987381110678801,
+    128: .00014313734718665358,
+    256: 3.549617203207291e-5,
+    512: 8.865373334924762e-6,
+}
+
+
+def wavenumbers(nx: int, eps: float = 1.e-6) -> np.ndarray:
+    """Common.jl:106-112."""
+    hx = 2 * np.pi / nx
+    kx = np.empty(nx)
+    i = np.arange(1, nx // 2 + 1)
+    kx[i - 1] = hx * (i - 1)
+    kx[i + nx // 2 - 1] = hx * (i - nx // 2 - 1)
+    kx[0] = eps
+    return kx
+
+
+def divisor(nx, ny, dx, dy, eps=1.e-6):
+    """Common.jl:101-103,119-121: aa + bb*cos(kx[i]) + cc*cos(ky[j]) (ky = kx, :113)."""
+    assert nx == ny
+    aa = -2 / dx**2 - 2 / dy**2
+    bb = 2 / dx**2
+    cc = 2 / dy**2
+    ck = np.cos(wavenumbers(nx, eps))
+    return (aa + bb * ck[:, None]) + cc * ck[None, :]
+
+
+def poisson(nx, ny, dx, dy, f, eps=1.e-6):
+    """real(ifft(fft(f)/divisor)) with e[1,1]=0 (Common.jl:115-123); f is nx x ny."""
+    e = np.fft.fft2(np.asarray(f, dtype=np.complex128))
+    e[0, 0] = 0
+    return np.real(np.fft.ifft2(e / divisor(nx, ny, dx, dy, eps)))
+
+
+def fps(nx, ny, dx, dy, f, s, eps=1.e-6):
+    s[1:nx + 1, 1:ny + 1] = poisson(nx, ny, dx, dy, f[:nx, :ny], eps)
+
+
+def ps_fft(nx, ny, dx, dy, f, eps=1.e-6):
+    """fft_p.jl:8-42; f is (nx+1)x(ny+1)."""
+    return poisson(nx, ny, dx, dy, f[:nx, :ny], eps)
+
+
+def ghost_fill(nx, ny, a):
+    """Common.jl:138-146 / vm.jl:30-38 order."""
+    a[nx + 1, :] = a[1, :]
+    a[:, ny + 1] = a[:, 1]
+    a[0, :] = a[nx, :]
+    a[:, 0] = a[:, ny]
+
+
+def vm_rhs(nx, ny, dx, dy, re, w, r, s, f):
+    """Common.jl:132-182."""
+    f[:nx, :ny] = -w[1:nx + 1, 1:ny + 1]
+    fps(nx, ny, dx, dy, f, s)
+    ghost_fill(nx, ny, s)
+    aa = 1 / (re * dx**2)
+    bb = 1 / (re * dy**2)
+    gg = 1 / (4 * dx * dy)
+    hh = 1 / 3
+    c = slice(1, nx + 1), slice(1, ny + 1)
+
+    def sh(a, di, dj):
+        return a[1 + di:nx + 1 + di, 1 + dj:ny + 1 + dj]
+
+    j1 = ((sh(w, 1, 0) - sh(w, -1, 0)) * (sh(s, 0, 1) - sh(s, 0, -1)) -
+          (sh(w, 0, 1) - sh(w, 0, -1)) * (sh(s, 1, 0) - sh(s, -1, 0)))
+    j2 = (sh(w, 1, 0) * (sh(s, 1, 1) - sh(s, 1, -1)) -
+          sh(w, -1, 0) * (sh(s, -1, 1) - sh(s, -1, -1)) -
+          sh(w, 0, 1) * (sh(s, 1, 1) - sh(s, -1, 1)) +
+          sh(w, 0, -1) * (sh(s, 1, -1) - sh(s, -1, -1)))
+    j3 = (sh(w, 1, 1) * (sh(s, 0, 1) - sh(s, 1, 0)) -
+          sh(w, -1, -1) * (sh(s, -1, 0) - sh(s, 0, -1)) -
+          sh(w, -1, 1) * (sh(s, 0, 1) - sh(s, -1, 0)) +
+          sh(w, 1, -1) * (sh(s, 1, 0) - sh(s, 0, -1)))
+    jac = gg * (j1 + j2 + j3) * hh
+    r[c] = -jac + (aa * (sh(w, 1, 0) - 2 * sh(w, 0, 0) + sh(w, -1, 0)) +
+                   bb * (sh(w, 0, 1) - 2 * sh(w, 0, 0) + sh(w, 0, -1)))
+
+
+def numerical(nx, ny, nt, dx, dy, dt, re, wn, snap=None, freq=0):
+    """vm.jl:12-90 / tgv.jl:13-79 (no file output).  Returns (wn[2:nx+2,2:ny+2], last psi ghosted)."""
+    wt = np.zeros_like(wn)
+    r = np.zeros_like(wn)
+    s = np.zeros_like(wn)
+    f = np.zeros((nx, ny), order="F")
+    c = slice(1, nx + 1), slice(1, ny + 1)
+    for k in range(1, nt + 1):
+        vm_rhs(nx, ny, dx, dy, re, wn, r, s, f)
+        wt[c] = wn[c] + dt * r[c]
+        ghost_fill(nx, ny, wt)
+        vm_rhs(nx, ny, dx, dy, re, wt, r, s, f)
+        wt[c] = .75 * wn[c] + .25 * wt[c] + (.25 * dt) * r[c]
+        ghost_fill(nx, ny, wt)
+        vm_rhs(nx, ny, dx, dy, re, wt, r, s, f)
+        wn[c] = wn[c] / 3. + (2 / 3) * wt[c] + ((2 / 3) * dt) * r[c]
+        ghost_fill(nx, ny, wn)
+        if snap is not None and freq and k % freq == 0:
+            snap(k, wn)
+    return wn[1:nx + 2, 1:ny + 2].copy(order="F"), s
+
+
+def vm_ic(nx, ny, x, y, w):
+    """Common.jl:208-219 followed by main()'s ghost fill vm.jl:121-128."""
+    sigma = np.pi
+    xc1, yc1 = np.pi - np.pi / 4., np.pi
+    xc2, yc2 = np.pi + np.pi / 4., np.pi
+    X = x[:, None]
+    Y = y[None, :]
+    w[1:nx + 2, 1:ny + 2] = (np.exp(-sigma * ((X - xc1)**2 + (Y - yc1)**2)) +
+                             np.exp(-sigma * ((X - xc2)**2 + (Y - yc2)**2)))
+    w[0, :] = w[nx, :]
+    w[:, 0] = w[:, ny]
+    w[nx + 1, :] = w[1, :]
+    w[:, ny + 1] = w[:, 1]
+
+
+def exact_tgv(nx, ny, x, y, time, re):
+    """tgv.jl:82-90."""
+    nq = 4
+    return np.asfortranarray(2 * nq * np.cos(nq * x[:, None]) * np.cos(nq * y[None, :]) *
+                             np.exp(-2 * nq**2 * time / re))
+
+
+def compute_l2norm_bnds(nx, ny, r):
+    """Common.jl:234-237."""
+    return float(np.sqrt(np.sum(r[:nx + 1, :ny + 1]**2) / ((nx + 1) * (ny + 1))))
+
+
+def fft_p_case(nx):
+    """fft_p.jl:44-108 for one grid size: returns (rms_error, max_error)."""
+    ny = nx
+    dx = 1. / nx
+    dy = 1. / ny
+    x = dx * np.arange(nx + 1)
+    y = dy * np.arange(ny + 1)
+    km = 16
+    c1 = (1. / km)**2
+    c2 = -8 * np.pi**2
+    X = x[:, None]
+    Y = y[None, :]
+    ue = (np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y) +
+          c1 * np.sin(km * 2 * np.pi * X) * np.sin(km * 2 * np.pi * Y))
+    f = (c2 * np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y) +
+         c2 * np.sin(km * 2 * np.pi * X) * np.sin(km * 2 * np.pi * Y))
+    un = np.zeros_like(f)
+    un[:nx, :ny] = ps_fft(nx, ny, dx, dy, f)
+    un[nx, :] = un[0, :]
+    un[:, ny] = un[:, 0]
+    err = un - ue
+    return compute_l2norm_bnds(nx, ny, err), float(np.max(np.abs(err)))
+
+
+def grid(nx, ny, lx=2 * np.pi, ly=2 * np.pi):
+    dx = lx / nx
+    dy = ly / ny
+    return dx, dy, dx * np.arange(nx + 1), dy * np.arange(ny + 1)
