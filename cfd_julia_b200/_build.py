@@ -1,0 +1,53 @@
+"""Builds cfd_julia_b200/libvmk.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
+
+nvcc cross-compiles without a GPU.  The library is git-ignored but travels to the GPU box with
+the repo snapshot, so importing the package there does not need to rebuild.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "libvmk.so")
+SRC = os.path.join(HERE, "csrc", "vmk.cu")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    # the reference arithmetic is unfused (oracle: -ffp-contract=off); FMAs are written explicitly where wanted
+    "--fmad=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found: cannot build libvmk.so")
+    return cand
+
+
+def sources():
+    return [SRC] + sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [os.path.join(ROOT, "include", "vmk.h")]
+
+
+def stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(s) > t for s in sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if force or stale():
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
+        subprocess.check_call(cmd, cwd=ROOT)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,240 @@
+"""Host-side mirror of the reference's operator interface for the vortex-merger path.
+
+Same function names, positional arguments, in-place mutation and return values as the Julia
+originals (file:line relative to the CFD_Julia checkout):
+
+    fps(nx, ny, dx, dy, u, e, data, data1, f, s, eps=1e-6)          Common.jl:97-125
+    vm_rhs(nx, ny, dx, dy, re, w, u, e, data, data1, r, s, f)       Common.jl:132-182
+    numerical(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns)             19_NS2D_Vortex_Merger/vm.jl:12-90
+    numerical_tgv(nx, ny, nt, dx, dy, dt, re, wn)                   19_NS2D_Vortex_Merger/tgv.jl:13-79
+    ps_fft(nx, ny, dx, dy, f, eps=1e-6)                             12_Poisson_Solver_FFT/fft_p.jl:8-42
+    vm_ic / exact_tgv / compute_l2norm_bnds                         Common.jl:208-219,234-237, tgv.jl:82-90
+
+Arrays are numpy float64, Fortran-ordered (column-major like Julia); "ghosted" arrays have shape
+(nx+2, ny+2).  Everything on the path runs in libvmk.so on the GPU through the C ABI of
+include/vmk.h; this module only marshals pointers (the Julia wrapper julia/CommonB200.jl does the same
+with ccall).  There is no CPU implementation here: without the CUDA library or a device the calls raise.
+
+Reference behaviours kept: fps/vm_rhs leave the dead scratch arguments u, e, data, data1 untouched
+(`e` is rebound and `u` never used in the reference either); vm_rhs writes r's interior only, all of s,
+and f = -w interior; numerical mutates wn (all ghosts valid) and returns wn[2:nx+2, 2:ny+2].
+Reference behaviour NOT kept: vm.jl:78-86 writes every snapshot to "vm1.txt" because its record index
+m is never incremented (hybrid.jl:81 does increment it); numerical() here numbers the files vm1..vm{ns}.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from ._lib import SNAPSHOT_FN, VmkError, VmkLibrary, default_library
+
+__all__ = ["Common", "fps", "vm_rhs", "numerical", "numerical_tgv", "ps_fft", "vm_ic", "exact_tgv",
+           "compute_l2norm_bnds", "write_field", "Plan", "VmkError"]
+
+
+def _ptr(a: np.ndarray, shape, what: str):
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64:
+        raise TypeError(f"{what}: expected a float64 numpy array")
+    if tuple(a.shape) != tuple(shape):
+        raise IndexError(f"{what}: expected shape {tuple(shape)}, got {tuple(a.shape)}")  # Julia: BoundsError
+    if not a.flags.f_contiguous:
+        raise TypeError(f"{what}: expected a Fortran-ordered (column-major) array")
+    return a.ctypes.data
+
+
+class Plan:
+    """Owns a vmk_plan (device buffers, tables, stream).  The reference has no plan object: Common keeps a
+    cache keyed by grid size, as the Julia wrapper does."""
+
+    def __init__(self, lib: VmkLibrary, nx: int, ny: int, rank: int = 0, nranks: int = 1):
+        self.lib = lib
+        self.nx, self.ny, self.rank, self.nranks = nx, ny, rank, nranks
+        h = C.c_void_p()
+        lib.check(lib.plan_create_slab(nx, ny, rank, nranks, C.byref(h)))
+        self.handle = h
+        self._fin = weakref.finalize(self, lib.plan_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    # device-resident path
+    def upload(self, wn):
+        self.lib.check(self.lib.upload(self.handle, _ptr(wn, (self.nx + 2, self.ny + 2), "wn")))
+
+    def step(self, dx, dy, dt, re, nsteps=1):
+        self.lib.check(self.lib.step(self.handle, dx, dy, dt, re, nsteps))
+
+    def download(self, wn=None, psi=None):
+        sh = (self.nx + 2, self.ny + 2)
+        self.lib.check(self.lib.download(self.handle, None if wn is None else _ptr(wn, sh, "wn"),
+                                         None if psi is None else _ptr(psi, sh, "psi")))
+
+    def sync(self):
+        self.lib.check(self.lib.sync(self.handle))
+
+    def step_elapsed_ms(self) -> float:
+        ms = C.c_double()
+        self.lib.check(self.lib.step_elapsed_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    def profile_steps(self, dx, dy, dt, re, nsteps):
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        self.lib.check(self.lib.profile_steps(self.handle, dx, dy, dt, re, nsteps, ms, n))
+        return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(("k1", "k2", "k3", "k4"))}
+
+    def set_option(self, key: str, value: int):
+        self.lib.check(self.lib.set_option(self.handle, key.encode(), value))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.launch_count(self.handle))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.device_bytes(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.stream(self.handle) or 0)
+
+
+class Common:
+    """The reference's `Common` module surface for this path, bound to one C-ABI library."""
+
+    def __init__(self, lib: VmkLibrary | None = None):
+        self._lib = lib
+        self._plans: dict[tuple[int, int], Plan] = {}
+
+    @property
+    def lib(self) -> VmkLibrary:
+        if self._lib is None:
+            self._lib = default_library()
+        return self._lib
+
+    def plan(self, nx: int, ny: int) -> Plan:
+        key = (int(nx), int(ny))
+        p = self._plans.get(key)
+        if p is None:
+            p = self._plans[key] = Plan(self.lib, *key)
+        return p
+
+    def clear_plans(self):
+        for p in self._plans.values():
+            p.close()
+        self._plans.clear()
+
+    # ---- Common.jl:97-125 ---------------------------------------------------------------------
+    def fps(self, nx, ny, dx, dy, u, e, data, data1, f, s, eps=1.e-6):
+        p = self.plan(nx, ny)
+        self.lib.check(self.lib.fps(p.handle, dx, dy, _ptr(f, (nx, ny), "f"), _ptr(s, (nx + 2, ny + 2), "s"), eps))
+
+    # ---- Common.jl:132-182 --------------------------------------------------------------------
+    def vm_rhs(self, nx, ny, dx, dy, re, w, u, e, data, data1, r, s, f):
+        p = self.plan(nx, ny)
+        g = (nx + 2, ny + 2)
+        self.lib.check(self.lib.rhs(p.handle, dx, dy, re, _ptr(w, g, "w"), _ptr(r, g, "r"), _ptr(s, g, "s"),
+                                    None if f is None else _ptr(f, (nx, ny), "f")))
+
+    # ---- fft_p.jl:8-42 ------------------------------------------------------------------------
+    def ps_fft(self, nx, ny, dx, dy, f, eps=1.e-6):
+        p = self.plan(nx, ny)
+        u = np.zeros((nx, ny), order="F")
+        self.lib.check(self.lib.ps_fft(p.handle, dx, dy, _ptr(f, (nx + 1, ny + 1), "f"), u.ctypes.data, eps))
+        return u
+
+    # ---- vm.jl:12-90 --------------------------------------------------------------------------
+    def numerical(self, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
+        """snapshot(k, ut) is called every nt // ns steps with ut = wn[2:nx+2, 2:ny+2] (vm.jl:78-80); if
+        `outdir` is given the reference's text files are written there (numbered, see module docstring)."""
+        if ns <= 0 or nt // ns == 0:
+            raise ZeroDivisionError("mod(k, nt ÷ ns) with nt ÷ ns == 0")  # Julia: DivideError at vm.jl:78
+        freq = nt // ns
+        return self._numerical(nx, ny, nt, dx, dy, dt, re, wn, freq, x, y, snapshot, outdir)
+
+    # ---- tgv.jl:13-79 -------------------------------------------------------------------------
+    def numerical_tgv(self, nx, ny, nt, dx, dy, dt, re, wn):
+        return self._numerical(nx, ny, nt, dx, dy, dt, re, wn, 0, None, None, None, None)
+
+    def _numerical(self, nx, ny, nt, dx, dy, dt, re, wn, freq, x, y, snapshot, outdir):
+        p = self.plan(nx, ny)
+        g = (nx + 2, ny + 2)
+        out = np.zeros((nx + 1, ny + 1), order="F")
+        rec = [0]
+
+        def _snap(k, ptr, _user):
+            rec[0] += 1
+            ut = wn[1:nx + 2, 1:ny + 2]
+            if snapshot is not None:
+                snapshot(int(k), ut)
+            if outdir is not None:
+                write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut)
+
+        want = freq > 0 and (snapshot is not None or outdir is not None)
+        cb = SNAPSHOT_FN(_snap) if want else SNAPSHOT_FN()
+        self.lib.check(self.lib.numerical(p.handle, int(nt), dx, dy, dt, re, _ptr(wn, g, "wn"), out.ctypes.data,
+                                          freq if want else 0, cb, None))
+        return out
+
+
+def write_field(path, x, y, ut):
+    """The reference's text dump "x y w" with j outer, i inner (vm.jl:81-85, 132-136, 142-146)."""
+    nx1, ny1 = ut.shape
+    with open(path, "w") as io:
+        for j in range(ny1):
+            for i in range(nx1):
+                io.write(f"{float(x[i])!r} {float(y[j])!r} {float(ut[i, j])!r}\n")
+
+
+# ---- setup helpers of the callers (host-side, not on the hot path) ----------------------------------
+def vm_ic(nx, ny, x, y, w):
+    """Common.jl:208-219: two Gaussian vortices on w[2:nx+2, 2:ny+2] (ghost fill is the caller's, vm.jl:121-128)."""
+    sigma = np.pi
+    xc1, yc1 = np.pi - np.pi / 4., np.pi
+    xc2, yc2 = np.pi + np.pi / 4., np.pi
+    X = np.asarray(x)[:nx + 1, None]
+    Y = np.asarray(y)[None, :ny + 1]
+    w[1:nx + 2, 1:ny + 2] = (np.exp(-sigma * ((X - xc1)**2 + (Y - yc1)**2)) +
+                            np.exp(-sigma * ((X - xc2)**2 + (Y - yc2)**2)))
+
+
+def exact_tgv(nx, ny, x, y, time, re):
+    """tgv.jl:82-90."""
+    nq = 4.
+    X = np.asarray(x)[:nx + 1, None]
+    Y = np.asarray(y)[None, :ny + 1]
+    return np.asfortranarray(2 * nq * np.cos(nq * X) * np.cos(nq * Y) * np.exp(-2 * nq**2 * time / re))
+
+
+def compute_l2norm_bnds(nx, ny, r):
+    """Common.jl:234-237."""
+    return float(np.sqrt(np.sum(np.asarray(r)[:nx + 1, :ny + 1]**2) / ((nx + 1) * (ny + 1))))
+
+
+_common = Common()
+
+
+def fps(nx, ny, dx, dy, u, e, data, data1, f, s, eps=1.e-6):
+    return _common.fps(nx, ny, dx, dy, u, e, data, data1, f, s, eps)
+
+
+def vm_rhs(nx, ny, dx, dy, re, w, u, e, data, data1, r, s, f):
+    return _common.vm_rhs(nx, ny, dx, dy, re, w, u, e, data, data1, r, s, f)
+
+
+def ps_fft(nx, ny, dx, dy, f, eps=1.e-6):
+    return _common.ps_fft(nx, ny, dx, dy, f, eps)
+
+
+def numerical(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
+    return _common.numerical(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot, outdir)
+
+
+def numerical_tgv(nx, ny, nt, dx, dy, dt, re, wn):
+    return _common.numerical_tgv(nx, ny, nt, dx, dy, dt, re, wn)
+
+
+def plan(nx, ny) -> Plan:
+    return _common.plan(nx, ny)

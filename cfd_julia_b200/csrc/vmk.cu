@@ -1,0 +1,822 @@
+// vmk.cu -- plan object and C ABI (include/vmk.h) of the vortex-merger step on B200.
+//
+// Host-side orchestration only: which kernel runs on which buffer in which order.  All arithmetic on
+// field data happens in the kernel bodies of vmk_kernels.cuh, on the device.  There is no CPU
+// compute path in this file; without a CUDA device every entry point returns VMK_ECUDA.
+//
+// Reference lines replaced (relative to the CFD_Julia checkout):
+//   vmk_plan_create   vm.jl:13-19 (per-call allocations), Common.jl:98-113 (k table), FFTW plans :117,:123
+//   enqueue_poisson   Common.jl:115-123   (K1, K2, K3)
+//   enqueue_stage     Common.jl:132-182 + vm.jl:28-38 / 43-57 / 62-76 (K1..K4)
+//   vmk_numerical     vm.jl:24-89
+#ifdef VMK_EMUL
+// the host-emulation build (tests/emul) exports the same ABI under vmke_* so both can be loaded at once
+#define vmk_version vmke_version
+#define vmk_last_error vmke_last_error
+#define vmk_plan_create vmke_plan_create
+#define vmk_plan_create_slab vmke_plan_create_slab
+#define vmk_plan_destroy vmke_plan_destroy
+#define vmk_fps vmke_fps
+#define vmk_ps_fft vmke_ps_fft
+#define vmk_rhs vmke_rhs
+#define vmk_numerical vmke_numerical
+#define vmk_upload vmke_upload
+#define vmk_step vmke_step
+#define vmk_download vmke_download
+#define vmk_sync vmke_sync
+#define vmk_stream vmke_stream
+#define vmk_step_elapsed_ms vmke_step_elapsed_ms
+#define vmk_profile_steps vmke_profile_steps
+#define vmk_launch_count vmke_launch_count
+#define vmk_set_option vmke_set_option
+#define vmk_device_bytes vmke_device_bytes
+#define vmk_peer_blob_bytes vmke_peer_blob_bytes
+#define vmk_peer_export vmke_peer_export
+#define vmk_peer_import vmke_peer_import
+#define vmk_peer_attach_local vmke_peer_attach_local
+#define vmk_barrier_hook vmke_barrier_hook
+#endif
+#include "../../include/vmk.h"
+
+#include <math.h>
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "vmk_backend.cuh"
+#include "vmk_kernels.cuh"
+
+using namespace vmk;
+
+#define VMK_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__) return rc__;       \
+  } while (0)
+
+namespace {
+
+struct StepParams {
+  double dx, dy, dt, re;
+  bool operator<(const StepParams& o) const {
+    return std::tie(dx, dy, dt, re) < std::tie(o.dx, o.dy, o.dt, o.re);
+  }
+};
+
+struct SizeOps {
+  size_t twn;       // twiddle table entries
+  size_t smem;      // dynamic shared memory of K1/K2/K3
+  int fpc;          // transforms per CTA
+  void (*fill_tw)(double2*);
+  int (*configure)(int* res_k1, int* res_k2, int* res_k3);
+  int (*k1)(int grid, const K1Args&, Stream&);
+  int (*k2)(int grid, const K2Args&, Stream&);
+  int (*k3)(int grid, const K3Args&, Stream&);
+};
+
+template <class C>
+struct K1Body {
+  VMK_HD static void run(const Ctx& c, const K1Args& a) { k1_body<C>(c, a); }
+};
+template <class C>
+struct K2Body {
+  VMK_HD static void run(const Ctx& c, const K2Args& a) { k2_body<C>(c, a); }
+};
+template <class C>
+struct K3Body {
+  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C>(c, a); }
+};
+template <int MODE>
+struct K4Body {
+  VMK_HD static void run(const Ctx& c, const K4Args& a) { k4_body<MODE>(c, a); }
+};
+struct K5Unpack {
+  VMK_HD static void run(const Ctx& c, const K5Args& a) { k5_unpack_body(c, a); }
+};
+struct K5Pack {
+  VMK_HD static void run(const Ctx& c, const K5Args& a) { k5_pack_body(c, a); }
+};
+struct K5Negate {
+  VMK_HD static void run(const Ctx& c, const K5Args& a) { k5_negate_body(c, a); }
+};
+
+// twiddles W_B^x = exp(-2 pi i x / B), rounded from long double (same recipe as the oracle's tables)
+template <class C>
+void fill_twiddles(double2* tw) {
+  const long double tau = 6.283185307179586476925286766559005768L;
+  for (int k = 0; k < C::P - 1; k++) {
+    const int B = 1 << C::hi(k), len = C::tw_len(k), off = C::tw_off(k);
+    for (int x = 0; x < len; x++) {
+      const long double ang = tau * (long double)x / (long double)B;
+      tw[off + x].x = (double)cosl(ang);
+      tw[off + x].y = (double)(-sinl(ang));
+    }
+  }
+}
+
+template <int M>
+SizeOps make_ops() {
+  using C = typename CfgFor<M>::type;
+  SizeOps o;
+  o.twn = C::TWN;
+  o.smem = C::SMEM_BYTES;
+  o.fpc = C::FPC;
+  o.fill_tw = &fill_twiddles<C>;
+  o.configure = [](int* r1, int* r2, int* r3) -> int {
+    VMK_TRY((be_configure<K1Body<C>, K1Args, C::CT, C::MINB>(C::SMEM_BYTES, r1)));
+    VMK_TRY((be_configure<K2Body<C>, K2Args, C::CT, C::MINB>(C::SMEM_BYTES, r2)));
+    VMK_TRY((be_configure<K3Body<C>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, r3)));
+    return 0;
+  };
+  o.k1 = [](int grid, const K1Args& a, Stream& s) -> int {
+    return be_launch<K1Body<C>, K1Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+  };
+  o.k2 = [](int grid, const K2Args& a, Stream& s) -> int {
+    return be_launch<K2Body<C>, K2Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+  };
+  o.k3 = [](int grid, const K3Args& a, Stream& s) -> int {
+    return be_launch<K3Body<C>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+  };
+  return o;
+}
+
+bool ops_for(int M, SizeOps* o) {
+  switch (M) {
+    case 5: *o = make_ops<5>(); return true;
+    case 6: *o = make_ops<6>(); return true;
+    case 7: *o = make_ops<7>(); return true;
+    case 8: *o = make_ops<8>(); return true;
+    case 9: *o = make_ops<9>(); return true;
+    case 10: *o = make_ops<10>(); return true;
+    case 11: *o = make_ops<11>(); return true;
+    case 12: *o = make_ops<12>(); return true;
+    case 13: *o = make_ops<13>(); return true;
+    default: return false;
+  }
+}
+
+int ilog2_exact(int64_t n) {
+  int m = 0;
+  while ((((int64_t)1) << m) < n) m++;
+  return ((((int64_t)1) << m) == n) ? m : -1;
+}
+
+enum { KI_K1 = 0, KI_K2, KI_K3, KI_K4, KI_COUNT };
+
+}  // namespace
+
+struct vmk_plan {
+  int N = 0, M = 0, rank = 0, nranks = 1, NJ = 0, log2NJ = 0, j0 = 0;
+  int sms = 0;
+  SizeOps ops{};
+  int res_k1 = 0, res_k2 = 0, res_k3 = 0;
+  // device buffers
+  double* w[3] = {nullptr, nullptr, nullptr};  // wn, wtA, wtB: slabs with halo rows
+  double* psi = nullptr;                       // slab with halo rows
+  double2* T = nullptr;                        // local half spectrum [N/2][NJ]
+  double2* tw = nullptr;
+  double* bbcos = nullptr;
+  double* cccos = nullptr;
+  double* staging = nullptr;  // (NJ+2) x (N+2), allocated on first host-array call
+  int64_t dev_bytes = 0;
+  // peers (slab decomposition): pointers to every rank's buffers, own entries included
+  double* peer_w[3][kMaxPeers];
+  double* peer_psi[kMaxPeers];
+  double2* peer_T[kMaxPeers];
+  bool peers_ready = false;
+  std::vector<void*> ipc_opened;
+  void (*barrier_fn)(void*) = nullptr;  // enqueues a cross-rank barrier on the plan's stream
+  void* barrier_user = nullptr;
+  // divisor cache (Common.jl:101-113)
+  bool div_valid = false;
+  double div_dx = 0, div_dy = 0, div_eps = 0, div_aa = 0;
+  Stream st;
+  Event ev0, ev1;
+  bool ev_valid = false;
+  bool uploaded = false;
+  int64_t launches = 0;
+  int k4_rows = 32;
+  int use_graph = 1;
+#ifndef VMK_EMUL
+  std::map<StepParams, cudaGraphExec_t> graphs;
+#endif
+  // per-kernel timing (vmk_profile_steps)
+  bool profiling = false;
+  double prof_ms[KI_COUNT] = {0, 0, 0, 0};
+  int64_t prof_n[KI_COUNT] = {0, 0, 0, 0};
+  std::vector<std::pair<int, std::pair<Event, Event>>> prof_events;
+};
+
+namespace {
+
+size_t slab_elems(const vmk_plan* p) { return (size_t)(p->NJ + 2) * p->N; }
+
+int dev_alloc(vmk_plan* p, void** ptr, size_t bytes) {
+  VMK_TRY(be_malloc(ptr, bytes));
+  p->dev_bytes += (int64_t)bytes;
+  return 0;
+}
+
+int ensure_staging(vmk_plan* p) {
+  if (p->staging) return 0;
+  return dev_alloc(p, (void**)&p->staging, sizeof(double) * (size_t)(p->NJ + 2) * (p->N + 2));
+}
+
+// bb*cos(kx[i]) and cc*cos(ky[j]) exactly as Common.jl:101-113,120 evaluates them (kx[1] = eps, ky = kx).
+// 2N cos() evaluations on the host per (dx,dy,eps); the 2 N^2 per call of the reference disappear.
+int ensure_divisor(vmk_plan* p, double dx, double dy, double eps) {
+  if (p->div_valid && p->div_dx == dx && p->div_dy == dy && p->div_eps == eps) return 0;
+  const int n = p->N;
+  std::vector<double> kx(n), b(n), c(n);
+  const double hx = 2.0 * M_PI / (double)n;  // Common.jl:106
+  for (int i = 1; i <= n / 2; i++) {         // :108-111
+    kx[i - 1] = hx * (double)(i - 1);
+    kx[i + n / 2 - 1] = hx * (double)(i - n / 2 - 1);
+  }
+  kx[0] = eps;  // :112
+  const double bb = 2.0 / (dx * dx), cc = 2.0 / (dy * dy);
+  for (int i = 0; i < n; i++) {
+    const double ck = cos(kx[i]);
+    b[i] = bb * ck;
+    c[i] = cc * ck;
+  }
+  VMK_TRY(be_sync(p->st));  // the tables may still be in use by queued kernels
+  VMK_TRY(be_h2d(p->bbcos, b.data(), sizeof(double) * n, p->st));
+  VMK_TRY(be_h2d(p->cccos, c.data(), sizeof(double) * n, p->st));
+  VMK_TRY(be_sync(p->st));
+  p->div_aa = -2.0 / (dx * dx) - 2.0 / (dy * dy);  // :101
+  p->div_dx = dx;
+  p->div_dy = dy;
+  p->div_eps = eps;
+  p->div_valid = true;
+#ifndef VMK_EMUL
+  for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
+  p->graphs.clear();
+#endif
+  return 0;
+}
+
+struct Timed {
+  vmk_plan* p;
+  int which;
+  Event a, b;
+  bool on;
+  Timed(vmk_plan* p_, int w) : p(p_), which(w), on(p_->profiling) {
+    if (on) {
+      be_event_create(a);
+      be_event_create(b);
+      be_event_record(a, p->st);
+    }
+  }
+  void done() {
+    if (on) {
+      be_event_record(b, p->st);
+      p->prof_events.push_back({which, {a, b}});
+    }
+  }
+};
+
+int cross_rank_barrier(vmk_plan* p) {
+  if (p->nranks == 1) return 0;
+  if (!p->barrier_fn) return fail(VMK_ESTATE, "slab plan has no barrier hook (vmk_barrier_hook)");
+  p->barrier_fn(p->barrier_user);
+  return 0;
+}
+
+int launch_k1(vmk_plan* p, const double* src) {
+  K1Args a;
+  a.w = src;
+  a.T = p->T;
+  a.tw = p->tw;
+  a.NJ = p->NJ;
+  a.npairs = p->NJ / 2;
+  const int work = (a.npairs + p->ops.fpc - 1) / p->ops.fpc;
+  Timed t(p, KI_K1);
+  VMK_TRY(p->ops.k1(work < p->res_k1 ? work : p->res_k1, a, p->st));
+  t.done();
+  p->launches++;
+  return 0;
+}
+
+int launch_k2(vmk_plan* p, double sign) {
+  K2Args a;
+  for (int r = 0; r < kMaxPeers; r++) a.T.p[r] = r < p->nranks ? (void*)p->peer_T[r] : nullptr;
+  a.tw = p->tw;
+  a.bbcos = p->bbcos;
+  a.cccos = p->cccos;
+  a.aa = p->div_aa;
+  a.scale = sign / (2.0 * (double)p->N * (double)p->N);
+  a.NJ = p->NJ;
+  a.log2NJ = p->log2NJ;
+  a.nrows = (p->N / 2) / p->nranks;
+  a.row0 = p->rank * a.nrows;
+  const int work = (a.nrows + p->ops.fpc - 1) / p->ops.fpc;
+  Timed t(p, KI_K2);
+  VMK_TRY(p->ops.k2(work < p->res_k2 ? work : p->res_k2, a, p->st));
+  t.done();
+  p->launches++;
+  return 0;
+}
+
+int launch_k3(vmk_plan* p) {
+  K3Args a;
+  a.T = p->T;
+  a.tw = p->tw;
+  a.psi = p->psi;
+  const int prev = (p->rank + p->nranks - 1) % p->nranks, next = (p->rank + 1) % p->nranks;
+  a.lo_dst = p->peer_psi[prev] + (size_t)(p->NJ + 1) * p->N;
+  a.hi_dst = p->peer_psi[next];
+  a.NJ = p->NJ;
+  a.npairs = p->NJ / 2;
+  const int work = (a.npairs + p->ops.fpc - 1) / p->ops.fpc;
+  Timed t(p, KI_K3);
+  VMK_TRY(p->ops.k3(work < p->res_k3 ? work : p->res_k3, a, p->st));
+  t.done();
+  p->launches++;
+  return 0;
+}
+
+// mode 0: out = r; 1..3: RK3 stages.  win/wn/out index p->w[]
+int launch_k4(vmk_plan* p, int mode, int win, int wn, int out, const StepParams& sp) {
+  K4Args a;
+  a.w = p->w[win];
+  a.psi = p->psi;
+  a.wn = p->w[wn];
+  a.out = p->w[out];
+  const int prev = (p->rank + p->nranks - 1) % p->nranks, next = (p->rank + 1) % p->nranks;
+  a.lo_dst = p->peer_w[out][prev] + (size_t)(p->NJ + 1) * p->N;
+  a.hi_dst = p->peer_w[out][next];
+  a.N = p->N;
+  a.log2N = p->M;
+  a.NJ = p->NJ;
+  a.rows_per_cta = p->k4_rows;
+  a.aa = 1.0 / (sp.re * (sp.dx * sp.dx));  // Common.jl:149
+  a.bb = 1.0 / (sp.re * (sp.dy * sp.dy));  // :150
+  a.gg = 1.0 / (4.0 * sp.dx * sp.dy);      // :151
+  a.hh = 1.0 / 3.0;                        // :152
+  a.dt = sp.dt;
+  const int cols = p->N / 2, tw = cols < kK4Threads ? cols : kK4Threads, groups = kK4Threads / tw;
+  const int ctas_x = cols / tw;
+  const int rows_per = groups * a.rows_per_cta;
+  const int grid = ctas_x * ((p->NJ + rows_per - 1) / rows_per);
+  Timed t(p, KI_K4);
+  int rc = 0;
+  switch (mode) {
+    case 0: rc = be_launch<K4Body<0>, K4Args, kK4Threads, 4>(grid, 0, a, p->st); break;
+    case 1: rc = be_launch<K4Body<1>, K4Args, kK4Threads, 4>(grid, 0, a, p->st); break;
+    case 2: rc = be_launch<K4Body<2>, K4Args, kK4Threads, 4>(grid, 0, a, p->st); break;
+    default: rc = be_launch<K4Body<3>, K4Args, kK4Threads, 4>(grid, 0, a, p->st); break;
+  }
+  VMK_TRY(rc);
+  t.done();
+  p->launches++;
+  return 0;
+}
+
+template <class Body>
+int launch_k5(vmk_plan* p, const double* src, double* dst, size_t total) {
+  K5Args a;
+  a.src = src;
+  a.dst = dst;
+  a.N = p->N;
+  a.NJ = p->NJ;
+  size_t want = (total + kK5Threads - 1) / kK5Threads;
+  const size_t cap = (size_t)p->sms * 16;
+  const int grid = (int)(want < cap ? want : cap);
+  VMK_TRY((be_launch<Body, K5Args, kK5Threads, 4>(grid < 1 ? 1 : grid, 0, a, p->st)));
+  p->launches++;
+  return 0;
+}
+
+// psi = solve(sign * src): K1 -> K2 -> K3.  Common.jl:115-123
+int enqueue_poisson(vmk_plan* p, const double* src, double sign) {
+  VMK_TRY(launch_k1(p, src));
+  VMK_TRY(cross_rank_barrier(p));  // every rank's spectrum is written before any rank transforms along j
+  VMK_TRY(launch_k2(p, sign));
+  VMK_TRY(cross_rank_barrier(p));  // ... and transformed back before the owners read it
+  VMK_TRY(launch_k3(p));
+  return 0;
+}
+
+// One SSP-RK3 step, vm.jl:26-76.  Ping-pong: S1 wn -> wtA; S2 (wn, wtA) -> wtB; S3 (wn, wtB) -> wn
+// (in place is safe in S3: wn is only read point-wise there).
+int enqueue_step(vmk_plan* p, const StepParams& sp) {
+  VMK_TRY(enqueue_poisson(p, p->w[0], -1.0));
+  VMK_TRY(cross_rank_barrier(p));  // neighbours' psi halo rows have landed
+  VMK_TRY(launch_k4(p, 1, 0, 0, 1, sp));
+  VMK_TRY(enqueue_poisson(p, p->w[1], -1.0));
+  VMK_TRY(cross_rank_barrier(p));
+  VMK_TRY(launch_k4(p, 2, 1, 0, 2, sp));
+  VMK_TRY(enqueue_poisson(p, p->w[2], -1.0));
+  VMK_TRY(cross_rank_barrier(p));
+  VMK_TRY(launch_k4(p, 3, 2, 0, 0, sp));
+  return 0;
+}
+
+int check_plan(vmk_plan* p) {
+  if (!p) return fail(VMK_EARG, "plan is NULL");
+  if (p->nranks > 1 && !p->peers_ready) return fail(VMK_ESTATE, "slab plan: peers not attached yet");
+  return 0;
+}
+
+// host ghosted array -> slab (rows j0..j0+NJ-1 plus periodic halo rows, read from the interior)
+int upload_ghosted(vmk_plan* p, const double* host, double* slab) {
+  VMK_TRY(ensure_staging(p));
+  const size_t ld = (size_t)p->N + 2;
+  const int N = p->N, NJ = p->NJ;
+  VMK_TRY(be_h2d(p->staging + ld, host + ld * (size_t)(p->j0 + 1), sizeof(double) * ld * NJ, p->st));
+  const int jlo = (p->j0 + N - 1) % N, jhi = (p->j0 + NJ) % N;  // interior rows that wrap into the halos
+  VMK_TRY(be_h2d(p->staging, host + ld * (size_t)(jlo + 1), sizeof(double) * ld, p->st));
+  VMK_TRY(be_h2d(p->staging + ld * (size_t)(NJ + 1), host + ld * (size_t)(jhi + 1), sizeof(double) * ld, p->st));
+  VMK_TRY(launch_k5<K5Unpack>(p, p->staging, slab, slab_elems(p)));
+  return 0;
+}
+
+// slab -> host ghosted rows j0 .. j0+NJ+1 (all of the array on a single GPU), i-ghosts included
+int download_ghosted(vmk_plan* p, const double* slab, double* host) {
+  VMK_TRY(ensure_staging(p));
+  const size_t ld = (size_t)p->N + 2;
+  VMK_TRY(launch_k5<K5Pack>(p, slab, p->staging, (size_t)(p->NJ + 2) * ld));
+  VMK_TRY(be_d2h(host + ld * (size_t)p->j0, p->staging, sizeof(double) * ld * (p->NJ + 2), p->st));
+  return 0;
+}
+
+// slab interior -> interior of a host ghosted array (ghost cells untouched)
+int download_interior(vmk_plan* p, const double* slab, double* host) {
+  const size_t ld = (size_t)p->N + 2;
+  return be_d2h_2d(host + ld * (size_t)(p->j0 + 1) + 1, sizeof(double) * ld, slab + p->N, sizeof(double) * p->N,
+                   sizeof(double) * p->N, (size_t)p->NJ, p->st);
+}
+
+int collect_profile(vmk_plan* p) {
+  VMK_TRY(be_sync(p->st));
+  for (auto& e : p->prof_events) {
+    double ms = 0;
+    VMK_TRY(be_event_elapsed(e.second.first, e.second.second, &ms));
+    p->prof_ms[e.first] += ms;
+    p->prof_n[e.first]++;
+    be_event_destroy(e.second.first);
+    be_event_destroy(e.second.second);
+  }
+  p->prof_events.clear();
+  return 0;
+}
+
+}  // namespace
+
+// ============================================ C ABI =================================================
+extern "C" {
+
+int vmk_version(void) { return 100; }
+
+const char* vmk_last_error(void) { return err_slot().c_str(); }
+
+int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan** out) {
+  if (!out) return fail(VMK_EARG, "plan output pointer is NULL");
+  *out = nullptr;
+  if (nx != ny) return fail(VMK_ESIZE, "nx != ny: the reference aliases ky = kx (Common.jl:113)");
+  const int M = ilog2_exact(nx);
+  SizeOps ops;
+  if (M < 0 || !ops_for(M, &ops))
+    return fail(VMK_ESIZE, "grid size must be a power of two in [32, 8192]");
+  if (nranks < 1 || nranks > kMaxPeers || rank < 0 || rank >= nranks || ilog2_exact(nranks) < 0)
+    return fail(VMK_EARG, "nranks must be 1, 2, 4 or 8 and 0 <= rank < nranks");
+  if ((nx / nranks) < 2 || ((nx / 2) % nranks) != 0)
+    return fail(VMK_ESIZE, "too many ranks for this grid");
+  vmk_plan* p = new vmk_plan();
+  p->N = (int)nx;
+  p->M = M;
+  p->rank = rank;
+  p->nranks = nranks;
+  p->NJ = (int)(nx / nranks);
+  p->log2NJ = ilog2_exact(p->NJ);
+  p->j0 = rank * p->NJ;
+  p->ops = ops;
+  int rc = 0;
+  do {
+    if ((rc = be_num_sms(&p->sms))) break;
+    if ((rc = be_stream_create(p->st))) break;
+    if ((rc = be_event_create(p->ev0)) || (rc = be_event_create(p->ev1))) break;
+    if ((rc = ops.configure(&p->res_k1, &p->res_k2, &p->res_k3))) break;
+    const size_t sb = sizeof(double) * slab_elems(p);
+    for (int b = 0; b < 3 && !rc; b++) rc = dev_alloc(p, (void**)&p->w[b], sb);
+    if (rc) break;
+    if ((rc = dev_alloc(p, (void**)&p->psi, sb))) break;
+    if ((rc = dev_alloc(p, (void**)&p->T, sizeof(double2) * (size_t)(p->N / 2) * p->NJ))) break;
+    if ((rc = dev_alloc(p, (void**)&p->tw, sizeof(double2) * (ops.twn ? ops.twn : 1)))) break;
+    if ((rc = dev_alloc(p, (void**)&p->bbcos, sizeof(double) * p->N))) break;
+    if ((rc = dev_alloc(p, (void**)&p->cccos, sizeof(double) * p->N))) break;
+    std::vector<double2> tw(ops.twn ? ops.twn : 1);
+    ops.fill_tw(tw.data());
+    if ((rc = be_h2d(p->tw, tw.data(), sizeof(double2) * tw.size(), p->st))) break;
+    if ((rc = be_sync(p->st))) break;
+  } while (0);
+  if (rc) {
+    vmk_plan_destroy(p);
+    return rc;
+  }
+  for (int r = 0; r < kMaxPeers; r++) {
+    for (int b = 0; b < 3; b++) p->peer_w[b][r] = nullptr;
+    p->peer_psi[r] = nullptr;
+    p->peer_T[r] = nullptr;
+  }
+  for (int b = 0; b < 3; b++) p->peer_w[b][rank] = p->w[b];
+  p->peer_psi[rank] = p->psi;
+  p->peer_T[rank] = p->T;
+  p->peers_ready = (nranks == 1);
+  *out = p;
+  return VMK_OK;
+}
+
+int vmk_plan_create(int64_t nx, int64_t ny, vmk_plan** out) { return vmk_plan_create_slab(nx, ny, 0, 1, out); }
+
+int vmk_plan_destroy(vmk_plan* p) {
+  if (!p) return VMK_OK;
+  if (be_stream_valid(p->st)) be_sync(p->st);
+#ifndef VMK_EMUL
+  for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
+  for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
+#endif
+  for (int b = 0; b < 3; b++) be_free(p->w[b]);
+  be_free(p->psi);
+  be_free(p->T);
+  be_free(p->tw);
+  be_free(p->bbcos);
+  be_free(p->cccos);
+  be_free(p->staging);
+  be_event_destroy(p->ev0);
+  be_event_destroy(p->ev1);
+  be_stream_destroy(p->st);
+  delete p;
+  return VMK_OK;
+}
+
+// ---- slab decomposition: peer buffer exchange ------------------------------------------------------
+// A blob carries the handles of one rank's five exchange buffers (w[0..2], psi, T).
+#ifndef VMK_EMUL
+struct PeerBlob {
+  cudaIpcMemHandle_t h[5];
+};
+#else
+struct PeerBlob {
+  void* h[5];
+};
+#endif
+
+size_t vmk_peer_blob_bytes(void) { return sizeof(PeerBlob); }
+
+int vmk_peer_export(vmk_plan* p, void* blob) {
+  if (!p || !blob) return fail(VMK_EARG, "NULL argument");
+  PeerBlob* b = static_cast<PeerBlob*>(blob);
+  void* ptrs[5] = {p->w[0], p->w[1], p->w[2], p->psi, p->T};
+  for (int i = 0; i < 5; i++) {
+#ifndef VMK_EMUL
+    VMK_CUDA_TRY(cudaIpcGetMemHandle(&b->h[i], ptrs[i]));
+#else
+    b->h[i] = ptrs[i];
+#endif
+  }
+  return VMK_OK;
+}
+
+// blobs: nranks blobs in rank order (own entry ignored): one process per GPU, handles via CUDA IPC
+int vmk_peer_import(vmk_plan* p, const void* blobs) {
+  if (!p || !blobs) return fail(VMK_EARG, "NULL argument");
+  const PeerBlob* b = static_cast<const PeerBlob*>(blobs);
+  for (int r = 0; r < p->nranks; r++) {
+    if (r == p->rank) continue;
+    void* ptrs[5];
+    for (int i = 0; i < 5; i++) {
+#ifndef VMK_EMUL
+      VMK_CUDA_TRY(cudaIpcOpenMemHandle(&ptrs[i], b[r].h[i], cudaIpcMemLazyEnablePeerAccess));
+      p->ipc_opened.push_back(ptrs[i]);
+#else
+      ptrs[i] = b[r].h[i];
+#endif
+    }
+    for (int q = 0; q < 3; q++) p->peer_w[q][r] = (double*)ptrs[q];
+    p->peer_psi[r] = (double*)ptrs[3];
+    p->peer_T[r] = (double2*)ptrs[4];
+  }
+  p->peers_ready = true;
+  return VMK_OK;
+}
+
+// all ranks live in this process (one host thread driving several devices, the Julia model):
+// plans[r] is rank r's plan; peer access must already be enabled between the devices
+int vmk_peer_attach_local(vmk_plan* p, vmk_plan* const* plans) {
+  if (!p || !plans) return fail(VMK_EARG, "NULL argument");
+  for (int r = 0; r < p->nranks; r++) {
+    if (!plans[r] || plans[r]->N != p->N || plans[r]->nranks != p->nranks || plans[r]->rank != r)
+      return fail(VMK_EARG, "plans[] does not hold one matching plan per rank");
+    for (int q = 0; q < 3; q++) p->peer_w[q][r] = plans[r]->w[q];
+    p->peer_psi[r] = plans[r]->psi;
+    p->peer_T[r] = plans[r]->T;
+  }
+  p->peers_ready = true;
+  return VMK_OK;
+}
+
+int vmk_barrier_hook(vmk_plan* p, void (*fn)(void*), void* user) {
+  if (!p) return fail(VMK_EARG, "plan is NULL");
+  p->barrier_fn = fn;
+  p->barrier_user = user;
+  return VMK_OK;
+}
+
+// ---- reference-signature entry points on host arrays -----------------------------------------------
+int vmk_fps(vmk_plan* p, double dx, double dy, const double* f, double* s, double eps) {
+  VMK_TRY(check_plan(p));
+  if (!f || !s) return fail(VMK_EARG, "f or s is NULL");
+  VMK_TRY(ensure_divisor(p, dx, dy, eps));
+  // wtA is scratch between steps; the source needs no halo rows
+  VMK_TRY(be_h2d(p->w[1] + p->N, f + (size_t)p->j0 * p->N, sizeof(double) * (size_t)p->N * p->NJ, p->st));
+  VMK_TRY(enqueue_poisson(p, p->w[1], +1.0));
+  VMK_TRY(download_interior(p, p->psi, s));
+  return be_sync(p->st);
+}
+
+int vmk_ps_fft(vmk_plan* p, double dx, double dy, const double* f, double* u, double eps) {
+  VMK_TRY(check_plan(p));
+  if (!f || !u) return fail(VMK_EARG, "f or u is NULL");
+  VMK_TRY(ensure_divisor(p, dx, dy, eps));
+  const size_t N = (size_t)p->N;
+  // f is (nx+1) x (ny+1); [1:nx, 1:ny] is read (fft_p.jl:23-27)
+  VMK_TRY(be_h2d_2d(p->w[1] + N, sizeof(double) * N, f + (size_t)p->j0 * (N + 1), sizeof(double) * (N + 1),
+                    sizeof(double) * N, (size_t)p->NJ, p->st));
+  VMK_TRY(enqueue_poisson(p, p->w[1], +1.0));
+  VMK_TRY(be_d2h(u + (size_t)p->j0 * N, p->psi + N, sizeof(double) * N * p->NJ, p->st));
+  return be_sync(p->st);
+}
+
+int vmk_rhs(vmk_plan* p, double dx, double dy, double re, const double* w, double* r, double* s, double* f) {
+  VMK_TRY(check_plan(p));
+  if (!w || !r || !s) return fail(VMK_EARG, "w, r or s is NULL");
+  VMK_TRY(ensure_divisor(p, dx, dy, 1.e-6));  // vm_rhs calls fps with the default eps (Common.jl:136)
+  VMK_TRY(upload_ghosted(p, w, p->w[1]));
+  if (f) {
+    // T is free until K1 runs: borrow it for f = -w (Common.jl:134)
+    double* fd = reinterpret_cast<double*>(p->T);
+    VMK_TRY(launch_k5<K5Negate>(p, p->w[1], fd, (size_t)p->NJ * p->N));
+    VMK_TRY(be_d2h(f + (size_t)p->j0 * p->N, fd, sizeof(double) * (size_t)p->N * p->NJ, p->st));
+  }
+  VMK_TRY(enqueue_poisson(p, p->w[1], -1.0));
+  VMK_TRY(cross_rank_barrier(p));
+  const StepParams sp{dx, dy, 0.0, re};
+  VMK_TRY(launch_k4(p, 0, 1, 1, 2, sp));
+  VMK_TRY(download_interior(p, p->w[2], r));
+  VMK_TRY(download_ghosted(p, p->psi, s));
+  return be_sync(p->st);
+}
+
+int vmk_upload(vmk_plan* p, const double* wn) {
+  VMK_TRY(check_plan(p));
+  if (!wn) return fail(VMK_EARG, "wn is NULL");
+  VMK_TRY(upload_ghosted(p, wn, p->w[0]));
+  VMK_TRY(be_sync(p->st));
+  p->uploaded = true;
+  return VMK_OK;
+}
+
+int vmk_step(vmk_plan* p, double dx, double dy, double dt, double re, int64_t nsteps) {
+  VMK_TRY(check_plan(p));
+  if (!p->uploaded) return fail(VMK_ESTATE, "vmk_step before vmk_upload");
+  if (nsteps < 0) return fail(VMK_EARG, "nsteps < 0");
+  VMK_TRY(ensure_divisor(p, dx, dy, 1.e-6));
+  const StepParams sp{dx, dy, dt, re};
+  VMK_TRY(be_event_record(p->ev0, p->st));
+#ifndef VMK_EMUL
+  if (p->use_graph && p->nranks == 1 && !p->profiling && nsteps > 0) {
+    auto it = p->graphs.find(sp);
+    if (it == p->graphs.end()) {
+      cudaGraph_t g = nullptr;
+      cudaGraphExec_t ge = nullptr;
+      VMK_CUDA_TRY(cudaStreamBeginCapture(p->st.s, cudaStreamCaptureModeThreadLocal));
+      const int64_t before = p->launches;
+      int rc = enqueue_step(p, sp);
+      p->launches = before;
+      cudaError_t e = cudaStreamEndCapture(p->st.s, &g);
+      if (rc) return rc;
+      VMK_CUDA_TRY(e);
+      VMK_CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      it = p->graphs.emplace(sp, ge).first;
+    }
+    for (int64_t k = 0; k < nsteps; k++) {
+      VMK_CUDA_TRY(cudaGraphLaunch(it->second, p->st.s));
+      p->launches += 12;
+    }
+    VMK_TRY(be_event_record(p->ev1, p->st));
+    p->ev_valid = true;
+    return VMK_OK;
+  }
+#endif
+  for (int64_t k = 0; k < nsteps; k++) VMK_TRY(enqueue_step(p, sp));
+  VMK_TRY(be_event_record(p->ev1, p->st));
+  p->ev_valid = true;
+  return VMK_OK;
+}
+
+int vmk_download(vmk_plan* p, double* wn, double* psi) {
+  VMK_TRY(check_plan(p));
+  if (!p->uploaded) return fail(VMK_ESTATE, "vmk_download before vmk_upload");
+  if (wn) VMK_TRY(download_ghosted(p, p->w[0], wn));
+  if (psi) VMK_TRY(download_ghosted(p, p->psi, psi));
+  return be_sync(p->st);
+}
+
+int vmk_sync(vmk_plan* p) {
+  VMK_TRY(check_plan(p));
+  return be_sync(p->st);
+}
+
+int vmk_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, double re, double* wn, double* out,
+                  int64_t freq, vmk_snapshot_fn snap, void* user) {
+  VMK_TRY(check_plan(p));
+  if (!wn) return fail(VMK_EARG, "wn is NULL");
+  if (nt < 0) return fail(VMK_EARG, "nt < 0");
+  VMK_TRY(vmk_upload(p, wn));
+  if (snap && freq > 0) {
+    for (int64_t k = 0; k < nt;) {
+      const int64_t chunk = (freq - (k % freq)) < (nt - k) ? (freq - (k % freq)) : (nt - k);
+      VMK_TRY(vmk_step(p, dx, dy, dt, re, chunk));
+      k += chunk;
+      if (k % freq == 0) {  // vm.jl:78
+        VMK_TRY(vmk_download(p, wn, nullptr));
+        snap(k, wn, user);
+      }
+    }
+  } else {
+    VMK_TRY(vmk_step(p, dx, dy, dt, re, nt));
+  }
+  VMK_TRY(vmk_download(p, wn, nullptr));
+  if (out) {
+    if (p->nranks != 1) return fail(VMK_EARG, "out is only produced by single-GPU plans");
+    // wn[2:nx+2, 2:ny+2] (vm.jl:89): a strided view of the array that was just downloaded
+    const size_t ld = (size_t)p->N + 2, n1 = (size_t)p->N + 1;
+    for (size_t j = 0; j < n1; j++) memcpy(out + j * n1, wn + (j + 1) * ld + 1, sizeof(double) * n1);
+  }
+  return VMK_OK;
+}
+
+// ---- measurement -----------------------------------------------------------------------------------
+void* vmk_stream(vmk_plan* p) {
+#ifndef VMK_EMUL
+  return p ? (void*)p->st.s : nullptr;
+#else
+  (void)p;
+  return nullptr;
+#endif
+}
+
+int vmk_step_elapsed_ms(vmk_plan* p, double* ms) {
+  VMK_TRY(check_plan(p));
+  if (!ms) return fail(VMK_EARG, "ms is NULL");
+  if (!p->ev_valid) return fail(VMK_ESTATE, "no vmk_step call to time");
+  return be_event_elapsed(p->ev0, p->ev1, ms);
+}
+
+int vmk_profile_steps(vmk_plan* p, double dx, double dy, double dt, double re, int64_t nsteps, double* ms,
+                      int64_t* launches) {
+  VMK_TRY(check_plan(p));
+  if (!p->uploaded) return fail(VMK_ESTATE, "vmk_profile_steps before vmk_upload");
+  for (int k = 0; k < KI_COUNT; k++) {
+    p->prof_ms[k] = 0;
+    p->prof_n[k] = 0;
+  }
+  p->profiling = true;
+  int rc = vmk_step(p, dx, dy, dt, re, nsteps);
+  if (!rc) rc = collect_profile(p);
+  p->profiling = false;
+  VMK_TRY(rc);
+  for (int k = 0; k < KI_COUNT; k++) {
+    if (ms) ms[k] = p->prof_ms[k];
+    if (launches) launches[k] = p->prof_n[k];
+  }
+  return VMK_OK;
+}
+
+int64_t vmk_launch_count(vmk_plan* p) { return p ? p->launches : 0; }
+
+int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
+  if (!p || !key) return fail(VMK_EARG, "NULL argument");
+  const std::string k(key);
+  if (k == "graph") {
+    p->use_graph = value != 0;
+  } else if (k == "k4_rows") {
+    if (value < 1 || value > 8192) return fail(VMK_EARG, "k4_rows out of range");
+    p->k4_rows = (int)value;
+#ifndef VMK_EMUL
+    for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
+    p->graphs.clear();
+#endif
+  } else {
+    return fail(VMK_EARG, "unknown option: " + k);
+  }
+  return VMK_OK;
+}
+
+int64_t vmk_device_bytes(vmk_plan* p) { return p ? p->dev_bytes : 0; }
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// vmk_backend.cuh -- where kernel bodies execute.
+//
+// Product build (default): CUDA.  Every body becomes a __global__ kernel, memory is device memory,
+// errors are CUDA errors.  There is no CPU fallback in this build.
+//
+// -DVMK_EMUL (tests/emul only, builds libvmk_emul.so with vmke_* symbols): the same bodies and the same
+// plan logic run on the host with one pthread per CUDA thread, so the index math can be tested in CI
+// without a GPU.  Test infrastructure; never loaded by the package.
+#pragma once
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "vmk_common.cuh"
+
+namespace vmk {
+
+inline std::string& err_slot() {
+  static thread_local std::string e;
+  return e;
+}
+inline int fail(int code, const std::string& msg) {
+  err_slot() = msg;
+  return code;
+}
+
+#ifndef VMK_EMUL
+// ================================ CUDA backend =====================================================
+#define VMK_CUDA_TRY(expr)                                                                     \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return ::vmk::fail(2, std::string(#expr) + ": " + cudaGetErrorName(e__) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct Stream {
+  cudaStream_t s = nullptr;
+};
+struct Event {
+  cudaEvent_t e = nullptr;
+};
+
+template <class Body, class Args, int CT, int MINB>
+__global__ void __launch_bounds__(CT, MINB) body_kernel(const __grid_constant__ Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx c;
+  c.tid = (int)threadIdx.x;
+  c.bid = (int)blockIdx.x;
+  c.nblk = (int)gridDim.x;
+  c.smem = smem_raw;
+  c.hbar = nullptr;
+  Body::run(c, a);
+}
+
+inline int be_malloc(void** p, size_t bytes) {
+  VMK_CUDA_TRY(cudaMalloc(p, bytes));
+  return 0;
+}
+inline void be_free(void* p) {
+  if (p) cudaFree(p);
+}
+inline int be_stream_create(Stream& s) {
+  VMK_CUDA_TRY(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
+  return 0;
+}
+inline void be_stream_destroy(Stream& s) {
+  if (s.s) cudaStreamDestroy(s.s);
+  s.s = nullptr;
+}
+inline bool be_stream_valid(const Stream& s) { return s.s != nullptr; }
+inline int be_event_create(Event& e) {
+  VMK_CUDA_TRY(cudaEventCreate(&e.e));
+  return 0;
+}
+inline void be_event_destroy(Event& e) {
+  if (e.e) cudaEventDestroy(e.e);
+  e.e = nullptr;
+}
+inline int be_event_record(Event& e, Stream& s) {
+  VMK_CUDA_TRY(cudaEventRecord(e.e, s.s));
+  return 0;
+}
+inline int be_event_elapsed(Event& a, Event& b, double* ms) {
+  VMK_CUDA_TRY(cudaEventSynchronize(b.e));
+  float f = 0.f;
+  VMK_CUDA_TRY(cudaEventElapsedTime(&f, a.e, b.e));
+  *ms = (double)f;
+  return 0;
+}
+inline int be_sync(Stream& s) {
+  VMK_CUDA_TRY(cudaStreamSynchronize(s.s));
+  return 0;
+}
+inline int be_h2d(void* dst, const void* src, size_t bytes, Stream& s) {
+  VMK_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.s));
+  return 0;
+}
+inline int be_d2h(void* dst, const void* src, size_t bytes, Stream& s) {
+  VMK_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s.s));
+  return 0;
+}
+inline int be_d2d(void* dst, const void* src, size_t bytes, Stream& s) {
+  VMK_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s.s));
+  return 0;
+}
+inline int be_h2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, Stream& s) {
+  VMK_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, s.s));
+  return 0;
+}
+inline int be_d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, Stream& s) {
+  VMK_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, s.s));
+  return 0;
+}
+inline int be_num_sms(int* n) {
+  int dev = 0;
+  VMK_CUDA_TRY(cudaGetDevice(&dev));
+  VMK_CUDA_TRY(cudaDeviceGetAttribute(n, cudaDevAttrMultiProcessorCount, dev));
+  return 0;
+}
+
+// occupancy query + shared-memory opt-in for one kernel on the CURRENT device; resident = SMs x CTAs/SM
+template <class Body, class Args, int CT, int MINB>
+inline int be_configure(size_t smem, int* resident) {
+  auto kfn = body_kernel<Body, Args, CT, MINB>;
+  if (smem > 48 * 1024)
+    VMK_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0, sms = 0;
+  VMK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, CT, smem));
+  if (be_num_sms(&sms)) return 2;
+  if (occ < 1) return fail(2, "kernel does not fit on an SM (shared memory / registers)");
+  *resident = occ * sms;
+  return 0;
+}
+
+template <class Body, class Args, int CT, int MINB>
+inline int be_launch(int grid, size_t smem, const Args& a, Stream& s) {
+  body_kernel<Body, Args, CT, MINB><<<grid, CT, smem, s.s>>>(a);
+  VMK_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+#else
+// ================================ host emulation backend (tests only) ================================
+struct Stream {
+  int dummy = 0;
+};
+struct Event {
+  double t = 0;
+};
+inline int be_malloc(void** p, size_t bytes) {
+  *p = aligned_alloc(256, (bytes + 255) / 256 * 256);
+  if (!*p) return fail(2, "emul: out of memory");
+  memset(*p, 0xff, bytes);  // NaN-fill so reads of never-written memory show up
+  return 0;
+}
+inline void be_free(void* p) { free(p); }
+inline int be_stream_create(Stream&) { return 0; }
+inline void be_stream_destroy(Stream&) {}
+inline bool be_stream_valid(const Stream&) { return true; }
+inline int be_event_create(Event&) { return 0; }
+inline void be_event_destroy(Event&) {}
+double emul_now_ms();
+inline int be_event_record(Event& e, Stream&) {
+  e.t = emul_now_ms();
+  return 0;
+}
+inline int be_event_elapsed(Event& a, Event& b, double* ms) {
+  *ms = b.t - a.t;
+  return 0;
+}
+inline int be_sync(Stream&) { return 0; }
+inline int be_h2d(void* dst, const void* src, size_t bytes, Stream&) {
+  memcpy(dst, src, bytes);
+  return 0;
+}
+inline int be_d2h(void* dst, const void* src, size_t bytes, Stream&) {
+  memcpy(dst, src, bytes);
+  return 0;
+}
+inline int be_d2d(void* dst, const void* src, size_t bytes, Stream&) {
+  memmove(dst, src, bytes);
+  return 0;
+}
+inline int be_h2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, Stream&) {
+  for (size_t r = 0; r < height; r++) memcpy((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+  return 0;
+}
+inline int be_d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, Stream& s) {
+  return be_h2d_2d(dst, dpitch, src, spitch, width, height, s);
+}
+inline int be_num_sms(int* n) {
+  *n = 4;  // a small "GPU" so that the persistent loops are exercised
+  return 0;
+}
+typedef void (*emul_body_fn)(const Ctx&, const void*);
+int emul_run(int grid, int block, size_t smem, emul_body_fn fn, const void* args);
+
+template <class Body, class Args, int CT, int MINB>
+inline int be_configure(size_t, int* resident) {
+  int sms = 0;
+  be_num_sms(&sms);
+  *resident = sms * MINB;
+  return 0;
+}
+template <class Body, class Args, int CT, int MINB>
+inline int be_launch(int grid, size_t smem, const Args& a, Stream&) {
+  return emul_run(
+      grid, CT, smem, [](const Ctx& c, const void* p) { Body::run(c, *static_cast<const Args*>(p)); }, &a);
+}
+#endif
+
+}  // namespace vmk

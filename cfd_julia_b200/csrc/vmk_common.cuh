@@ -1,0 +1,145 @@
+// vmk_common.cuh -- shared helpers for the vmk kernels.
+//
+// Every kernel body in this directory is written as  body(const Ctx&, Args)  and is
+// __host__ __device__: the same source runs as a CUDA kernel (product) and, for CI on machines
+// without a GPU, as pthreads on the CPU (tests/emul, test infrastructure only -- the product
+// library never executes kernel bodies on the host).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#define VMK_HD __host__ __device__ __forceinline__
+
+namespace vmk {
+
+#ifndef __CUDA_ARCH__
+extern "C" void vmk_host_barrier_wait(void* bar);  // defined in the emulator only
+#endif
+
+struct Ctx {
+  int tid;              // thread index in the CTA
+  int bid;              // CTA index
+  int nblk;             // number of CTAs in the grid
+  unsigned char* smem;  // dynamic shared memory base (16-byte aligned)
+  void* hbar;           // host emulation barrier (unused on device)
+  VMK_HD void sync() const {
+#ifdef __CUDA_ARCH__
+    __syncthreads();
+#else
+    vmk_host_barrier_wait(hbar);
+#endif
+  }
+};
+
+// ---- compile-time loop ---------------------------------------------------------------------
+template <int I, int N, class F>
+VMK_HD void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// ---- complex arithmetic on double2 ---------------------------------------------------------
+VMK_HD double2 mk2(double x, double y) {
+  double2 r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+VMK_HD double2 cadd(double2 a, double2 b) { return mk2(a.x + b.x, a.y + b.y); }
+VMK_HD double2 csub(double2 a, double2 b) { return mk2(a.x - b.x, a.y - b.y); }
+VMK_HD double2 cmul(double2 a, double2 b) { return mk2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+VMK_HD double2 cmulc(double2 a, double2 b) {  // a * conj(b)
+  return mk2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+VMK_HD double2 cconj(double2 a) { return mk2(a.x, -a.y); }
+VMK_HD double2 cscale(double2 a, double s) { return mk2(a.x * s, a.y * s); }
+
+// ---- global memory access with cache hints -------------------------------------------------
+// Streaming data is touched once per kernel: keep it out of L1 (it is staged in registers /
+// shared memory by the kernels themselves).
+VMK_HD double2 ld_stream2(const double2* p) {
+#ifdef __CUDA_ARCH__
+  double2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+VMK_HD double ld_stream1(const double* p) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+VMK_HD void st_stream2(double2* p, double2 v) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+#else
+  *p = v;
+#endif
+}
+VMK_HD void st_stream1(double* p, double v) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+#else
+  *p = v;
+#endif
+}
+// one 32-byte store (two adjacent complex values); p must be 32-byte aligned.
+// sm_100 has 256-bit global stores (st.global.v4.f64).
+VMK_HD void st_stream4(double2* p, double2 a, double2 b) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x),
+               "d"(b.y)
+               : "memory");
+#else
+  p[0] = a;
+  p[1] = b;
+#endif
+}
+VMK_HD void ld_stream4(const double2* p, double2& a, double2& b) {
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y)
+               : "l"(p));
+#else
+  a = p[0];
+  b = p[1];
+#endif
+}
+VMK_HD double ld_ro(const double* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+VMK_HD void prefetch_l2(const void* p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+VMK_HD double rcp_rn(double d) {
+#ifdef __CUDA_ARCH__
+  return __drcp_rn(d);
+#else
+  return 1.0 / d;
+#endif
+}
+
+constexpr int kMaxPeers = 8;
+struct PeerPtrs {
+  void* p[kMaxPeers];
+};
+
+}  // namespace vmk

@@ -1,0 +1,288 @@
+// vmk_fft.cuh -- CTA-level power-of-two complex FP64 FFT, data in registers, exchanged through
+// padded shared memory.  Replaces the reference's FFTW calls (Common.jl:117 fft, :123 ifft).
+//
+// Scheme (derivation and numpy spec: tools/fft_proto.py):
+//   * N = 2^M points, E = 2^LE values per thread, T = N/E threads per transform.
+//   * forward = in-place mixed-radix DIF: pass k does radix-2^b_k butterflies on position bits
+//     [lo_k, hi_k) entirely in registers, multiplies by W_{2^hi_k}^{low*p}, and the values go back
+//     to the SAME positions.  Natural order in, digit-reversed ("position") order out.
+//   * inverse = the adjoint DIT (conjugate twiddle first, then the conjugate butterfly), passes in
+//     reverse order: position order in, natural order out, unnormalised.
+//   * the spectral side never needs natural order: the divide, the real-pair unpack and the
+//     transposed store are all index-agnostic, so no reordering pass exists anywhere.
+//   * shared memory address of position pos is pos + (pos >> b_last): conflict-free 128-bit
+//     accesses for every pass (checked with the bank model in tools/fft_proto.py).
+#pragma once
+#include "vmk_common.cuh"
+
+namespace vmk {
+
+// cos(pi*j/16), j = 0..8, correctly rounded (mpmath)
+VMK_HD constexpr double cos16th(int j) {
+  return j == 0   ? 1.0
+         : j == 1 ? 0.9807852804032304
+         : j == 2 ? 0.9238795325112867
+         : j == 3 ? 0.8314696123025452
+         : j == 4 ? 0.7071067811865476
+         : j == 5 ? 0.5555702330196022
+         : j == 6 ? 0.3826834323650898
+         : j == 7 ? 0.19509032201612828
+                  : 0.0;
+}
+// cos / sin of 2*pi*j/32 for j in [0,16]
+VMK_HD constexpr double cos32(int j) { return j <= 8 ? cos16th(j) : -cos16th(16 - j); }
+VMK_HD constexpr double sin32(int j) { return j <= 8 ? cos16th(8 - j) : cos16th(j - 8); }
+
+VMK_HD constexpr int brev(int x, int bits) {
+  int r = 0;
+  for (int b = 0; b < bits; b++)
+    if (x & (1 << b)) r |= 1 << (bits - 1 - b);
+  return r;
+}
+VMK_HD constexpr int ilog2c(int n) {
+  int m = 0;
+  while ((1 << m) < n) m++;
+  return m;
+}
+
+// d * W_R^I  (SIGN=-1: W = exp(-2 pi i/R), SIGN=+1: its conjugate), I in [0, R/2)
+template <int R, int I, int SIGN>
+VMK_HD double2 mul_const(double2 d) {
+  if constexpr (I == 0) {
+    return d;
+  } else if constexpr (4 * I == R) {
+    return SIGN < 0 ? mk2(d.y, -d.x) : mk2(-d.y, d.x);
+  } else {
+    constexpr int j = I * (32 / R);
+    constexpr double c = cos32(j), s = sin32(j);
+    if constexpr (SIGN < 0)
+      return mk2(d.x * c + d.y * s, d.y * c - d.x * s);
+    else
+      return mk2(d.x * c - d.y * s, d.y * c + d.x * s);
+  }
+}
+
+// radix-R DIF network on a[OFF .. OFF+R): natural order in, bit-reversed order out.
+template <int R, int SIGN, int OFF>
+struct Net {
+  template <class A>
+  VMK_HD static void run(A& a) {
+    constexpr int H = R / 2;
+    static_for<0, H>([&](auto i_) {
+      constexpr int i = decltype(i_)::value;
+      const double2 x = a[OFF + i], y = a[OFF + i + H];
+      a[OFF + i] = cadd(x, y);
+      a[OFF + i + H] = mul_const<R, i, SIGN>(csub(x, y));
+    });
+    Net<H, SIGN, OFF>::run(a);
+    Net<H, SIGN, OFF + H>::run(a);
+  }
+};
+template <int SIGN, int OFF>
+struct Net<1, SIGN, OFF> {
+  template <class A>
+  VMK_HD static void run(A&) {}
+};
+
+// ---- configuration ---------------------------------------------------------------------------
+template <int M_, int LE_, int P_, int B0_, int B1_, int B2_, int CT_, int MINB_>
+struct FftCfg {
+  static constexpr int M = M_, N = 1 << M_, LE = LE_, E = 1 << LE_, T = N >> LE_, P = P_;
+  static constexpr int CT = CT_ > T ? CT_ : T;  // CTA threads
+  static constexpr int FPC = CT / T;            // transforms per CTA
+  static constexpr int MINB = MINB_;            // min CTAs per SM (launch bounds)
+  VMK_HD static constexpr int bits(int k) { return k == 0 ? B0_ : (k == 1 ? B1_ : B2_); }
+  VMK_HD static constexpr int hi(int k) {
+    int h = M_;
+    for (int m = 0; m < k; m++) h -= bits(m);
+    return h;
+  }
+  VMK_HD static constexpr int lo(int k) { return hi(k) - bits(k); }
+  static constexpr int PADSH = bits(P_ - 1);
+  static constexpr int SMN = N + (N >> PADSH);  // padded complex slots per transform
+  // twiddle tables: pass k < P-1 uses W_{Bk}^x, Bk = 2^hi(k); full wave if small, else half wave
+  VMK_HD static constexpr bool tw_full(int k) { return (1 << hi(k)) <= 1024; }
+  VMK_HD static constexpr int tw_len(int k) { return k >= P_ - 1 ? 0 : (tw_full(k) ? (1 << hi(k)) : (1 << (hi(k) - 1))); }
+  VMK_HD static constexpr int tw_off(int k) {
+    int o = 0;
+    for (int m = 0; m < k; m++) o += tw_len(m);
+    return o;
+  }
+  static constexpr int TWN = tw_off(P_);  // total table entries (complex)
+  static constexpr size_t SMEM_DATA = sizeof(double2) * (size_t)SMN * FPC;
+  static constexpr size_t SMEM_BYTES = SMEM_DATA + sizeof(double2) * (size_t)TWN;
+  static_assert(B0_ + B1_ + (P_ > 2 ? B2_ : 0) == M_, "pass bits must sum to M");
+  static_assert(B0_ <= LE_ && B1_ <= LE_ && B2_ <= LE_, "radix exceeds per-thread elements");
+};
+
+// one configuration per supported size (32 .. 8192); radices grow towards the last
+// (twiddle-free) pass.  M=13 keeps 32 values per thread so a row needs only 2 exchanges.
+template <int M>
+struct CfgFor;
+template <> struct CfgFor<5>  { using type = FftCfg<5, 4, 2, 2, 3, 0, 128, 4>; };
+template <> struct CfgFor<6>  { using type = FftCfg<6, 4, 2, 3, 3, 0, 128, 4>; };
+template <> struct CfgFor<7>  { using type = FftCfg<7, 4, 2, 3, 4, 0, 128, 4>; };
+template <> struct CfgFor<8>  { using type = FftCfg<8, 4, 2, 4, 4, 0, 128, 4>; };
+template <> struct CfgFor<9>  { using type = FftCfg<9, 4, 3, 3, 3, 3, 128, 4>; };
+template <> struct CfgFor<10> { using type = FftCfg<10, 4, 3, 3, 3, 4, 128, 4>; };
+template <> struct CfgFor<11> { using type = FftCfg<11, 4, 3, 3, 4, 4, 128, 3>; };
+template <> struct CfgFor<12> { using type = FftCfg<12, 4, 3, 4, 4, 4, 256, 2>; };
+template <> struct CfgFor<13> { using type = FftCfg<13, 5, 3, 4, 4, 5, 256, 1>; };
+
+// ---- the engine --------------------------------------------------------------------------------
+template <class C>
+struct Fft {
+  static constexpr int E = C::E, T = C::T, P = C::P, M = C::M, N = C::N;
+
+  VMK_HD static int addr(int pos) { return pos + (pos >> C::PADSH); }
+
+  // position of element q of butterfly u of thread t in pass K
+  template <int K>
+  VMK_HD static int base_pos(int t, int u, int& low) {
+    constexpr int l = C::lo(K), h = C::hi(K);
+    const int id = t + T * u;
+    low = id & ((1 << l) - 1);
+    return ((id >> l) << h) | low;
+  }
+
+  template <int K>
+  VMK_HD static void load_smem(double2 (&v)[E], const double2* sm, int t) {
+    constexpr int b = C::bits(K), r = 1 << b, l = C::lo(K);
+    static_for<0, E / r>([&](auto u_) {
+      constexpr int u = decltype(u_)::value;
+      int low;
+      const int bp = base_pos<K>(t, u, low);
+      static_for<0, r>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        v[u * r + q] = sm[addr(bp | (q << l))];
+      });
+    });
+  }
+  template <int K>
+  VMK_HD static void store_smem(const double2 (&v)[E], double2* sm, int t) {
+    constexpr int b = C::bits(K), r = 1 << b, l = C::lo(K);
+    static_for<0, E / r>([&](auto u_) {
+      constexpr int u = decltype(u_)::value;
+      int low;
+      const int bp = base_pos<K>(t, u, low);
+      static_for<0, r>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        sm[addr(bp | (q << l))] = v[u * r + q];
+      });
+    });
+  }
+
+  // W_{2^hi(K)}^x, x < 2^hi(K); tw points at the start of all tables
+  template <int K>
+  VMK_HD static double2 twiddle(const double2* tw, int x) {
+    const double2* tk = tw + C::tw_off(K);
+    if constexpr (C::tw_full(K)) {
+      return tk[x];
+    } else {
+      constexpr int half = 1 << (C::hi(K) - 1);
+      double2 w = tk[x & (half - 1)];
+      if (x & half) {
+        w.x = -w.x;
+        w.y = -w.y;
+      }
+      return w;
+    }
+  }
+
+  // forward pass K on registers: radix network, then twiddle.  v[u*r+p] <- y[p].
+  template <int K>
+  VMK_HD static void fwd_compute(double2 (&v)[E], const double2* tw, int t) {
+    constexpr int b = C::bits(K), r = 1 << b;
+    static_for<0, E / r>([&](auto u_) {
+      constexpr int u = decltype(u_)::value;
+      double2 a[r];
+      static_for<0, r>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        a[q] = v[u * r + q];
+      });
+      Net<r, -1, 0>::run(a);
+      int low;
+      (void)base_pos<K>(t, u, low);
+      static_for<0, r>([&](auto p_) {
+        constexpr int p = decltype(p_)::value;
+        double2 y = a[brev(p, b)];
+        if constexpr (K < P - 1 && p > 0) y = cmul(y, twiddle<K>(tw, low * p));
+        v[u * r + p] = y;
+      });
+    });
+  }
+  // inverse pass K: conjugate twiddle, then conjugate network.  v[u*r+q] <- x[q].
+  template <int K>
+  VMK_HD static void inv_compute(double2 (&v)[E], const double2* tw, int t) {
+    constexpr int b = C::bits(K), r = 1 << b;
+    static_for<0, E / r>([&](auto u_) {
+      constexpr int u = decltype(u_)::value;
+      double2 a[r];
+      int low;
+      (void)base_pos<K>(t, u, low);
+      static_for<0, r>([&](auto p_) {
+        constexpr int p = decltype(p_)::value;
+        double2 y = v[u * r + p];
+        if constexpr (K < P - 1 && p > 0) y = cmulc(y, twiddle<K>(tw, low * p));
+        a[p] = y;
+      });
+      Net<r, +1, 0>::run(a);
+      static_for<0, r>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        v[u * r + q] = a[brev(q, b)];
+      });
+    });
+  }
+
+  // registers hold pass-0 layout (natural positions) on entry, last-pass layout on exit
+  VMK_HD static void forward(const Ctx& c, double2 (&v)[E], double2* sm, const double2* tw, int t) {
+    static_for<0, P>([&](auto k_) {
+      constexpr int K = decltype(k_)::value;
+      fwd_compute<K>(v, tw, t);
+      if constexpr (K < P - 1) {
+        store_smem<K>(v, sm, t);
+        c.sync();
+        load_smem<K + 1>(v, sm, t);
+      }
+    });
+  }
+  // registers hold last-pass layout on entry, pass-0 layout (natural positions) on exit
+  VMK_HD static void inverse(const Ctx& c, double2 (&v)[E], double2* sm, const double2* tw, int t) {
+    static_for<0, P>([&](auto k_) {
+      constexpr int K = P - 1 - decltype(k_)::value;
+      inv_compute<K>(v, tw, t);
+      if constexpr (K > 0) {
+        store_smem<K>(v, sm, t);
+        c.sync();
+        load_smem<K - 1>(v, sm, t);
+      }
+    });
+  }
+
+  // spectral index held at position pos after forward(), and its inverse map
+  VMK_HD static int k_of_pos(int pos) {
+    int k = 0;
+    static_for<0, P>([&](auto k_) {
+      constexpr int K = decltype(k_)::value;
+      constexpr int sh = M - C::hi(K);  // sum of bits of earlier passes
+      k |= ((pos >> C::lo(K)) & ((1 << C::bits(K)) - 1)) << sh;
+    });
+    return k;
+  }
+  VMK_HD static int pos_of_k(int k) {
+    int pos = 0;
+    static_for<0, P>([&](auto k_) {
+      constexpr int K = decltype(k_)::value;
+      constexpr int sh = M - C::hi(K);
+      pos |= ((k >> sh) & ((1 << C::bits(K)) - 1)) << C::lo(K);
+    });
+    return pos;
+  }
+
+  // cooperative copy of the twiddle tables into shared memory (all CT threads)
+  VMK_HD static void load_tables(const Ctx& c, double2* tw_sm, const double2* tw_g) {
+    for (int i = c.tid; i < C::TWN; i += C::CT) tw_sm[i] = tw_g[i];
+  }
+};
+
+}  // namespace vmk

@@ -1,0 +1,115 @@
+/*
+ * vmk.h -- C ABI of libvmk.so, the B200 (sm_100a) implementation of the CFD_Julia vortex-merger step.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The reference is a set of
+ * Julia scripts with no FFI of its own; the entry points below are what a `ccall` wrapper keeping the
+ * reference's Julia signatures binds (julia/CommonB200.jl).  File:line citations are
+ * relative to the reference checkout (t-bltg/CFD_Julia).
+ *
+ * Conventions
+ *   - All host arrays are column-major Float64 exactly as Julia lays them out.  "ghosted" means
+ *     (nx+2) x (ny+2) with interior [2:nx+1, 2:ny+1] (1-based), element (i,j) at [(i-1) + (nx+2)*(j-1)].
+ *   - nx == ny (the reference aliases ky = kx, Common.jl:113) and a power of two in [32, 8192].
+ *   - Every function returns 0 on success; otherwise a VMK_E* code, and vmk_last_error() (thread-local)
+ *     describes it.  The library never falls back to a CPU path: without a usable CUDA device every
+ *     compute entry point fails with VMK_ECUDA.
+ *   - Entry points taking host pointers are synchronous (they return after the device->host copy), because
+ *     Julia only roots ccall arguments for the duration of the call.  A plan must not be used from two
+ *     host threads at once.
+ */
+#ifndef VMK_H_
+#define VMK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMK_OK 0
+#define VMK_ESIZE 1  /* unsupported grid size (not square, not a power of two, out of range) */
+#define VMK_ECUDA 2  /* CUDA runtime error (including "no device") */
+#define VMK_EARG 3   /* bad argument (NULL pointer, bad rank, ...) */
+#define VMK_ESTATE 4 /* call sequence error (e.g. step before upload) */
+
+typedef struct vmk_plan vmk_plan;
+
+int vmk_version(void);
+const char* vmk_last_error(void);
+
+/* Owns device buffers, twiddle/divisor tables and the stream for one grid size on the current device.
+ * Replaces the per-call allocations of numerical() (vm.jl:13-19) and the per-call FFTW plans and kx table
+ * of fps (Common.jl:98-113,117,123). */
+int vmk_plan_create(int64_t nx, int64_t ny, vmk_plan** plan);
+int vmk_plan_destroy(vmk_plan* plan);
+
+/* ---- slab decomposition over several GPUs (no counterpart in the reference, which is single-threaded) --
+ * Rank g of nranks (1, 2, 4 or 8) owns grid columns j in [g*ny/nranks, (g+1)*ny/nranks) (Julia dim 2) on the
+ * CUDA device that is current when the plan is created.  The kernels exchange data by loading from /
+ * storing to the other ranks' buffers directly over NVLink (halo rows of w and psi; the j-direction FFT
+ * reads the whole spectrum row from all ranks), so every rank needs the others' buffer addresses:
+ *   one process per GPU : vmk_peer_export -> all-gather the blobs -> vmk_peer_import (CUDA IPC)
+ *   one process, N GPUs : vmk_peer_attach_local (peer access enabled by the caller)
+ * and a cross-rank barrier that the plan enqueues on its stream between dependent kernels
+ * (vmk_barrier_hook; e.g. a 1-element NCCL all-reduce on that stream).
+ * Host-array entry points of a slab plan read/write only the rank's own columns of the caller's arrays. */
+int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan** plan);
+size_t vmk_peer_blob_bytes(void);
+int vmk_peer_export(vmk_plan* plan, void* blob);
+int vmk_peer_import(vmk_plan* plan, const void* blobs /* nranks blobs in rank order */);
+int vmk_peer_attach_local(vmk_plan* plan, vmk_plan* const* plans /* nranks plans in rank order */);
+int vmk_barrier_hook(vmk_plan* plan, void (*enqueue_barrier)(void* user), void* user);
+
+/* ---- reference-signature entry points on HOST arrays ------------------------------------------------ */
+
+/* fps(nx,ny,dx,dy,u,e,data,data1,f,s,eps)  Common.jl:97-125.
+ * f: nx x ny source.  s: ghosted; only s[2:nx+1,2:ny+1] is written (the reference leaves ghosts alone).
+ * The dead scratch arguments u,e,data,data1 of the reference are not part of the ABI. */
+int vmk_fps(vmk_plan* plan, double dx, double dy, const double* f, double* s, double eps);
+
+/* ps_fft(nx,ny,dx,dy,f,eps)  12_Poisson_Solver_FFT/fft_p.jl:8-42.
+ * f: (nx+1) x (ny+1), only [1:nx,1:ny] is read.  u: nx x ny result. */
+int vmk_ps_fft(vmk_plan* plan, double dx, double dy, const double* f, double* u, double eps);
+
+/* vm_rhs(nx,ny,dx,dy,re,w,u,e,data,data1,r,s,f)  Common.jl:132-182.
+ * w: ghosted vorticity with periodic ghosts (read).  r: ghosted, interior written.  s: ghosted, all cells
+ * written (ghost fill of Common.jl:138-146).  f: nx x ny, receives -w interior (Common.jl:134); may be NULL. */
+int vmk_rhs(vmk_plan* plan, double dx, double dy, double re, const double* w, double* r, double* s, double* f);
+
+/* numerical(nx,ny,nt,dx,dy,dt,re,x,y,wn,ns)  19_NS2D_Vortex_Merger/vm.jl:12-90 and
+ * numerical(nx,ny,nt,dx,dy,dt,re,wn)        19_NS2D_Vortex_Merger/tgv.jl:13-79.
+ * wn: ghosted, mutated in place, all ghosts valid on return.  out: (nx+1) x (ny+1) = wn[2:nx+2,2:ny+2], or NULL.
+ * If snap != NULL and freq > 0, after every step k with k % freq == 0 (vm.jl:78) wn is brought to the host
+ * (into the caller's wn) and snap(k, wn, user) is called; file output stays on the caller's side. */
+typedef void (*vmk_snapshot_fn)(int64_t k, const double* wn_ghosted, void* user);
+int vmk_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, double re, double* wn, double* out,
+                  int64_t freq, vmk_snapshot_fn snap, void* user);
+
+/* ---- device-resident path (what numerical() is built from) ------------------------------------------- */
+int vmk_upload(vmk_plan* plan, const double* wn_ghosted);
+int vmk_step(vmk_plan* plan, double dx, double dy, double dt, double re, int64_t nsteps); /* asynchronous */
+int vmk_download(vmk_plan* plan, double* wn_ghosted, double* psi_ghosted);                /* either may be NULL */
+int vmk_sync(vmk_plan* plan);
+
+/* ---- measurement ------------------------------------------------------------------------------------ */
+/* cudaStream_t the plan launches on (cast to void*), so callers can bracket calls with their own events */
+void* vmk_stream(vmk_plan* plan);
+/* device time of the last vmk_step call, from CUDA events recorded on the plan's stream */
+int vmk_step_elapsed_ms(vmk_plan* plan, double* ms);
+/* runs `nsteps` steps with events around every kernel; ms[0..3] receive the summed device time of
+ * K1 (row forward), K2 (column forward+divide+inverse), K3 (row inverse), K4 (stencil+RK3); launches[0..3]
+ * the launch counts */
+int vmk_profile_steps(vmk_plan* plan, double dx, double dy, double dt, double re, int64_t nsteps, double* ms,
+                      int64_t* launches);
+/* kernels launched by this plan since creation */
+int64_t vmk_launch_count(vmk_plan* plan);
+/* tuning knobs (integers): "graph" (0/1 CUDA-graph the step), "k4_rows" */
+int vmk_set_option(vmk_plan* plan, const char* key, int64_t value);
+/* bytes of device memory held by the plan */
+int64_t vmk_device_bytes(vmk_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMK_H_ */

@@ -1,0 +1,147 @@
+// emul.cpp -- host execution of the vmk kernel bodies for CI machines without a GPU.
+//
+// TEST INFRASTRUCTURE ONLY.  Built (with -DVMK_EMUL) into tests/emul/libvmk_emul.so, which exports the
+// C ABI under vmke_* names; the package never loads it.  It exists so that the index arithmetic of the
+// kernels (FFT digit permutations, transposed spectrum layout, packed DC/Nyquist row, halo rows, slab
+// decomposition) can be checked against the oracle in the "-m 'not gpu'" suite.  It proves nothing about
+// the CUDA build's performance, and the parity claims are made by the "-m gpu" tests on the real library.
+//
+// Execution model: one CTA at a time per worker; the CTA's threads are ucontext fibers run round-robin,
+// Ctx::sync() yields to the scheduler, which resumes the next fiber -- after a full round every fiber has
+// reached the barrier, exactly __syncthreads() semantics (threads that returned are skipped, as on the
+// device).  CTAs of a grid are distributed over a few OS threads.
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <ucontext.h>
+
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "../../cfd_julia_b200/csrc/vmk_backend.cuh"
+
+namespace {
+
+constexpr size_t kStackBytes = 96 * 1024;
+
+struct Fiber {
+  ucontext_t ctx;
+  void* stack = nullptr;
+  bool done = false;
+};
+
+struct Worker {
+  ucontext_t sched;
+  std::vector<Fiber> fibers;
+  int current = -1;
+  // launch description
+  vmk::emul_body_fn fn = nullptr;
+  const void* args = nullptr;
+  unsigned char* smem = nullptr;
+  int bid = 0, nblk = 0;
+};
+
+thread_local Worker* tl_worker = nullptr;
+
+void fiber_entry(unsigned lo, unsigned hi) {
+  Worker* w = reinterpret_cast<Worker*>(((uintptr_t)hi << 32) | (uintptr_t)lo);
+  const int tid = w->current;
+  vmk::Ctx c;
+  c.tid = tid;
+  c.bid = w->bid;
+  c.nblk = w->nblk;
+  c.smem = w->smem;
+  c.hbar = w;
+  w->fn(c, w->args);
+  w->fibers[tid].done = true;
+  swapcontext(&w->fibers[tid].ctx, &w->sched);
+}
+
+void run_cta(Worker* w, int block) {
+  for (int t = 0; t < block; t++) {
+    Fiber& f = w->fibers[t];
+    f.done = false;
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = kStackBytes;
+    f.ctx.uc_link = nullptr;
+    const uintptr_t p = (uintptr_t)w;
+    makecontext(&f.ctx, (void (*)())fiber_entry, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
+  }
+  int alive = block;
+  while (alive > 0) {
+    for (int t = 0; t < block; t++) {
+      Fiber& f = w->fibers[t];
+      if (f.done) continue;
+      w->current = t;
+      swapcontext(&w->sched, &f.ctx);
+      if (f.done) alive--;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" void vmk_host_barrier_wait(void* bar) {
+  Worker* w = static_cast<Worker*>(bar);
+  swapcontext(&w->fibers[w->current].ctx, &w->sched);
+}
+
+namespace vmk {
+
+double emul_now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
+int emul_run(int grid, int block, size_t smem, emul_body_fn fn, const void* args) {
+  if (grid < 1 || block < 1) return fail(2, "emul: empty launch");
+  unsigned hw = std::thread::hardware_concurrency();
+  int nworkers = (int)(hw ? hw : 1);
+  if (nworkers > grid) nworkers = grid;
+  if (nworkers > 8) nworkers = 8;
+  std::atomic<int> next{0};
+  std::atomic<int> failed{0};
+  auto work = [&]() {
+    Worker w;
+    w.fn = fn;
+    w.args = args;
+    w.nblk = grid;
+    w.fibers.resize(block);
+    void* sm = nullptr;
+    if (posix_memalign(&sm, 256, smem ? smem : 256)) {
+      failed = 1;
+      return;
+    }
+    w.smem = static_cast<unsigned char*>(sm);
+    for (auto& f : w.fibers) {
+      f.stack = malloc(kStackBytes);
+      if (!f.stack) failed = 1;
+    }
+    if (!failed) {
+      for (;;) {
+        const int b = next.fetch_add(1);
+        if (b >= grid) break;
+        w.bid = b;
+        memset(w.smem, 0xff, smem);  // shared memory is uninitialised on the device: poison it
+        run_cta(&w, block);
+      }
+    }
+    for (auto& f : w.fibers) free(f.stack);
+    free(sm);
+  };
+  if (nworkers == 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < nworkers; i++) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  return failed ? fail(2, "emul: out of memory") : 0;
+}
+
+}  // namespace vmk

@@ -1,0 +1,146 @@
+"""Parity checks written once and run against two libraries: the product (libvmk.so on the GPU, `-m gpu`)
+and the host emulation of the same kernel bodies (tests/emul, CPU suite).  `cm` is a
+cfd_julia_b200.common.Common bound to the library under test, `oc` the C oracle.
+
+Tolerance: north_star asks for rel-L2 <= 1e-10 on vorticity and streamfunction; single calls are held
+to 1e-12 here (observed ~5e-16), multi-step runs to 1e-10.
+"""
+import numpy as np
+
+from helpers import (GOLD, ORDER_JL_FFT_FDM, ghost_fill, grid, mms, noise_field, rel_l2, stable_dt, tgv_field,
+                     vm_field)
+
+TOL_CALL = 1e-12
+TOL_RUN = 1e-10
+
+
+def check_fps_noise(cm, oc, n, seed=0):
+    dx, dy, _, _ = grid(n)
+    f = np.asfortranarray(np.random.default_rng(seed).uniform(-1, 1, (n, n)))
+    s = np.full((n + 2, n + 2), 7.0, order="F")
+    ref = np.full((n + 2, n + 2), 7.0, order="F")
+    cm.fps(n, n, dx, dy, None, None, None, None, f, s)
+    oc.fps(n, n, dx, dy, f, ref)
+    assert rel_l2(s[1:n + 1, 1:n + 1], ref[1:n + 1, 1:n + 1]) < TOL_CALL
+    # the reference writes the interior only (Common.jl:123): ghosts keep the caller's values
+    for edge in (s[0, :], s[n + 1, :], s[:, 0], s[:, n + 1]):
+        assert np.all(edge == 7.0)
+
+
+def check_rhs(cm, oc, w, re=1000.):
+    n = w.shape[0] - 2
+    dx, dy, _, _ = grid(n)
+    r = np.full_like(w, 3.0)
+    s = np.zeros_like(w)
+    f = np.zeros((n, n), order="F")
+    r2 = np.full_like(w, 3.0)
+    s2 = np.zeros_like(w)
+    f2 = np.zeros((n, n), order="F")
+    w_before = w.copy(order="F")
+    cm.vm_rhs(n, n, dx, dy, re, w, None, None, None, None, r, s, f)
+    oc.vm_rhs(n, n, dx, dy, re, w_before, r2, s2, f2)
+    assert np.array_equal(w, w_before)
+    assert np.array_equal(f, f2)  # f = -w is exact
+    assert rel_l2(s, s2) < TOL_CALL  # all cells incl. ghosts (Common.jl:138-146)
+    assert rel_l2(r[1:n + 1, 1:n + 1], r2[1:n + 1, 1:n + 1]) < TOL_CALL
+    for edge in (r[0, :], r[n + 1, :], r[:, 0], r[:, n + 1]):  # r's ghosts are never written
+        assert np.all(edge == 3.0)
+
+
+def check_numerical(cm, oc, w0, nt, dt, re, tol=TOL_RUN):
+    n = w0.shape[0] - 2
+    dx, dy, _, _ = grid(n)
+    wa = w0.copy(order="F")
+    wb = w0.copy(order="F")
+    out = cm.numerical_tgv(n, n, nt, dx, dy, dt, re, wa)
+    ref, _ = oc.numerical(n, n, nt, dx, dy, dt, re, wb)
+    assert out.shape == (n + 1, n + 1)
+    assert rel_l2(out, ref) < tol
+    assert rel_l2(wa, wb) < tol  # wn mutated in place, ghosts valid
+    assert np.array_equal(out, wa[1:n + 2, 1:n + 2])
+    return out
+
+
+def check_golden(cm):
+    g = np.load(f"{GOLD}/fps_noise_32.npz")
+    s = np.zeros((34, 34), order="F")
+    cm.fps(32, 32, float(g["dx"]), float(g["dy"]), None, None, None, None, np.asfortranarray(g["f"]), s)
+    assert rel_l2(s, g["s"]) < TOL_CALL
+    g = np.load(f"{GOLD}/vm_rhs_64.npz")
+    w = np.asfortranarray(g["w"])
+    r = np.zeros_like(w)
+    s = np.zeros_like(w)
+    f = np.zeros((64, 64), order="F")
+    cm.vm_rhs(64, 64, float(g["dx"]), float(g["dy"]), float(g["re"]), w, None, None, None, None, r, s, f)
+    assert rel_l2(r, g["r"]) < TOL_CALL and rel_l2(s, g["s"]) < TOL_CALL and np.array_equal(f, g["f"])
+    g = np.load(f"{GOLD}/vm_numerical_64_25.npz")
+    wn = np.asfortranarray(g["w0"].copy())
+    out = cm.numerical_tgv(64, 64, int(g["nt"]), float(g["dx"]), float(g["dy"]), float(g["dt"]), float(g["re"]), wn)
+    assert rel_l2(out, g["out"]) < TOL_RUN and rel_l2(wn, g["wn"]) < TOL_RUN
+    g = np.load(f"{GOLD}/tgv_64_100.npz")
+    wn = np.asfortranarray(g["w0"].copy())
+    out = cm.numerical_tgv(64, 64, int(g["nt"]), float(g["dx"]), float(g["dy"]), float(g["dt"]), float(g["re"]), wn)
+    assert rel_l2(out, g["out"]) < TOL_RUN
+
+
+def check_order_jl(cm, n):
+    """The reference's only recorded outputs: fft_p.jl L2 errors hard-coded at order.jl:13."""
+    from cfd_julia_b200.common import compute_l2norm_bnds
+    dx, f, ue = mms(n)
+    un = np.zeros_like(f)
+    un[:n, :n] = cm.ps_fft(n, n, dx, dx, f)
+    un[n, :] = un[0, :]  # fft_p.jl:95-98
+    un[:, n] = un[:, 0]
+    l2 = compute_l2norm_bnds(n, n, un - ue)
+    assert abs(l2 - ORDER_JL_FFT_FDM[n]) / ORDER_JL_FFT_FDM[n] < 1e-10
+
+
+def check_tgv_defaults(cm):
+    """tgv.jl defaults: 64^2, Re=10, dt=.01, 100 steps; survey-probe values of the printed errors."""
+    from cfd_julia_b200.common import compute_l2norm_bnds, exact_tgv
+    n = 64
+    dx, dy, x, y = grid(n)
+    wn = tgv_field(n)
+    out = cm.numerical_tgv(n, n, 100, dx, dy, .01, 10., wn)
+    ue = exact_tgv(n, n, x, y, 1., 10.)
+    assert abs(compute_l2norm_bnds(n, n, out - ue) - 6.9131011113e-3) < 1e-11
+    assert abs(np.max(np.abs(out - ue)) - 1.3616714310e-2) < 1e-10
+
+
+def check_snapshots(cm, oc, tmp_path):
+    """vm.jl:78-86 cadence: every nt // ns steps; text format "x y w", j outer."""
+    n, nt, ns = 32, 10, 5
+    dx, dy, x, y = grid(n)
+    wn = vm_field(n)
+    ref_w = wn.copy(order="F")
+    seen = []
+    out = cm.numerical(n, n, nt, dx, dy, .01, 1000., x, y, wn, ns, snapshot=lambda k, ut: seen.append((k, ut.copy())),
+                       outdir=str(tmp_path))
+    assert [k for k, _ in seen] == [2, 4, 6, 8, 10]
+    ref2, _ = oc.numerical(n, n, 2, dx, dy, .01, 1000., ref_w)
+    assert rel_l2(seen[0][1], ref2) < TOL_RUN
+    assert np.array_equal(seen[-1][1], out)
+    rows = np.loadtxt(tmp_path / "vm5.txt")
+    assert rows.shape == ((n + 1) * (n + 1), 3)
+    assert np.array_equal(rows[:, 2].reshape(n + 1, n + 1).T, out)  # j outer, i inner
+    assert np.array_equal(rows[:n + 1, 0], x)
+
+
+def check_errors(cm):
+    import pytest
+    from cfd_julia_b200.common import VmkError
+    with pytest.raises(VmkError) as e:
+        cm.plan(48, 48)  # not a power of two
+    assert e.value.code == 1
+    with pytest.raises(VmkError):
+        cm.plan(64, 128)  # ky = kx aliasing of the reference needs nx == ny
+    with pytest.raises(VmkError):
+        cm.plan(16, 16)
+    with pytest.raises(IndexError):
+        cm.fps(32, 32, .1, .1, None, None, None, None, np.zeros((32, 32), order="F"), np.zeros((32, 32), order="F"))
+    from cfd_julia_b200.common import Plan
+    p = Plan(cm.lib, 32, 32)
+    with pytest.raises(VmkError) as e:
+        p.step(.1, .1, .01, 100., 1)  # step before upload
+    assert e.value.code == 4
+    p.close()

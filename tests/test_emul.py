@@ -1,0 +1,141 @@
+"""CPU suite: the kernel bodies (same source as the CUDA build) executed by the host emulator
+(tests/emul) against the oracle.  Checks the index arithmetic of every FFT size configuration, the
+transposed/packed spectrum layout, halo handling and the slab decomposition without a GPU.
+The parity claims proper are made by tests/test_gpu_parity.py on the real library."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from helpers import ROOT, grid, noise_field, rel_l2, stable_dt, tgv_field, vm_field
+
+
+@pytest.fixture(scope="module")
+def emul():
+    from cfd_julia_b200._lib import VmkLibrary
+    from cfd_julia_b200.common import Common
+    d = os.path.join(ROOT, "tests", "emul")
+    subprocess.check_call(["make", "-C", d, "-s"])
+    return Common(VmkLibrary(os.path.join(d, "libvmk_emul.so"), "vmke_"))
+
+
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048])
+def test_fps_noise(emul, oracle_c, n):
+    pc.check_fps_noise(emul, oracle_c, n)
+
+
+def test_fps_4096(emul, oracle_c):
+    pc.check_fps_noise(emul, oracle_c, 4096)
+
+
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024])
+def test_rhs_noise(emul, oracle_c, n):
+    pc.check_rhs(emul, oracle_c, noise_field(n, seed=n))
+
+
+def test_rhs_vm_ic(emul, oracle_c):
+    pc.check_rhs(emul, oracle_c, vm_field(128))
+
+
+@pytest.mark.parametrize("n,nt", [(32, 20), (64, 10), (128, 10), (256, 5), (512, 3), (1024, 2)])
+def test_numerical_vm(emul, oracle_c, n, nt):
+    pc.check_numerical(emul, oracle_c, vm_field(n), nt, stable_dt(n, 1000.), 1000.)
+
+
+def test_numerical_noise(emul, oracle_c):
+    pc.check_numerical(emul, oracle_c, noise_field(64, 3), 5, 1e-3, 100.)
+
+
+def test_golden(emul):
+    pc.check_golden(emul)
+
+
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 512])
+def test_order_jl(emul, n):
+    pc.check_order_jl(emul, n)
+
+
+def test_tgv_defaults(emul):
+    pc.check_tgv_defaults(emul)
+
+
+def test_snapshots(emul, oracle_c, tmp_path):
+    pc.check_snapshots(emul, oracle_c, tmp_path)
+
+
+def test_errors(emul):
+    pc.check_errors(emul)
+
+
+def test_device_path_and_options(emul, oracle_c):
+    n = 64
+    dx, dy, _, _ = grid(n)
+    w0 = vm_field(n)
+    p = emul.plan(n, n)
+    p.set_option("k4_rows", 5)  # ragged last row block
+    p.upload(w0)
+    p.step(dx, dy, .01, 1000., 2)
+    p.step(dx, dy, .01, 1000., 1)
+    wn = np.zeros_like(w0)
+    psi = np.zeros_like(w0)
+    p.download(wn, psi)
+    ref = w0.copy(order="F")
+    _, s = oracle_c.numerical(n, n, 3, dx, dy, .01, 1000., ref)
+    assert rel_l2(wn, ref) < 1e-12 and rel_l2(psi, s) < 1e-12
+    assert p.launch_count >= 36 and p.device_bytes > 0
+    prof = p.profile_steps(dx, dy, .01, 1000., 1)
+    assert all(prof[k]["launches"] == 3 for k in ("k1", "k2", "k3", "k4"))
+    p.set_option("k4_rows", 32)
+
+
+@pytest.mark.parametrize("n,nranks", [(64, 2), (64, 4), (128, 8), (256, 2)])
+def test_slab_decomposition(emul, oracle_c, n, nranks):
+    """Ranks as plans in one process (vmk_peer_attach_local); the emulator runs launches synchronously,
+    so stepping the ranks kernel by kernel in lock-step stands in for the cross-rank barrier."""
+    from cfd_julia_b200.common import Plan
+    from cfd_julia_b200._lib import BARRIER_FN
+    lib = emul.lib
+    plans = [Plan(lib, n, n, r, nranks) for r in range(nranks)]
+    arr = (C.c_void_p * nranks)(*[p.handle for p in plans])
+    for p in plans:
+        lib.check(lib.peer_attach_local(p.handle, arr))
+    # lock-step execution: each rank runs on its own thread, the barrier hook is a host barrier
+    import threading
+    bar = threading.Barrier(nranks)
+    hook = BARRIER_FN(lambda _u: bar.wait())
+    for p in plans:
+        lib.check(lib.barrier_hook(p.handle, hook, None))
+    dx, dy, _, _ = grid(n)
+    w0 = vm_field(n) + 0.1 * noise_field(n, 5)
+    outs = [np.zeros_like(w0) for _ in plans]
+    psis = [np.zeros_like(w0) for _ in plans]
+    errs = []
+
+    def run(r):
+        try:
+            p = plans[r]
+            p.upload(w0)
+            bar.wait()
+            p.step(dx, dy, 1e-3, 1000., 3)
+            bar.wait()
+            p.download(outs[r], psis[r])
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+            bar.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(nranks)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    ref = w0.copy(order="F")
+    _, s = oracle_c.numerical(n, n, 3, dx, dy, 1e-3, 1000., ref)
+    nj = n // nranks
+    for r in range(nranks):
+        rows = slice(r * nj, (r + 1) * nj + 2)  # the rank's ghosted rows j0 .. j0+NJ+1
+        assert rel_l2(outs[r][:, rows], ref[:, rows]) < 1e-12
+        assert rel_l2(psis[r][:, rows], s[:, rows]) < 1e-12
+    for p in plans:
+        p.close()
