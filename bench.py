@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- vortex-merger grid-point-steps/s at 8192^2 FP64 on N B200s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (libvmk.so through the C ABI)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's CPU algorithm on the host cores
+
+One "step" = one SSP-RK3 time step of the 8192^2 periodic vortex merger (vm.jl:24-76): 3 x (Poisson solve +
+Arakawa/Laplacian rhs + stage combine) = 12 kernel launches.  Re = 1000, dt = 1e-4 (the scripts' dt = .01 is
+unstable at this resolution).  The working set (~3.2 GB) is far larger than the 126 MB L2, so no
+flush is needed between timed steps.
+
+JSON line keys beyond the base contract:
+  roofline     the slowest kernel of the step: algorithmic bytes per launch / mean launch duration (CUDA
+               events on the plan's stream, measured here) against MEASURED_PEAKS.json's HBM copy bandwidth;
+               `step` holds the same for the whole step (232 B per grid-point-step)
+  cpu_baseline the oracle port (oracle/vm_oracle.c, OpenMP) timed on this box's host cores on a bounded sample
+  e2e          vmk_numerical(nt = K) on a pinned HOST array: upload + K steps + download inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vortex_merger_grid_point_steps_per_s_8192x8192_fp64"
+UNIT = "grid-point-steps/s"
+BYTES_PER_POINT_STEP = 232.0
+# algorithmic bytes per grid point per launch: K1/K2/K3 read 8 + write 8; K4 reads w, psi (+wn) and writes
+KERNEL_BYTES = {"k1": 16.0, "k2": 16.0, "k3": 16.0, "k4": (24.0 + 32.0 + 32.0) / 3.0}
+RE, DT = 1000., 1e-4
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
+        for l in rows:
+            p = [q.strip() for q in l.split(",")]
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except Exception:  # noqa: BLE001
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def vm_initial_condition(n):
+    """vm_ic + main()'s ghost fill (Common.jl:208-219, vm.jl:107-128) -- synthetic input, no files."""
+    import cfd_julia_b200 as vm
+    dx = 2 * np.pi / n
+    x = dx * np.arange(n + 1)
+    w = np.zeros((n + 2, n + 2), order="F")
+    vm.vm_ic(n, n, x, x, w)
+    w[0, :] = w[n, :]
+    w[:, 0] = w[:, n]
+    w[n + 1, :] = w[1, :]
+    w[:, n + 1] = w[:, 1]
+    return dx, w
+
+
+def cpu_sample(n, steps, warmup=0):
+    """The oracle port on the host cores: returns (grid-point-steps/s, threads, seconds per step)."""
+    from oracle import oracle_c as oc
+    oc.build()
+    dx, w = vm_initial_condition(n)
+    dt = min(.01, DT * (8192. / n)**2)
+    if warmup:
+        oc.numerical(n, n, warmup, dx, dx, dt, RE, w)
+    t0 = time.perf_counter()
+    oc.numerical(n, n, steps, dx, dx, dt, RE, w)
+    el = time.perf_counter() - t0
+    return n * n * steps / el, oc.num_threads(), el / steps
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the CPU.  Julia + FFTW.jl are not in the image, so this is
+    the oracle port (kind "port"), all host threads (OpenMP), on a bounded 4096^2 sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.cpu_n
+    v, threads, s_per_step = cpu_sample(n, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "vortex merger 8192x8192 periodic, Re=1000, RK3 + FFT Poisson (BASELINE configs[3])",
+                   "sample": f"{n}x{n} grid, same IC and Re, dt scaled with dx^2"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"oracle/vm_oracle.c (OpenMP, {threads} threads), {args.steps} RK3 steps at {n}x{n}; "
+                                   "Julia/FFTW.jl absent from the image"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=8192, help="grid size (default: the BASELINE workload)")
+    ap.add_argument("--cpu-n", type=int, default=4096, help="grid size of the --impl reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import cfd_julia_b200 as vm
+    from cfd_julia_b200.common import Plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    lib = vm.default_library()
+    n, K, W = args.n, args.steps, args.warmup
+    dx, w0 = vm_initial_condition(n)
+
+    dist = None
+    keep = []
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        plan = Plan(lib, n, n, rank, world)
+        nb = lib.peer_blob_bytes()
+        mine = torch.zeros(nb, dtype=torch.uint8)
+        lib.check(lib.peer_export(plan.handle, mine.data_ptr()))
+        allb = [torch.zeros(nb, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allb, mine.cuda())
+        blobs = torch.cat([b.cpu() for b in allb]).contiguous()
+        lib.check(lib.peer_import(plan.handle, blobs.data_ptr()))
+        stream = torch.cuda.ExternalStream(plan.stream)
+        token = torch.zeros(1, device="cuda")
+        from cfd_julia_b200._lib import BARRIER_FN
+
+        def _barrier(_u):
+            with torch.cuda.stream(stream):
+                dist.all_reduce(token)
+
+        hook = BARRIER_FN(_barrier)
+        keep.append(hook)
+        lib.check(lib.barrier_hook(plan.handle, hook, None))
+    else:
+        plan = Plan(lib, n, n)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    plan.upload(w0)
+    plan.step(dx, dx, DT, RE, W)  # warm-up (also builds the CUDA graph)
+    plan.sync()
+
+    # ---- timed region: K steps, device-resident, CUDA events on the plan's stream -----------------------------
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    l0 = plan.launch_count
+    t0 = time.time()
+    plan.step(dx, dx, DT, RE, K)
+    plan.sync()
+    barrier()
+    t1 = time.time()
+    ms = plan.step_elapsed_ms()
+    launches = plan.launch_count - l0
+    clk = clocks.stop(t0, t1) if clocks else None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tl = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tl)
+        launches = int(tl.item())
+    value = float(n) * n * K / (ms * 1e-3)
+
+    # sanity: the field is finite after the run (a wrong dt would give NaNs and a meaningless number)
+    chk = np.zeros_like(w0)
+    plan.download(chk)
+    j0, nj = rank * (n // world), n // world
+    assert np.isfinite(chk[:, j0:j0 + nj + 2]).all(), "non-finite vorticity after the timed steps"
+
+    # ---- per-kernel durations (events around every launch; separate, untimed pass) ---------------------------------
+    peak, peak_src = measured_peak()
+    prof = plan.profile_steps(dx, dx, DT, RE, 3)
+    pts = float(n) * (n // world)
+    kern = {}
+    for k, v in prof.items():
+        if v["launches"]:
+            dur = v["ms"] / v["launches"]
+            ach = KERNEL_BYTES[k] * pts / (dur * 1e-3) / 1e9
+            kern[k] = {"ms_per_launch": dur, "achieved_gbs": ach, "frac": ach / peak,
+                       "share": v["ms"] / sum(q["ms"] for q in prof.values())}
+    top = max(kern, key=lambda k: kern[k]["ms_per_launch"]) if kern else None
+    step_gbs = BYTES_PER_POINT_STEP * value / world / 1e9
+    roofline = {"bound": "hbm", "kernel": top, "achieved": kern[top]["achieved_gbs"] if top else None, "peak": peak,
+                "unit": "GB/s", "frac": kern[top]["frac"] if top else None, "traffic": None, "peak_source": peak_src,
+                "kernels": kern,
+                "step": {"achieved": step_gbs, "frac": step_gbs / peak, "frac_of_8TBs": step_gbs / 8000.,
+                         "bytes_per_point_step": BYTES_PER_POINT_STEP}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if top and os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(top)
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- e2e: the reference-facing call on a pinned host array ----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n + 2) * (n + 2), dtype=torch.float64).pin_memory()
+        hv = host.numpy().reshape((n + 2, n + 2), order="F")
+        hv[...] = w0
+        barrier()
+        te = time.perf_counter()
+        lib.check(lib.numerical(plan.handle, K, dx, dx, DT, RE, host.data_ptr(), None, 0,
+                                vm._lib.SNAPSHOT_FN(), None))
+        barrier()
+        el = time.perf_counter() - te
+        if dist is not None:
+            t = torch.tensor([el], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        slab_bytes = 8 * (n + 2) * (n // world + 2)
+        e2e = {"value": float(n) * n * K / el, "unit": UNIT, "h2d_bytes_per_step": slab_bytes * world / K,
+               "d2h_bytes_per_step": slab_bytes * world / K,
+               "call": f"vmk_numerical(nt={K}) on a pinned host array: upload + {K} steps + download"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, threads, sps = cpu_sample(n, 2)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"oracle/vm_oracle.c (OpenMP, {threads} threads): 2 RK3 steps of the same {n}x{n} workload, "
+                         f"{sps:.2f} s/step; Julia/FFTW.jl absent from the image"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"vortex merger {n}x{n} periodic, Re=1000, dt=1e-4, RK3 + FFT Poisson "
+                                   "(BASELINE configs[3])",
+                       "l2": "working set 3.2 GB >> 126 MB L2, no flush needed",
+                       "parallelism": f"slab{world}" if world > 1 else "single GPU",
+                       "cuda_graph": True if world == 1 else False},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        plan.close()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -197,6 +197,7 @@ struct vmk_plan {
   bool uploaded = false;
   int64_t launches = 0;
   int k4_rows = 32;
+  int k1_group = 1, k3_group = 1, k1_prefetch = 1, k2_prefetch = 1, k3_prefetch = 0;
   int use_graph = 1;
 #ifndef VMK_EMUL
   std::map<StepParams, cudaGraphExec_t> graphs;
@@ -216,6 +217,15 @@ int dev_alloc(vmk_plan* p, void** ptr, size_t bytes) {
   VMK_TRY(be_malloc(ptr, bytes));
   p->dev_bytes += (int64_t)bytes;
   return 0;
+}
+
+void drop_graphs(vmk_plan* p) {
+#ifndef VMK_EMUL
+  for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
+  p->graphs.clear();
+#else
+  (void)p;
+#endif
 }
 
 int ensure_staging(vmk_plan* p) {
@@ -250,10 +260,7 @@ int ensure_divisor(vmk_plan* p, double dx, double dy, double eps) {
   p->div_dy = dy;
   p->div_eps = eps;
   p->div_valid = true;
-#ifndef VMK_EMUL
-  for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
-  p->graphs.clear();
-#endif
+  drop_graphs(p);
   return 0;
 }
 
@@ -284,6 +291,13 @@ int cross_rank_barrier(vmk_plan* p) {
   return 0;
 }
 
+// K1/K3 work units: groups of row pairs (see k1_body / k3_body)
+int rowpair_units(const vmk_plan* p, int npairs, int g) {
+  const int fpc = p->ops.fpc;
+  const int nblocks = (npairs + fpc - 1) / fpc;
+  return (nblocks + g - 1) / g;
+}
+
 int launch_k1(vmk_plan* p, const double* src) {
   K1Args a;
   a.w = src;
@@ -291,7 +305,9 @@ int launch_k1(vmk_plan* p, const double* src) {
   a.tw = p->tw;
   a.NJ = p->NJ;
   a.npairs = p->NJ / 2;
-  const int work = (a.npairs + p->ops.fpc - 1) / p->ops.fpc;
+  a.group = p->k1_group;
+  a.prefetch = p->k1_prefetch;
+  const int work = rowpair_units(p, a.npairs, a.group);
   Timed t(p, KI_K1);
   VMK_TRY(p->ops.k1(work < p->res_k1 ? work : p->res_k1, a, p->st));
   t.done();
@@ -311,6 +327,7 @@ int launch_k2(vmk_plan* p, double sign) {
   a.log2NJ = p->log2NJ;
   a.nrows = (p->N / 2) / p->nranks;
   a.row0 = p->rank * a.nrows;
+  a.prefetch = p->k2_prefetch;
   const int work = (a.nrows + p->ops.fpc - 1) / p->ops.fpc;
   Timed t(p, KI_K2);
   VMK_TRY(p->ops.k2(work < p->res_k2 ? work : p->res_k2, a, p->st));
@@ -329,7 +346,9 @@ int launch_k3(vmk_plan* p) {
   a.hi_dst = p->peer_psi[next];
   a.NJ = p->NJ;
   a.npairs = p->NJ / 2;
-  const int work = (a.npairs + p->ops.fpc - 1) / p->ops.fpc;
+  a.group = p->k3_group;
+  a.prefetch = p->k3_prefetch;
+  const int work = rowpair_units(p, a.npairs, a.group);
   Timed t(p, KI_K3);
   VMK_TRY(p->ops.k3(work < p->res_k3 ? work : p->res_k3, a, p->st));
   t.done();
@@ -356,17 +375,17 @@ int launch_k4(vmk_plan* p, int mode, int win, int wn, int out, const StepParams&
   a.gg = 1.0 / (4.0 * sp.dx * sp.dy);      // :151
   a.hh = 1.0 / 3.0;                        // :152
   a.dt = sp.dt;
-  const int cols = p->N / 2, tw = cols < kK4Threads ? cols : kK4Threads, groups = kK4Threads / tw;
+  const int cols = p->N / kK4Cols, tw = cols < kK4Threads ? cols : kK4Threads, groups = kK4Threads / tw;
   const int ctas_x = cols / tw;
   const int rows_per = groups * a.rows_per_cta;
   const int grid = ctas_x * ((p->NJ + rows_per - 1) / rows_per);
   Timed t(p, KI_K4);
   int rc = 0;
   switch (mode) {
-    case 0: rc = be_launch<K4Body<0>, K4Args, kK4Threads, 4>(grid, 0, a, p->st); break;
-    case 1: rc = be_launch<K4Body<1>, K4Args, kK4Threads, 4>(grid, 0, a, p->st); break;
-    case 2: rc = be_launch<K4Body<2>, K4Args, kK4Threads, 4>(grid, 0, a, p->st); break;
-    default: rc = be_launch<K4Body<3>, K4Args, kK4Threads, 4>(grid, 0, a, p->st); break;
+    case 0: rc = be_launch<K4Body<0>, K4Args, kK4Threads, 3>(grid, 0, a, p->st); break;
+    case 1: rc = be_launch<K4Body<1>, K4Args, kK4Threads, 3>(grid, 0, a, p->st); break;
+    case 2: rc = be_launch<K4Body<2>, K4Args, kK4Threads, 3>(grid, 0, a, p->st); break;
+    default: rc = be_launch<K4Body<3>, K4Args, kK4Threads, 3>(grid, 0, a, p->st); break;
   }
   VMK_TRY(rc);
   t.done();
@@ -802,15 +821,19 @@ int64_t vmk_launch_count(vmk_plan* p) { return p ? p->launches : 0; }
 int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
   if (!p || !key) return fail(VMK_EARG, "NULL argument");
   const std::string k(key);
-  if (k == "graph") {
+  int* knob = k == "k1_group" ? &p->k1_group : k == "k3_group" ? &p->k3_group : k == "k1_prefetch" ? &p->k1_prefetch
+              : k == "k2_prefetch" ? &p->k2_prefetch : k == "k3_prefetch" ? &p->k3_prefetch : nullptr;
+  if (knob) {
+    if (value < 0 || value > 64 || (value == 0 && k.find("group") != std::string::npos))
+      return fail(VMK_EARG, "option value out of range");
+    *knob = (int)value;
+    drop_graphs(p);
+  } else if (k == "graph") {
     p->use_graph = value != 0;
   } else if (k == "k4_rows") {
     if (value < 1 || value > 8192) return fail(VMK_EARG, "k4_rows out of range");
     p->k4_rows = (int)value;
-#ifndef VMK_EMUL
-    for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
-    p->graphs.clear();
-#endif
+    drop_graphs(p);
   } else {
     return fail(VMK_EARG, "unknown option: " + k);
   }

@@ -51,9 +51,21 @@ VMK_HD double2 mk2(double x, double y) {
 }
 VMK_HD double2 cadd(double2 a, double2 b) { return mk2(a.x + b.x, a.y + b.y); }
 VMK_HD double2 csub(double2 a, double2 b) { return mk2(a.x - b.x, a.y - b.y); }
-VMK_HD double2 cmul(double2 a, double2 b) { return mk2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// Explicit fused multiply-add.  The library is compiled with --fmad=false so that the stencil and the divisor
+// keep the reference's unfused source-order arithmetic; the FFT butterflies ask for FMAs by name (2 DMUL + 2 DFMA
+// per complex multiply instead of 4 DMUL + 2 DADD; the FP64 pipe is a co-bottleneck of the FFT kernels).
+VMK_HD double fma_(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+  return __fma_rn(a, b, c);
+#else
+  return __builtin_fma(a, b, c);
+#endif
+}
+VMK_HD double2 cmul(double2 a, double2 b) {
+  return mk2(fma_(a.x, b.x, -(a.y * b.y)), fma_(a.x, b.y, a.y * b.x));
+}
 VMK_HD double2 cmulc(double2 a, double2 b) {  // a * conj(b)
-  return mk2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+  return mk2(fma_(a.x, b.x, a.y * b.y), fma_(a.y, b.x, -(a.x * b.y)));
 }
 VMK_HD double2 cconj(double2 a) { return mk2(a.x, -a.y); }
 VMK_HD double2 cscale(double2 a, double s) { return mk2(a.x * s, a.y * s); }
@@ -129,9 +141,37 @@ VMK_HD void prefetch_l2(const void* p) {
   (void)p;
 #endif
 }
+// one instruction asks the L2 to fetch a whole contiguous range (16-byte aligned, multiple of 16 bytes):
+// issued by one thread for the NEXT row while the CTA transforms the current one, so that HBM streams
+// during the compute phase and the register loads of the next iteration are L2 hits
+VMK_HD void prefetch_l2_bulk(const void* p, unsigned bytes) {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+  (void)p;
+  (void)bytes;
+#endif
+}
 VMK_HD double rcp_rn(double d) {
 #ifdef __CUDA_ARCH__
   return __drcp_rn(d);
+#else
+  return 1.0 / d;
+#endif
+}
+
+// 1/d to <= 1 ulp without the branches of the IEEE-rounded reciprocal: hardware seed (20 mantissa bits) and two
+// Newton steps.  d is a Poisson divisor: finite, normal, never zero (the eps quirk keeps mode (0,0) off zero).
+VMK_HD double rcp_fast(double d) {
+#ifdef __CUDA_ARCH__
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = __fma_rn(-d, x, 1.0);
+  x = __fma_rn(x, e, x);
+  e = __fma_rn(-d, x, 1.0);
+  x = __fma_rn(x, e, x);
+  e = __fma_rn(-d, x, 1.0);
+  return __fma_rn(x, e, x);
 #else
   return 1.0 / d;
 #endif

@@ -55,10 +55,21 @@ VMK_HD double2 mul_const(double2 d) {
   } else {
     constexpr int j = I * (32 / R);
     constexpr double c = cos32(j), s = sin32(j);
-    if constexpr (SIGN < 0)
-      return mk2(d.x * c + d.y * s, d.y * c - d.x * s);
-    else
-      return mk2(d.x * c - d.y * s, d.y * c + d.x * s);
+    if constexpr (j == 4) {  // c == s: 2 adds + 2 multiplies
+      if constexpr (SIGN < 0)
+        return mk2((d.x + d.y) * c, (d.y - d.x) * c);
+      else
+        return mk2((d.x - d.y) * c, (d.y + d.x) * c);
+    } else if constexpr (j == 12) {  // c == -s
+      if constexpr (SIGN < 0)
+        return mk2((d.y - d.x) * s, -((d.x + d.y) * s));
+      else
+        return mk2(-((d.x + d.y) * s), (d.x - d.y) * s);
+    } else if constexpr (SIGN < 0) {
+      return mk2(fma_(d.x, c, d.y * s), fma_(d.y, c, -(d.x * s)));
+    } else {
+      return mk2(fma_(d.x, c, -(d.y * s)), fma_(d.y, c, d.x * s));
+    }
   }
 }
 

@@ -33,6 +33,8 @@ struct K1Args {
   const double2* tw;  // twiddle tables (global)
   int NJ;             // local rows
   int npairs;         // NJ/2
+  int group;          // consecutive row pairs per work unit (tuning)
+  int prefetch;       // 0 off, 1: bulk L2 prefetch of the next pair's rows
 };
 
 template <class C>
@@ -45,48 +47,66 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
   c.sync();
   const int g = c.tid / T, t = c.tid % T;
   double2* sm = sm_all + (size_t)C::SMN * g;
+  // A CTA works on units of `group` consecutive blocks of FPC row pairs (group > 1 makes its 32-byte transposed
+  // stores fill whole 128-byte lines of T within a short time).  While it transforms one block, the rows of the
+  // block it will transform next are prefetched into L2 by a single bulk-prefetch instruction, so HBM keeps
+  // streaming during the compute phase and the next register loads are L2 hits.
+  const int G = a.group;
   const int nblocks = (a.npairs + C::FPC - 1) / C::FPC;
-  for (int pb = c.bid; pb < nblocks; pb += c.nblk) {
-    const int pair = pb * C::FPC + g;
-    const bool active = pair < a.npairs;
-    const int jl = 2 * pair;
-    double2 v[E];
-    {
-      constexpr int r = 1 << C::bits(0), l = C::lo(0);
-      const double* r0 = a.w + (size_t)(jl + 1) * N;
-      const double* r1 = r0 + N;
-      static_for<0, E / r>([&](auto u_) {
-        constexpr int u = decltype(u_)::value;
-        int low;
-        const int bp = F::template base_pos<0>(t, u, low);
-        static_for<0, r>([&](auto q_) {
-          constexpr int q = decltype(q_)::value;
-          const int pos = bp | (q << l);
-          v[u * r + q] = active ? mk2(ld_stream1(r0 + pos), ld_stream1(r1 + pos)) : mk2(0.0, 0.0);
-        });
-      });
-    }
-    F::forward(c, v, sm, tw, t);
-    F::template store_smem<P - 1>(v, sm, t);
-    c.sync();
-    if (active) {
-      for (int idx = t; idx < N / 2; idx += T) {
-        const int pos = halfspec_pos<C>(idx);
-        const int k = F::k_of_pos(pos);
-        double2 o0, o1;
-        if (k == 0) {
-          const double2 z0 = sm[F::addr(0)], zh = sm[F::addr(F::pos_of_k(N / 2))];
-          o0 = mk2(2.0 * z0.x, 2.0 * zh.x);
-          o1 = mk2(2.0 * z0.y, 2.0 * zh.y);
-        } else {
-          const double2 zk = sm[F::addr(pos)], zm = sm[F::addr(F::pos_of_k(N - k))];
-          o0 = mk2(zk.x + zm.x, zk.y - zm.y);  // 2 X_j[k]   = Z[k] + conj Z[N-k]
-          o1 = mk2(zk.y + zm.y, zm.x - zk.x);  // 2 X_j+1[k] = -i (Z[k] - conj Z[N-k])
+  const int nunits = (nblocks + G - 1) / G;
+  for (int un = c.bid; un < nunits; un += c.nblk) {
+    for (int sub = 0; sub < G; sub++) {
+      const int pb = un * G + sub;
+      if (pb >= nblocks) break;
+      if (a.prefetch && c.tid == 0) {
+        const int nb = (sub + 1 < G && pb + 1 < nblocks) ? pb + 1 : (un + c.nblk) * G;  // next block of this CTA
+        if (nb < nblocks) {
+          const int p0 = nb * C::FPC;
+          const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
+          prefetch_l2_bulk(a.w + (size_t)(2 * p0 + 1) * N, (unsigned)(np * 2 * N * sizeof(double)));
         }
-        st_stream4(a.T + (size_t)k * a.NJ + jl, o0, o1);
       }
+      const int pair = pb * C::FPC + g;
+      const bool active = pair < a.npairs;
+      const int jl = 2 * pair;
+      double2 v[E];
+      {
+        constexpr int r = 1 << C::bits(0), l = C::lo(0);
+        const double* r0 = a.w + (size_t)(jl + 1) * N;
+        const double* r1 = r0 + N;
+        static_for<0, E / r>([&](auto u_) {
+          constexpr int u = decltype(u_)::value;
+          int low;
+          const int bp = F::template base_pos<0>(t, u, low);
+          static_for<0, r>([&](auto q_) {
+            constexpr int q = decltype(q_)::value;
+            const int pos = bp | (q << l);
+            v[u * r + q] = active ? mk2(ld_stream1(r0 + pos), ld_stream1(r1 + pos)) : mk2(0.0, 0.0);
+          });
+        });
+      }
+      F::forward(c, v, sm, tw, t);
+      F::template store_smem<P - 1>(v, sm, t);
+      c.sync();
+      if (active) {
+        for (int idx = t; idx < N / 2; idx += T) {
+          const int pos = halfspec_pos<C>(idx);
+          const int k = F::k_of_pos(pos);
+          double2 o0, o1;
+          if (k == 0) {
+            const double2 z0 = sm[F::addr(0)], zh = sm[F::addr(F::pos_of_k(N / 2))];
+            o0 = mk2(2.0 * z0.x, 2.0 * zh.x);
+            o1 = mk2(2.0 * z0.y, 2.0 * zh.y);
+          } else {
+            const double2 zk = sm[F::addr(pos)], zm = sm[F::addr(F::pos_of_k(N - k))];
+            o0 = mk2(zk.x + zm.x, zk.y - zm.y);  // 2 X_j[k]   = Z[k] + conj Z[N-k]
+            o1 = mk2(zk.y + zm.y, zm.x - zk.x);  // 2 X_j+1[k] = -i (Z[k] - conj Z[N-k])
+          }
+          st_stream4(a.T + (size_t)k * a.NJ + jl, o0, o1);
+        }
+      }
+      c.sync();
     }
-    c.sync();
   }
 }
 
@@ -100,6 +120,7 @@ struct K2Args {
   double scale;         // sign / (2 N^2): ifft normalisation, the factor 2 of the unpack, f = -w
   int NJ, log2NJ;
   int row0, nrows;      // kx rows owned by this rank
+  int prefetch;         // 0 off, 1: bulk L2 prefetch of the next row (single rank only)
 };
 
 template <class C>
@@ -119,6 +140,12 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
     const bool active = row < a.nrows;
     const int kx = a.row0 + row;
     const bool cta_has_row0 = (a.row0 + rb * C::FPC) == 0;
+    if (a.prefetch && c.tid == 0 && rb + c.nblk < nblocks && a.log2NJ == M) {  // single rank: the next rows are contiguous
+      const int r0n = (rb + c.nblk) * C::FPC;
+      const int nr = (a.nrows - r0n) < C::FPC ? (a.nrows - r0n) : C::FPC;
+      prefetch_l2_bulk(reinterpret_cast<const double2*>(a.T.p[0]) + (size_t)(a.row0 + r0n) * a.NJ,
+                       (unsigned)(nr * N * sizeof(double2)));
+    }
     double2 v[E];
     {
       constexpr int r = 1 << C::bits(0), l = C::lo(0);
@@ -173,15 +200,21 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
       }
       c.sync();
     } else {
+      // all divisor loads first (independent, L1/L2 hits), then branch-free reciprocals: the literal
+      // load -> add -> IEEE-reciprocal chain per element serialised 32 L2 latencies per thread
       const double ab = a.aa + ld_ro(a.bbcos + (active ? kx : 1));
+      double dd[E];
       static_for<0, E / rl>([&](auto u_) {
         constexpr int u = decltype(u_)::value;
         const int kb = F::k_of_pos((t + T * u) << bl);
         static_for<0, rl>([&](auto p_) {
           constexpr int p = decltype(p_)::value;
-          const int k = kb | (p << (M - bl));
-          v[u * rl + p] = cscale(v[u * rl + p], a.scale * rcp_rn(ab + ld_ro(a.cccos + k)));
+          dd[u * rl + p] = ab + ld_ro(a.cccos + (kb | (p << (M - bl))));  // (aa + bb cos kx) + cc cos ky
         });
+      });
+      static_for<0, E>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        v[i] = cscale(v[i], a.scale * rcp_fast(dd[i]));
       });
     }
     F::inverse(c, v, sm, tw, t);
@@ -210,6 +243,8 @@ struct K3Args {
   double* lo_dst;     // where interior row 0 is mirrored: previous rank's top halo row (row NJ+1 there)
   double* hi_dst;     // where interior row NJ-1 is mirrored: next rank's bottom halo row (row 0 there)
   int NJ, npairs;
+  int group;          // consecutive row pairs per work unit (tuning)
+  int prefetch;       // 0 off, 1: per-line L2 prefetch of the next unit's T columns
 };
 
 template <class C>
@@ -222,50 +257,64 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
   c.sync();
   const int g = c.tid / T, t = c.tid % T;
   double2* sm = sm_all + (size_t)C::SMN * g;
+  // units of kGroup consecutive row pairs: the CTA reads whole 128-byte lines of every T row over the unit, and
+  // prefetches the lines of its next unit into L2 while it transforms the current one
+  const int G = a.group;
+  const int LPU = (G * C::FPC * 2 * (int)sizeof(double2) + 127) / 128;  // lines per T row per unit
   const int nblocks = (a.npairs + C::FPC - 1) / C::FPC;
-  for (int pb = c.bid; pb < nblocks; pb += c.nblk) {
-    const int pair = pb * C::FPC + g;
-    const bool active = pair < a.npairs;
-    const int jl = 2 * pair;
-    if (active) {
-      for (int idx = t; idx < N / 2; idx += T) {
-        const int pos = halfspec_pos<C>(idx);
-        const int k = F::k_of_pos(pos);
-        double2 ua, ub;
-        ld_stream4(a.T + (size_t)k * a.NJ + jl, ua, ub);
-        if (k == 0) {
-          sm[F::addr(0)] = mk2(ua.x, ub.x);                      // Z[0]   = u0_j + i u0_j+1
-          sm[F::addr(F::pos_of_k(N / 2))] = mk2(ua.y, ub.y);     // Z[N/2] = uN2_j + i uN2_j+1
-        } else {
-          sm[F::addr(pos)] = mk2(ua.x - ub.y, ua.y + ub.x);                  // U_j[k] + i U_j+1[k]
-          sm[F::addr(F::pos_of_k(N - k))] = mk2(ua.x + ub.y, ub.x - ua.y);   // conj U_j[k] + i conj U_j+1[k]
+  const int nunits = (nblocks + G - 1) / G;
+  for (int un = c.bid; un < nunits; un += c.nblk) {
+    if (a.prefetch && un + c.nblk < nunits) {
+      const double2* nxt = a.T + (size_t)2 * (un + c.nblk) * G * C::FPC;
+      for (int idx = c.tid; idx < (N / 2) * LPU; idx += C::CT)
+        prefetch_l2(nxt + (size_t)(idx / LPU) * a.NJ + (idx % LPU) * 8);
+    }
+    for (int sub = 0; sub < G; sub++) {
+      const int pb = un * G + sub;
+      if (pb >= nblocks) break;
+      const int pair = pb * C::FPC + g;
+      const bool active = pair < a.npairs;
+      const int jl = 2 * pair;
+      if (active) {
+        for (int idx = t; idx < N / 2; idx += T) {
+          const int pos = halfspec_pos<C>(idx);
+          const int k = F::k_of_pos(pos);
+          double2 ua, ub;
+          ld_stream4(a.T + (size_t)k * a.NJ + jl, ua, ub);
+          if (k == 0) {
+            sm[F::addr(0)] = mk2(ua.x, ub.x);                   // Z[0]   = u0_j + i u0_j+1
+            sm[F::addr(F::pos_of_k(N / 2))] = mk2(ua.y, ub.y);  // Z[N/2] = uN2_j + i uN2_j+1
+          } else {
+            sm[F::addr(pos)] = mk2(ua.x - ub.y, ua.y + ub.x);                 // U_j[k] + i U_j+1[k]
+            sm[F::addr(F::pos_of_k(N - k))] = mk2(ua.x + ub.y, ub.x - ua.y);  // conj U_j[k] + i conj U_j+1[k]
+          }
         }
       }
-    }
-    c.sync();
-    double2 v[E];
-    F::template load_smem<P - 1>(v, sm, t);
-    F::inverse(c, v, sm, tw, t);
-    if (active) {
-      constexpr int r = 1 << C::bits(0), l = C::lo(0);
-      double* r0 = a.psi + (size_t)(jl + 1) * N;
-      double* r1 = r0 + N;
-      const bool first = (jl == 0), last = (jl + 2 == a.NJ);
-      static_for<0, E / r>([&](auto u_) {
-        constexpr int u = decltype(u_)::value;
-        int low;
-        const int bp = F::template base_pos<0>(t, u, low);
-        static_for<0, r>([&](auto q_) {
-          constexpr int q = decltype(q_)::value;
-          const int pos = bp | (q << l);
-          st_stream1(r0 + pos, v[u * r + q].x);
-          st_stream1(r1 + pos, v[u * r + q].y);
-          if (first) st_stream1(a.lo_dst + pos, v[u * r + q].x);
-          if (last) st_stream1(a.hi_dst + pos, v[u * r + q].y);
+      c.sync();
+      double2 v[E];
+      F::template load_smem<P - 1>(v, sm, t);
+      F::inverse(c, v, sm, tw, t);
+      if (active) {
+        constexpr int r = 1 << C::bits(0), l = C::lo(0);
+        double* r0 = a.psi + (size_t)(jl + 1) * N;
+        double* r1 = r0 + N;
+        const bool first = (jl == 0), last = (jl + 2 == a.NJ);
+        static_for<0, E / r>([&](auto u_) {
+          constexpr int u = decltype(u_)::value;
+          int low;
+          const int bp = F::template base_pos<0>(t, u, low);
+          static_for<0, r>([&](auto q_) {
+            constexpr int q = decltype(q_)::value;
+            const int pos = bp | (q << l);
+            st_stream1(r0 + pos, v[u * r + q].x);
+            st_stream1(r1 + pos, v[u * r + q].y);
+            if (first) st_stream1(a.lo_dst + pos, v[u * r + q].x);
+            if (last) st_stream1(a.hi_dst + pos, v[u * r + q].y);
+          });
         });
-      });
+      }
+      c.sync();
     }
-    c.sync();
   }
 }
 
@@ -284,85 +333,124 @@ struct K4Args {
   double dt;
 };
 constexpr int kK4Threads = 128;
+constexpr int kK4Cols = 4;  // grid columns per thread
 
-// r at one point from the 3x3 neighbourhoods (index [dj+1][di+1]); expression shapes of Common.jl:155-180
-VMK_HD double rhs_point(const double (&w)[3][3], const double (&s)[3][3], const K4Args& a) {
-  const double j1 = (w[1][2] - w[1][0]) * (s[2][1] - s[0][1]) - (w[2][1] - w[0][1]) * (s[1][2] - s[1][0]);
-  const double j2 = w[1][2] * (s[2][2] - s[0][2]) - w[1][0] * (s[2][0] - s[0][0]) - w[2][1] * (s[2][2] - s[2][0]) +
-                    w[0][1] * (s[0][2] - s[0][0]);
-  const double j3 = w[2][2] * (s[2][1] - s[1][2]) - w[0][0] * (s[1][0] - s[0][1]) - w[2][0] * (s[2][1] - s[1][0]) +
-                    w[0][2] * (s[1][2] - s[0][1]);
-  const double jac = a.gg * (j1 + j2 + j3) * a.hh;
-  return -jac + (a.aa * (w[1][2] - 2.0 * w[1][1] + w[1][0]) + a.bb * (w[2][1] - 2.0 * w[1][1] + w[0][1]));
+// x / 3 with three FP64 instructions instead of a division sequence: q = x*(1/3), one exact-residual
+// correction step (Markstein); equal to the correctly rounded quotient of vm.jl:63
+VMK_HD double div3(double x) {
+  const double third = 1.0 / 3.0;
+  const double q = x * third;
+  return fma_(fma_(-3.0, q, x), third, q);
 }
 
 // MODE 0: out = r (vm_rhs);  1: wn + dt r;  2: .75 wn + .25 wt + (.25 dt) r;  3: wn/3 + (2/3) wt + ((2/3) dt) r
 template <int MODE>
 VMK_HD double rk_combine(double wn, double wt, double r, double dt) {
   if constexpr (MODE == 0) return r;
-  if constexpr (MODE == 1) return wt + dt * r;  // stage 1: the stencil input IS wn (vm.jl:28)
-  if constexpr (MODE == 2) return .75 * wn + .25 * wt + (.25 * dt) * r;             // vm.jl:43-47
-  return wn / 3. + (2. / 3.) * wt + ((2. / 3.) * dt) * r;                           // vm.jl:62-66
+  if constexpr (MODE == 1) return fma_(dt, r, wt);  // stage 1: the stencil input IS wn (vm.jl:28)
+  if constexpr (MODE == 2) return fma_(.25 * dt, r, fma_(.25, wt, .75 * wn));   // vm.jl:43-47
+  return fma_((2. / 3.) * dt, r, fma_(2. / 3., wt, div3(wn)));                  // vm.jl:62-66
 }
 
-// Each thread owns two adjacent columns (i, i+1) and marches rows_per_cta rows, keeping a rolling
-// 3-row x 4-column window of w and psi in registers; i wraps periodically, j uses the halo rows.
+VMK_HD void ld4(const double* p, double& a, double& b, double& c, double& d) {
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#else
+  a = p[0];
+  b = p[1];
+  c = p[2];
+  d = p[3];
+#endif
+}
+VMK_HD void st4(double* p, double a, double b, double c, double d) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
+  p[0] = a;
+  p[1] = b;
+  p[2] = c;
+  p[3] = d;
+#endif
+}
+
+// Each thread owns four adjacent columns (one 32-byte load per row and field) and marches rows_per_cta rows with a
+// rolling 3-row x 6-column window of w and psi in registers; the row after next is already in flight while the
+// current one is evaluated.  i wraps periodically by index, j uses the slab's halo rows.
+//
+// Arithmetic: the Arakawa terms j1+j2+j3 of Common.jl:155-172 are accumulated as one chain of 10 products with
+// FMAs, sharing the vertical psi differences between neighbouring columns (27 FP64 instructions per point instead
+// of 45: the FP64 pipe, not HBM, was the limiter of the literal form).  The reference evaluates this loop under
+// @fastmath, i.e. it leaves association and contraction to the compiler as well; results differ from the unfused
+// oracle at the 1e-16 level.
 template <int MODE>
 VMK_HD void k4_body(const Ctx& c, const K4Args& a) {
   const int N = a.N;
-  const int cols = N / 2;                                        // column pairs
-  const int tw = cols < kK4Threads ? cols : kK4Threads;          // threads across i
-  const int groups = kK4Threads / tw;                            // row groups per CTA
-  const int ctas_x = cols / tw;
+  const int cols = N / kK4Cols;
+  const int tx = cols < kK4Threads ? cols : kK4Threads;  // threads across i
+  const int groups = kK4Threads / tx;                    // row groups per CTA
+  const int ctas_x = cols / tx;
   const int bx = c.bid % ctas_x, by = c.bid / ctas_x;
-  const int i0 = 2 * (bx * tw + c.tid % tw);
-  const int grp = c.tid / tw;
+  const int i0 = kK4Cols * (bx * tx + c.tid % tx);
+  const int grp = c.tid / tx;
   const int jbeg = (by * groups + grp) * a.rows_per_cta;
   if (jbeg >= a.NJ) return;
   const int jend = (jbeg + a.rows_per_cta < a.NJ) ? jbeg + a.rows_per_cta : a.NJ;
-  const int im = (i0 - 1) & (N - 1), ip = (i0 + 2) & (N - 1);
+  const int im = (i0 - 1) & (N - 1), ip = (i0 + kK4Cols) & (N - 1);
+  const double gh = a.gg * a.hh;
 
-  double W[3][4], S[3][4];  // [row: j-1, j, j+1][col: i-1, i, i+1, i+2]
-  auto load_row = [&](int jl_halo /*slab row index incl. halo offset*/, double (&wr)[4], double (&sr)[4]) {
-    const double* pw = a.w + (size_t)jl_halo * N;
-    const double* ps = a.psi + (size_t)jl_halo * N;
-    const double2 wc = *reinterpret_cast<const double2*>(pw + i0);
-    const double2 sc = *reinterpret_cast<const double2*>(ps + i0);
-    wr[0] = pw[im]; wr[1] = wc.x; wr[2] = wc.y; wr[3] = pw[ip];
-    sr[0] = ps[im]; sr[1] = sc.x; sr[2] = sc.y; sr[3] = ps[ip];
+  double W[3][6], S[3][6], Wp[6], Sp[6];  // [row: j-1, j, j+1][col: i-1 .. i+4]
+  auto load_row = [&](int row /*slab row incl. halo offset*/, double (&wr)[6], double (&sr)[6]) {
+    const double* pw = a.w + (size_t)row * N;
+    const double* ps = a.psi + (size_t)row * N;
+    ld4(pw + i0, wr[1], wr[2], wr[3], wr[4]);
+    ld4(ps + i0, sr[1], sr[2], sr[3], sr[4]);
+    wr[0] = pw[im];
+    wr[5] = pw[ip];
+    sr[0] = ps[im];
+    sr[5] = ps[ip];
   };
-  load_row(jbeg, W[0], S[0]);      // j-1 of the first row (slab row jbeg = interior jbeg-1 + 1)
+  load_row(jbeg, W[0], S[0]);  // slab row jbeg = interior row jbeg-1
   load_row(jbeg + 1, W[1], S[1]);
+  load_row(jbeg + 2, W[2], S[2]);
   for (int jl = jbeg; jl < jend; jl++) {
-    load_row(jl + 2, W[2], S[2]);
-    double wn0 = 0.0, wn1 = 0.0;
-    if constexpr (MODE >= 2) {
-      const double2 t2 = *reinterpret_cast<const double2*>(a.wn + (size_t)(jl + 1) * N + i0);
-      wn0 = t2.x;
-      wn1 = t2.y;
+    if (jl + 1 < jend) load_row(jl + 3, Wp, Sp);
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+    if constexpr (MODE >= 2) ld4(a.wn + (size_t)(jl + 1) * N + i0, n0, n1, n2, n3);
+    const double wnv[4] = {n0, n1, n2, n3};
+    double dv[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) dv[q] = S[2][q] - S[0][q];
+    double o[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const double wc = W[1][e + 1], we = W[1][e + 2], ww = W[1][e], wno = W[2][e + 1], wso = W[0][e + 1];
+      const double sn = S[2][e + 1], ss = S[0][e + 1], se = S[1][e + 2], sw = S[1][e];
+      double acc = (we - ww) * dv[e + 1];                      // j1, Common.jl:155-158
+      acc = fma_(-(wno - wso), se - sw, acc);
+      acc = fma_(we, dv[e + 2], acc);                          // j2, :160-165
+      acc = fma_(-ww, dv[e], acc);
+      acc = fma_(-wno, S[2][e + 2] - S[2][e], acc);
+      acc = fma_(wso, S[0][e + 2] - S[0][e], acc);
+      acc = fma_(W[2][e + 2], sn - se, acc);                   // j3, :167-172
+      acc = fma_(-W[0][e], sw - ss, acc);
+      acc = fma_(-W[2][e], sn - sw, acc);
+      acc = fma_(W[0][e + 2], se - ss, acc);
+      const double lapx = fma_(-2.0, wc, we + ww), lapy = fma_(-2.0, wc, wno + wso);
+      const double r = fma_(-gh, acc, fma_(a.aa, lapx, a.bb * lapy));  // :174-180
+      o[e] = rk_combine<MODE>(wnv[e], wc, r, a.dt);
     }
-    double o[2];
+    double* po = a.out + (size_t)(jl + 1) * N + i0;
+    st4(po, o[0], o[1], o[2], o[3]);
+    if (jl == 0) st4(a.lo_dst + i0, o[0], o[1], o[2], o[3]);
+    if (jl == a.NJ - 1) st4(a.hi_dst + i0, o[0], o[1], o[2], o[3]);
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      double w9[3][3], s9[3][3];
-#pragma unroll
-      for (int dj = 0; dj < 3; dj++)
-#pragma unroll
-        for (int di = 0; di < 3; di++) {
-          w9[dj][di] = W[dj][e + di];
-          s9[dj][di] = S[dj][e + di];
-        }
-      const double r = rhs_point(w9, s9, a);
-      o[e] = rk_combine<MODE>(e ? wn1 : wn0, W[1][e + 1], r, a.dt);
-    }
-    const double2 ov = mk2(o[0], o[1]);
-    *reinterpret_cast<double2*>(a.out + (size_t)(jl + 1) * N + i0) = ov;
-    if (jl == 0) *reinterpret_cast<double2*>(a.lo_dst + i0) = ov;
-    if (jl == a.NJ - 1) *reinterpret_cast<double2*>(a.hi_dst + i0) = ov;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      W[0][q] = W[1][q]; W[1][q] = W[2][q];
-      S[0][q] = S[1][q]; S[1][q] = S[2][q];
+    for (int q = 0; q < 6; q++) {
+      W[0][q] = W[1][q];
+      W[1][q] = W[2][q];
+      W[2][q] = Wp[q];
+      S[0][q] = S[1][q];
+      S[1][q] = S[2][q];
+      S[2][q] = Sp[q];
     }
   }
 }

@@ -1,0 +1,121 @@
+# CommonB200.jl -- drop-in replacements for the vortex-merger functions of CFD_Julia's Common.jl / vm.jl / tgv.jl,
+# implemented by ccall into libvmk.so (hand-written sm_100a CUDA kernels behind the C ABI of include/vmk.h).
+#
+#   include("CommonB200.jl"); using .CommonB200
+#   fps(nx, ny, Δx, Δy, u, e, data, data1, f, s, ε)          replaces Common.jl:97-125
+#   vm_rhs(nx, ny, Δx, Δy, re, w, u, e, data, data1, r, s, f) replaces Common.jl:132-182
+#   numerical(nx, ny, nt, Δx, Δy, Δt, re, x, y, wn, ns)       replaces 19_NS2D_Vortex_Merger/vm.jl:12-90
+#   numerical(nx, ny, nt, Δx, Δy, Δt, re, wn)                 replaces 19_NS2D_Vortex_Merger/tgv.jl:13-79
+#   ps_fft(nx, ny, Δx, Δy, f, ε)                              replaces 12_Poisson_Solver_FFT/fft_p.jl:8-42
+#
+# Same positional arguments, same in-place mutation, same return values, Array{Float64,2} throughout.  The dead
+# scratch arguments u, e, data, data1 are accepted and ignored (the reference never reads them either: `e` is
+# rebound at Common.jl:117 and `u` is untouched).  The library path comes from ENV["VMK_LIB"] or the repo layout.
+#
+# Julia is not installed in the build container, so this file is exercised only where a Julia binary exists;
+# the same ABI is exercised in CI through ctypes (cfd_julia_b200/common.py), which this file mirrors line by line.
+module CommonB200
+
+export fps, vm_rhs, numerical, ps_fft, vmk_plan, vmk_upload, vmk_step, vmk_download
+
+const libvmk = get(ENV, "VMK_LIB", joinpath(@__DIR__, "..", "cfd_julia_b200", "libvmk.so"))
+
+mutable struct Plan
+  handle::Ptr{Cvoid}
+end
+
+const PLANS = Dict{Tuple{Int,Int},Plan}()
+
+lasterror() = unsafe_string(ccall((:vmk_last_error, libvmk), Cstring, ()))
+check(rc::Cint) = rc == 0 ? nothing : error("vmk error $rc: $(lasterror())")
+
+# the reference API has no plan object: cache one per grid size (device buffers, tables, stream, CUDA graph)
+vmk_plan(nx::Integer, ny::Integer) = get!(PLANS, (Int(nx), Int(ny))) do
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:vmk_plan_create, libvmk), Cint, (Int64, Int64, Ptr{Ptr{Cvoid}}), nx, ny, h))
+  p = Plan(h[])
+  finalizer(q -> ccall((:vmk_plan_destroy, libvmk), Cint, (Ptr{Cvoid},), q.handle), p)
+  p
+end
+
+ghosted(a, nx, ny, name) = size(a) == (nx + 2, ny + 2) || throw(BoundsError(a, (nx + 2, ny + 2)))
+
+fps(nx, ny, Δx, Δy, u, e, data, data1, f::Matrix{Float64}, s::Matrix{Float64}, ε=1.e-6) = begin
+  size(f) == (nx, ny) || throw(BoundsError(f, (nx, ny)))
+  ghosted(s, nx, ny, "s")
+  check(ccall((:vmk_fps, libvmk), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble),
+              vmk_plan(nx, ny).handle, Δx, Δy, f, s, ε))
+  return
+end
+
+ps_fft(nx, ny, Δx, Δy, f::Matrix{Float64}, ε) = begin
+  size(f) == (nx + 1, ny + 1) || throw(BoundsError(f, (nx + 1, ny + 1)))
+  u = Array{Float64}(undef, nx, ny)
+  check(ccall((:vmk_ps_fft, libvmk), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble),
+              vmk_plan(nx, ny).handle, Δx, Δy, f, u, ε))
+  return u
+end
+
+vm_rhs(nx, ny, Δx, Δy, re, w::Matrix{Float64}, u, e, data, data1, r::Matrix{Float64}, s::Matrix{Float64},
+       f::Matrix{Float64}) = begin
+  ghosted(w, nx, ny, "w"); ghosted(r, nx, ny, "r"); ghosted(s, nx, ny, "s")
+  size(f) == (nx, ny) || throw(BoundsError(f, (nx, ny)))
+  check(ccall((:vmk_rhs, libvmk), Cint,
+              (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+              vmk_plan(nx, ny).handle, Δx, Δy, re, w, r, s, f))
+  return
+end
+
+# snapshot trampoline: the C side brings wn to the host and calls back with the step number
+function snap_trampoline(k::Int64, wn::Ptr{Cdouble}, user::Ptr{Cvoid})::Cvoid
+  f = unsafe_pointer_to_objref(user)::Base.RefValue{Function}
+  f[](k)
+  return
+end
+
+# vm.jl flavour: writes "vm<m>.txt" every nt ÷ ns steps like vm.jl:78-86 (the record index is incremented here; the
+# reference forgets to and overwrites vm1.txt ten times, compare hybrid.jl:81)
+numerical(nx, ny, nt, Δx, Δy, Δt, re, x, y, wn::Matrix{Float64}, ns) = begin
+  ghosted(wn, nx, ny, "wn")
+  freq = nt ÷ ns
+  m = Ref(1)
+  cb = Ref{Function}(k -> begin
+    @show k
+    open("vm$(m[]).txt", "w") do io
+      for j ∈ 1:ny + 1 for i ∈ 1:nx + 1
+        write(io, "$(x[i]) $(y[j]) $(wn[i + 1, j + 1])\n")
+      end end
+    end
+    m[] += 1
+  end)
+  out = Array{Float64}(undef, nx + 1, ny + 1)
+  GC.@preserve cb begin
+    check(ccall((:vmk_numerical, libvmk), Cint,
+                (Ptr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cvoid},
+                 Ptr{Cvoid}),
+                vmk_plan(nx, ny).handle, nt, Δx, Δy, Δt, re, wn, out, freq,
+                @cfunction(snap_trampoline, Cvoid, (Int64, Ptr{Cdouble}, Ptr{Cvoid})), pointer_from_objref(cb)))
+  end
+  return out
+end
+
+# tgv.jl flavour: no snapshots
+numerical(nx, ny, nt, Δx, Δy, Δt, re, wn::Matrix{Float64}) = begin
+  ghosted(wn, nx, ny, "wn")
+  out = Array{Float64}(undef, nx + 1, ny + 1)
+  check(ccall((:vmk_numerical, libvmk), Cint,
+              (Ptr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cvoid},
+               Ptr{Cvoid}),
+              vmk_plan(nx, ny).handle, nt, Δx, Δy, Δt, re, wn, out, 0, C_NULL, C_NULL))
+  return out
+end
+
+# device-resident pieces, for callers that want to keep the field on the GPU between calls
+vmk_upload(p::Plan, wn::Matrix{Float64}) = check(ccall((:vmk_upload, libvmk), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), p.handle, wn))
+vmk_step(p::Plan, Δx, Δy, Δt, re, nsteps) =
+  check(ccall((:vmk_step, libvmk), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Cdouble, Int64), p.handle, Δx, Δy, Δt, re, nsteps))
+vmk_download(p::Plan, wn::Matrix{Float64}, psi::Union{Matrix{Float64},Nothing}=nothing) =
+  check(ccall((:vmk_download, libvmk), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), p.handle, wn,
+              psi === nothing ? C_NULL : pointer(psi)))
+
+end # module
