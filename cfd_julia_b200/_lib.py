@@ -79,9 +79,11 @@ def default_library() -> VmkLibrary:
     """The product library.  Built on first use if the sources are newer; never replaced by anything else."""
     global _default
     if _default is None:
-        so = _build.SO
-        if _build.stale():
-            so = _build.build()
+        so = os.environ.get("VMK_LIB")  # an explicitly chosen build of the same CUDA library (tuning experiments)
+        if not so:
+            so = _build.SO
+            if _build.stale():
+                so = _build.build()
         if not os.path.exists(so):
             raise RuntimeError("cfd_julia_b200: libvmk.so is missing and could not be built")
         _default = VmkLibrary(so, "vmk_")

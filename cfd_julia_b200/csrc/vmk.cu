@@ -69,6 +69,7 @@ struct SizeOps {
   size_t smem;      // dynamic shared memory of K1/K2/K3
   int fpc;          // transforms per CTA
   void (*fill_tw)(double2*);
+  void (*fill_ccperm)(const double* cccos, double* ccperm);
   int (*configure)(int* res_k1, int* res_k2, int* res_k3);
   int (*k1)(int grid, const K1Args&, Stream&);
   int (*k2)(int grid, const K2Args&, Stream&);
@@ -115,6 +116,16 @@ void fill_twiddles(double2* tw) {
   }
 }
 
+// cccos permuted into the register order of K2's divide (see K2Args::ccperm)
+template <class C>
+void fill_ccperm(const double* cccos, double* out) {
+  using F = Fft<C>;
+  constexpr int bl = C::bits(C::P - 1), rl = 1 << bl;
+  for (int u = 0; u < C::E / rl; u++)
+    for (int p = 0; p < rl; p++)
+      for (int t = 0; t < C::T; t++) out[(u * rl + p) * C::T + t] = cccos[F::k_of_pos(((t + C::T * u) << bl) | p)];
+}
+
 template <int M>
 SizeOps make_ops() {
   using C = typename CfgFor<M>::type;
@@ -123,6 +134,7 @@ SizeOps make_ops() {
   o.smem = C::SMEM_BYTES;
   o.fpc = C::FPC;
   o.fill_tw = &fill_twiddles<C>;
+  o.fill_ccperm = &fill_ccperm<C>;
   o.configure = [](int* r1, int* r2, int* r3) -> int {
     VMK_TRY((be_configure<K1Body<C>, K1Args, C::CT, C::MINB>(C::SMEM_BYTES, r1)));
     VMK_TRY((be_configure<K2Body<C>, K2Args, C::CT, C::MINB>(C::SMEM_BYTES, r2)));
@@ -178,6 +190,7 @@ struct vmk_plan {
   double2* tw = nullptr;
   double* bbcos = nullptr;
   double* cccos = nullptr;
+  double* ccperm = nullptr;
   double* staging = nullptr;  // (NJ+2) x (N+2), allocated on first host-array call
   int64_t dev_bytes = 0;
   // peers (slab decomposition): pointers to every rank's buffers, own entries included
@@ -196,7 +209,7 @@ struct vmk_plan {
   bool ev_valid = false;
   bool uploaded = false;
   int64_t launches = 0;
-  int k4_rows = 32;
+  int k4_rows = 32, k4_ahead = 4;
   int k1_group = 1, k3_group = 1, k1_prefetch = 1, k2_prefetch = 1, k3_prefetch = 0;
   int use_graph = 1;
 #ifndef VMK_EMUL
@@ -254,6 +267,9 @@ int ensure_divisor(vmk_plan* p, double dx, double dy, double eps) {
   VMK_TRY(be_sync(p->st));  // the tables may still be in use by queued kernels
   VMK_TRY(be_h2d(p->bbcos, b.data(), sizeof(double) * n, p->st));
   VMK_TRY(be_h2d(p->cccos, c.data(), sizeof(double) * n, p->st));
+  std::vector<double> cp(n);
+  p->ops.fill_ccperm(c.data(), cp.data());
+  VMK_TRY(be_h2d(p->ccperm, cp.data(), sizeof(double) * n, p->st));
   VMK_TRY(be_sync(p->st));
   p->div_aa = -2.0 / (dx * dx) - 2.0 / (dy * dy);  // :101
   p->div_dx = dx;
@@ -321,6 +337,7 @@ int launch_k2(vmk_plan* p, double sign) {
   a.tw = p->tw;
   a.bbcos = p->bbcos;
   a.cccos = p->cccos;
+  a.ccperm = p->ccperm;
   a.aa = p->div_aa;
   a.scale = sign / (2.0 * (double)p->N * (double)p->N);
   a.NJ = p->NJ;
@@ -370,6 +387,7 @@ int launch_k4(vmk_plan* p, int mode, int win, int wn, int out, const StepParams&
   a.log2N = p->M;
   a.NJ = p->NJ;
   a.rows_per_cta = p->k4_rows;
+  a.ahead = p->k4_ahead;
   a.aa = 1.0 / (sp.re * (sp.dx * sp.dx));  // Common.jl:149
   a.bb = 1.0 / (sp.re * (sp.dy * sp.dy));  // :150
   a.gg = 1.0 / (4.0 * sp.dx * sp.dy);      // :151
@@ -526,6 +544,7 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     if ((rc = dev_alloc(p, (void**)&p->tw, sizeof(double2) * (ops.twn ? ops.twn : 1)))) break;
     if ((rc = dev_alloc(p, (void**)&p->bbcos, sizeof(double) * p->N))) break;
     if ((rc = dev_alloc(p, (void**)&p->cccos, sizeof(double) * p->N))) break;
+    if ((rc = dev_alloc(p, (void**)&p->ccperm, sizeof(double) * p->N))) break;
     std::vector<double2> tw(ops.twn ? ops.twn : 1);
     ops.fill_tw(tw.data());
     if ((rc = be_h2d(p->tw, tw.data(), sizeof(double2) * tw.size(), p->st))) break;
@@ -563,6 +582,7 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_free(p->tw);
   be_free(p->bbcos);
   be_free(p->cccos);
+  be_free(p->ccperm);
   be_free(p->staging);
   be_event_destroy(p->ev0);
   be_event_destroy(p->ev1);
@@ -822,7 +842,8 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
   if (!p || !key) return fail(VMK_EARG, "NULL argument");
   const std::string k(key);
   int* knob = k == "k1_group" ? &p->k1_group : k == "k3_group" ? &p->k3_group : k == "k1_prefetch" ? &p->k1_prefetch
-              : k == "k2_prefetch" ? &p->k2_prefetch : k == "k3_prefetch" ? &p->k3_prefetch : nullptr;
+              : k == "k2_prefetch" ? &p->k2_prefetch : k == "k3_prefetch" ? &p->k3_prefetch
+              : k == "k4_ahead" ? &p->k4_ahead : nullptr;
   if (knob) {
     if (value < 0 || value > 64 || (value == 0 && k.find("group") != std::string::npos))
       return fail(VMK_EARG, "option value out of range");

@@ -96,13 +96,13 @@ struct Net<1, SIGN, OFF> {
 };
 
 // ---- configuration ---------------------------------------------------------------------------
-template <int M_, int LE_, int P_, int B0_, int B1_, int B2_, int CT_, int MINB_>
+template <int M_, int LE_, int P_, int B0_, int B1_, int B2_, int CT_, int MINB_, int B3_ = 0>
 struct FftCfg {
   static constexpr int M = M_, N = 1 << M_, LE = LE_, E = 1 << LE_, T = N >> LE_, P = P_;
   static constexpr int CT = CT_ > T ? CT_ : T;  // CTA threads
   static constexpr int FPC = CT / T;            // transforms per CTA
   static constexpr int MINB = MINB_;            // min CTAs per SM (launch bounds)
-  VMK_HD static constexpr int bits(int k) { return k == 0 ? B0_ : (k == 1 ? B1_ : B2_); }
+  VMK_HD static constexpr int bits(int k) { return k == 0 ? B0_ : (k == 1 ? B1_ : (k == 2 ? B2_ : B3_)); }
   VMK_HD static constexpr int hi(int k) {
     int h = M_;
     for (int m = 0; m < k; m++) h -= bits(m);
@@ -122,8 +122,8 @@ struct FftCfg {
   static constexpr int TWN = tw_off(P_);  // total table entries (complex)
   static constexpr size_t SMEM_DATA = sizeof(double2) * (size_t)SMN * FPC;
   static constexpr size_t SMEM_BYTES = SMEM_DATA + sizeof(double2) * (size_t)TWN;
-  static_assert(B0_ + B1_ + (P_ > 2 ? B2_ : 0) == M_, "pass bits must sum to M");
-  static_assert(B0_ <= LE_ && B1_ <= LE_ && B2_ <= LE_, "radix exceeds per-thread elements");
+  static_assert(B0_ + B1_ + (P_ > 2 ? B2_ : 0) + (P_ > 3 ? B3_ : 0) == M_, "pass bits must sum to M");
+  static_assert(B0_ <= LE_ && B1_ <= LE_ && B2_ <= LE_ && B3_ <= LE_, "radix exceeds per-thread elements");
 };
 
 // one configuration per supported size (32 .. 8192); radices grow towards the last
@@ -138,7 +138,11 @@ template <> struct CfgFor<9>  { using type = FftCfg<9, 4, 3, 3, 3, 3, 128, 4>; }
 template <> struct CfgFor<10> { using type = FftCfg<10, 4, 3, 3, 3, 4, 128, 4>; };
 template <> struct CfgFor<11> { using type = FftCfg<11, 4, 3, 3, 4, 4, 128, 3>; };
 template <> struct CfgFor<12> { using type = FftCfg<12, 4, 3, 4, 4, 4, 256, 2>; };
+#ifdef VMK_M13_T512
+template <> struct CfgFor<13> { using type = FftCfg<13, 4, 4, 3, 3, 3, 512, 1, 4>; };
+#else
 template <> struct CfgFor<13> { using type = FftCfg<13, 5, 3, 4, 4, 5, 256, 1>; };
+#endif
 
 // ---- the engine --------------------------------------------------------------------------------
 template <class C>

@@ -116,6 +116,8 @@ struct K2Args {
   const double2* tw;    // twiddle tables
   const double* bbcos;  // [N]  bb*cos(kx[i])   Common.jl:120 (kx[1]=eps quirk inside)
   const double* cccos;  // [N]  cc*cos(ky[j])   (ky = kx, Common.jl:113)
+  const double* ccperm; // cccos in the order the threads hold the spectrum after the forward pass:
+                        // ccperm[(u*r_last + p)*T + t] = cccos[k_of_pos(((t + T*u) << b_last) | p)]  (coalesced)
   double aa;            // -2/dx^2 - 2/dy^2
   double scale;         // sign / (2 N^2): ifft normalisation, the factor 2 of the unpack, f = -w
   int NJ, log2NJ;
@@ -209,7 +211,8 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
         const int kb = F::k_of_pos((t + T * u) << bl);
         static_for<0, rl>([&](auto p_) {
           constexpr int p = decltype(p_)::value;
-          dd[u * rl + p] = ab + ld_ro(a.cccos + (kb | (p << (M - bl))));  // (aa + bb cos kx) + cc cos ky
+          (void)kb;
+          dd[u * rl + p] = ab + ld_ro(a.ccperm + (u * rl + p) * T + t);  // (aa + bb cos kx) + cc cos ky
         });
       });
       static_for<0, E>([&](auto i_) {
@@ -328,6 +331,7 @@ struct K4Args {
   double* hi_dst;     // mirror of interior row NJ-1 (next rank's bottom halo row of `out`)
   int N, log2N, NJ;
   int rows_per_cta;   // rows marched by one thread column
+  int ahead;          // rows ahead of the march that are prefetched into L2 (0 = off)
   double aa, bb;      // 1/(re dx^2), 1/(re dy^2)     Common.jl:149-150
   double gg, hh;      // 1/(4 dx dy), 1/3             Common.jl:151-152
   double dt;
@@ -412,8 +416,15 @@ VMK_HD void k4_body(const Ctx& c, const K4Args& a) {
   load_row(jbeg, W[0], S[0]);  // slab row jbeg = interior row jbeg-1
   load_row(jbeg + 1, W[1], S[1]);
   load_row(jbeg + 2, W[2], S[2]);
+  const bool pf_lane = a.ahead > 0 && (c.tid & 3) == 0;  // one lane per 128-byte line
   for (int jl = jbeg; jl < jend; jl++) {
     if (jl + 1 < jend) load_row(jl + 3, Wp, Sp);
+    if (pf_lane && jl + a.ahead < jend) {  // turn the DRAM latency of the rows further down into an L2 hit
+      const size_t off = (size_t)(jl + 2 + a.ahead) * N + i0;
+      prefetch_l2(a.w + off);
+      prefetch_l2(a.psi + off);
+      if constexpr (MODE >= 2) prefetch_l2(a.wn + off - N);
+    }
     double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
     if constexpr (MODE >= 2) ld4(a.wn + (size_t)(jl + 1) * N + i0, n0, n1, n2, n3);
     const double wnv[4] = {n0, n1, n2, n3};

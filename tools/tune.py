@@ -28,24 +28,11 @@ def main():
               f"  step={ms:.3f} ms", flush=True)
 
     measure("defaults")
-    for g, pf in itertools.product((1, 2, 4), (0, 1)):
-        p.set_option("k1_group", g)
-        p.set_option("k1_prefetch", pf)
-        measure(f"k1_group={g} k1_prefetch={pf}")
-    p.set_option("k1_group", 1)
-    p.set_option("k1_prefetch", 1)
-    for pf in (0, 1):
-        p.set_option("k2_prefetch", pf)
-        measure(f"k2_prefetch={pf}")
-    for g, pf in ((1, 0), (2, 0), (4, 0), (4, 1), (8, 1)):
-        p.set_option("k3_group", g)
-        p.set_option("k3_prefetch", pf)
-        measure(f"k3_group={g} k3_prefetch={pf}")
-    p.set_option("k3_group", 1)
-    p.set_option("k3_prefetch", 0)
-    for r in (8, 16, 32, 64, 128):
-        p.set_option("k4_rows", r)
-        measure(f"k4_rows={r}")
+    for arg in sys.argv[2:]:
+        for kv in arg.split(","):
+            k, v = kv.split("=")
+            p.set_option(k, int(v))
+        measure(arg)
 
 
 if __name__ == "__main__":
