@@ -321,9 +321,8 @@ int launch_k1(vmk_plan* p, const double* src) {
   a.tw = p->tw;
   a.NJ = p->NJ;
   a.npairs = p->NJ / 2;
-  a.group = p->k1_group;
   a.prefetch = p->k1_prefetch;
-  const int work = rowpair_units(p, a.npairs, a.group);
+  const int work = rowpair_units(p, a.npairs, 1);
   Timed t(p, KI_K1);
   VMK_TRY(p->ops.k1(work < p->res_k1 ? work : p->res_k1, a, p->st));
   t.done();

@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -125,6 +126,27 @@ VMK_HD void ld_stream4(const double2* p, double2& a, double2& b) {
 #else
   a = p[0];
   b = p[1];
+#endif
+}
+// Asynchronous 16-byte copy global -> shared (LDGSTS): no destination registers and no scoreboard wait, so a thread
+// can put the next row's loads in flight while its registers still hold the current row.  The data is visible to
+// the issuing thread after cp_async_wait_all(), to the rest of the CTA after a barrier on top of that.
+VMK_HD void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef __CUDA_ARCH__
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#else
+  memcpy(smem_dst, gsrc, 16);
+#endif
+}
+VMK_HD void cp_async_commit() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+VMK_HD void cp_async_wait_all() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
 }
 VMK_HD double ld_ro(const double* p) {

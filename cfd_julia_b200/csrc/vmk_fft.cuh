@@ -262,7 +262,11 @@ struct Fft {
     });
   }
   // registers hold last-pass layout on entry, pass-0 layout (natural positions) on exit
-  VMK_HD static void inverse(const Ctx& c, double2 (&v)[E], double2* sm, const double2* tw, int t) {
+  // `after_last_exchange` runs once the thread has read its pass-0 values back: from then on the thread's own
+  // pass-0 slots of the exchange buffer are free (the kernels start the next row's asynchronous loads there)
+  template <class Hook>
+  VMK_HD static void inverse(const Ctx& c, double2 (&v)[E], double2* sm, const double2* tw, int t,
+                             Hook&& after_last_exchange) {
     static_for<0, P>([&](auto k_) {
       constexpr int K = P - 1 - decltype(k_)::value;
       inv_compute<K>(v, tw, t);
@@ -270,8 +274,19 @@ struct Fft {
         store_smem<K>(v, sm, t);
         c.sync();
         load_smem<K - 1>(v, sm, t);
+        if constexpr (K == 1) after_last_exchange();
       }
     });
+  }
+  VMK_HD static void inverse(const Ctx& c, double2 (&v)[E], double2* sm, const double2* tw, int t) {
+    inverse(c, v, sm, tw, t, [] {});
+  }
+  // position of the thread's e-th register in the pass-0 layout (the slots a thread owns across iterations)
+  template <int e>
+  VMK_HD static int own_pos(int t) {
+    constexpr int r = 1 << C::bits(0), l = C::lo(0);
+    int low;
+    return base_pos<0>(t, e / r, low) | ((e % r) << l);
   }
 
   // spectral index held at position pos after forward(), and its inverse map

@@ -33,81 +33,89 @@ struct K1Args {
   const double2* tw;  // twiddle tables (global)
   int NJ;             // local rows
   int npairs;         // NJ/2
-  int group;          // consecutive row pairs per work unit (tuning)
-  int prefetch;       // 0 off, 1: bulk L2 prefetch of the next pair's rows
+  int prefetch;       // 0 off, 1: bulk L2 prefetch of the rows of the pair after next
 };
 
+// Per row pair: rows (already in the exchange buffer, put there asynchronously during the previous pair's store
+// phase) -> registers -> forward FFT -> spectrum to shared memory -> Z[k], Z[N-k] to registers -> start the
+// asynchronous copy of the next pair's rows -> unpack and transposed 32-byte stores.
 template <class C>
 VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
   using F = Fft<C>;
-  constexpr int N = C::N, E = C::E, T = C::T, P = C::P;
+  constexpr int N = C::N, E = C::E, T = C::T, P = C::P, NI = N / 2 / T;
   double2* sm_all = reinterpret_cast<double2*>(c.smem);
   double2* tw = sm_all + (size_t)C::SMN * C::FPC;
   F::load_tables(c, tw, a.tw);
   c.sync();
   const int g = c.tid / T, t = c.tid % T;
   double2* sm = sm_all + (size_t)C::SMN * g;
-  // A CTA works on units of `group` consecutive blocks of FPC row pairs (group > 1 makes its 32-byte transposed
-  // stores fill whole 128-byte lines of T within a short time).  While it transforms one block, the rows of the
-  // block it will transform next are prefetched into L2 by a single bulk-prefetch instruction, so HBM keeps
-  // streaming during the compute phase and the next register loads are L2 hits.
-  const int G = a.group;
   const int nblocks = (a.npairs + C::FPC - 1) / C::FPC;
-  const int nunits = (nblocks + G - 1) / G;
-  for (int un = c.bid; un < nunits; un += c.nblk) {
-    for (int sub = 0; sub < G; sub++) {
-      const int pb = un * G + sub;
-      if (pb >= nblocks) break;
-      if (a.prefetch && c.tid == 0) {
-        const int nb = (sub + 1 < G && pb + 1 < nblocks) ? pb + 1 : (un + c.nblk) * G;  // next block of this CTA
-        if (nb < nblocks) {
-          const int p0 = nb * C::FPC;
-          const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
-          prefetch_l2_bulk(a.w + (size_t)(2 * p0 + 1) * N, (unsigned)(np * 2 * N * sizeof(double)));
+  // the T threads of a transform copy its two rows (contiguous 2N doubles) as N 16-byte chunks
+  auto issue_rows = [&](int pb) {
+    const int pair = pb * C::FPC + g;
+    if (pb < nblocks && pair < a.npairs) {
+      const char* src = reinterpret_cast<const char*>(a.w + (size_t)(2 * pair + 1) * N);
+      char* dst = reinterpret_cast<char*>(sm);
+      static_for<0, E>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        cp_async16(dst + 16 * (t + T * i), src + 16 * (t + T * i));
+      });
+    }
+    cp_async_commit();
+  };
+  issue_rows(c.bid);
+  for (int pb = c.bid; pb < nblocks; pb += c.nblk) {
+    if (a.prefetch && c.tid == 0 && pb + 2 * c.nblk < nblocks) {
+      const int p0 = (pb + 2 * c.nblk) * C::FPC;
+      const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
+      prefetch_l2_bulk(a.w + (size_t)(2 * p0 + 1) * N, (unsigned)(np * 2 * N * sizeof(double)));
+    }
+    const int pair = pb * C::FPC + g;
+    const bool active = pair < a.npairs;
+    const int jl = 2 * pair;
+    cp_async_wait_all();
+    c.sync();
+    double2 v[E];
+    {
+      const double* r0 = reinterpret_cast<const double*>(sm);
+      const double* r1 = r0 + N;
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        const int pos = F::template own_pos<e>(t);
+        v[e] = active ? mk2(r0[pos], r1[pos]) : mk2(0.0, 0.0);
+      });
+    }
+    c.sync();  // all rows are in registers before the first exchange overwrites the buffer
+    F::forward(c, v, sm, tw, t);
+    F::template store_smem<P - 1>(v, sm, t);
+    c.sync();
+    double2 zk[NI], zm[NI];
+    static_for<0, NI>([&](auto i_) {
+      constexpr int i = decltype(i_)::value;
+      const int pos = halfspec_pos<C>(t + T * i);
+      const int k = F::k_of_pos(pos);
+      zk[i] = sm[F::addr(pos)];                                  // k == 0: Z[0]
+      zm[i] = sm[F::addr(F::pos_of_k(k == 0 ? N / 2 : N - k))];  // k == 0: Z[N/2]
+    });
+    c.sync();  // the spectrum is in registers: the buffer is free for the next pair's rows
+    issue_rows(pb + c.nblk);
+    if (active) {
+      static_for<0, NI>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        const int k = F::k_of_pos(halfspec_pos<C>(t + T * i));
+        double2 o0, o1;
+        if (k == 0) {
+          o0 = mk2(2.0 * zk[i].x, 2.0 * zm[i].x);
+          o1 = mk2(2.0 * zk[i].y, 2.0 * zm[i].y);
+        } else {
+          o0 = mk2(zk[i].x + zm[i].x, zk[i].y - zm[i].y);  // 2 X_j[k]   = Z[k] + conj Z[N-k]
+          o1 = mk2(zk[i].y + zm[i].y, zm[i].x - zk[i].x);  // 2 X_j+1[k] = -i (Z[k] - conj Z[N-k])
         }
-      }
-      const int pair = pb * C::FPC + g;
-      const bool active = pair < a.npairs;
-      const int jl = 2 * pair;
-      double2 v[E];
-      {
-        constexpr int r = 1 << C::bits(0), l = C::lo(0);
-        const double* r0 = a.w + (size_t)(jl + 1) * N;
-        const double* r1 = r0 + N;
-        static_for<0, E / r>([&](auto u_) {
-          constexpr int u = decltype(u_)::value;
-          int low;
-          const int bp = F::template base_pos<0>(t, u, low);
-          static_for<0, r>([&](auto q_) {
-            constexpr int q = decltype(q_)::value;
-            const int pos = bp | (q << l);
-            v[u * r + q] = active ? mk2(ld_stream1(r0 + pos), ld_stream1(r1 + pos)) : mk2(0.0, 0.0);
-          });
-        });
-      }
-      F::forward(c, v, sm, tw, t);
-      F::template store_smem<P - 1>(v, sm, t);
-      c.sync();
-      if (active) {
-        for (int idx = t; idx < N / 2; idx += T) {
-          const int pos = halfspec_pos<C>(idx);
-          const int k = F::k_of_pos(pos);
-          double2 o0, o1;
-          if (k == 0) {
-            const double2 z0 = sm[F::addr(0)], zh = sm[F::addr(F::pos_of_k(N / 2))];
-            o0 = mk2(2.0 * z0.x, 2.0 * zh.x);
-            o1 = mk2(2.0 * z0.y, 2.0 * zh.y);
-          } else {
-            const double2 zk = sm[F::addr(pos)], zm = sm[F::addr(F::pos_of_k(N - k))];
-            o0 = mk2(zk.x + zm.x, zk.y - zm.y);  // 2 X_j[k]   = Z[k] + conj Z[N-k]
-            o1 = mk2(zk.y + zm.y, zm.x - zk.x);  // 2 X_j+1[k] = -i (Z[k] - conj Z[N-k])
-          }
-          st_stream4(a.T + (size_t)k * a.NJ + jl, o0, o1);
-        }
-      }
-      c.sync();
+        st_stream4(a.T + (size_t)k * a.NJ + jl, o0, o1);
+      });
     }
   }
+  cp_async_wait_all();
 }
 
 // ======================================== K2 ====================================================
@@ -137,33 +145,41 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
   const int g = c.tid / T, t = c.tid % T;
   double2* sm = sm_all + (size_t)C::SMN * g;
   const int nblocks = (a.nrows + C::FPC - 1) / C::FPC;
+  // A thread owns the same E slots of the exchange buffer (its pass-0 positions) at the start and at the end of a
+  // row's transform, so the NEXT row is copied there asynchronously, element by element from the owning ranks,
+  // while the current row's last butterflies and stores run; no barrier is involved.
+  auto issue_row = [&](int rb) {
+    const int row = rb * C::FPC + g;
+    if (rb < nblocks && row < a.nrows) {
+      const int kx = a.row0 + row;
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        const int j = F::template own_pos<e>(t);
+        const double2* src =
+            reinterpret_cast<const double2*>(a.T.p[j >> a.log2NJ]) + (size_t)kx * a.NJ + (j & (a.NJ - 1));
+        cp_async16(sm + F::addr(j), src);
+      });
+    }
+    cp_async_commit();
+  };
+  issue_row(c.bid);
   for (int rb = c.bid; rb < nblocks; rb += c.nblk) {
     const int row = rb * C::FPC + g;
     const bool active = row < a.nrows;
     const int kx = a.row0 + row;
     const bool cta_has_row0 = (a.row0 + rb * C::FPC) == 0;
-    if (a.prefetch && c.tid == 0 && rb + c.nblk < nblocks && a.log2NJ == M) {  // single rank: the next rows are contiguous
-      const int r0n = (rb + c.nblk) * C::FPC;
+    if (a.prefetch && c.tid == 0 && rb + 2 * c.nblk < nblocks && a.log2NJ == M) {  // single rank: rows are contiguous
+      const int r0n = (rb + 2 * c.nblk) * C::FPC;
       const int nr = (a.nrows - r0n) < C::FPC ? (a.nrows - r0n) : C::FPC;
       prefetch_l2_bulk(reinterpret_cast<const double2*>(a.T.p[0]) + (size_t)(a.row0 + r0n) * a.NJ,
                        (unsigned)(nr * N * sizeof(double2)));
     }
+    cp_async_wait_all();
     double2 v[E];
-    {
-      constexpr int r = 1 << C::bits(0), l = C::lo(0);
-      static_for<0, E / r>([&](auto u_) {
-        constexpr int u = decltype(u_)::value;
-        int low;
-        const int bp = F::template base_pos<0>(t, u, low);
-        static_for<0, r>([&](auto q_) {
-          constexpr int q = decltype(q_)::value;
-          const int j = bp | (q << l);
-          const double2* src =
-              reinterpret_cast<const double2*>(a.T.p[j >> a.log2NJ]) + (size_t)kx * a.NJ + (j & (a.NJ - 1));
-          v[u * r + q] = active ? ld_stream2(src) : mk2(0.0, 0.0);
-        });
-      });
-    }
+    static_for<0, E>([&](auto e_) {
+      constexpr int e = decltype(e_)::value;
+      v[e] = active ? sm[F::addr(F::template own_pos<e>(t))] : mk2(0.0, 0.0);
+    });
     F::forward(c, v, sm, tw, t);
     // ---- divide (registers hold the last-pass layout: butterfly id = t + T*u, digit p) ----------
     if (cta_has_row0) {
@@ -220,22 +236,17 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
         v[i] = cscale(v[i], a.scale * rcp_fast(dd[i]));
       });
     }
-    F::inverse(c, v, sm, tw, t);
+    F::inverse(c, v, sm, tw, t, [&] { issue_row(rb + c.nblk); });
     if (active) {
-      constexpr int r = 1 << C::bits(0), l = C::lo(0);
-      static_for<0, E / r>([&](auto u_) {
-        constexpr int u = decltype(u_)::value;
-        int low;
-        const int bp = F::template base_pos<0>(t, u, low);
-        static_for<0, r>([&](auto q_) {
-          constexpr int q = decltype(q_)::value;
-          const int j = bp | (q << l);
-          double2* dst = reinterpret_cast<double2*>(a.T.p[j >> a.log2NJ]) + (size_t)kx * a.NJ + (j & (a.NJ - 1));
-          st_stream2(dst, v[u * r + q]);
-        });
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        const int j = F::template own_pos<e>(t);
+        double2* dst = reinterpret_cast<double2*>(a.T.p[j >> a.log2NJ]) + (size_t)kx * a.NJ + (j & (a.NJ - 1));
+        st_stream2(dst, v[e]);
       });
     }
   }
+  cp_async_wait_all();
 }
 
 // ======================================== K3 ====================================================
