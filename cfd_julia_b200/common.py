@@ -59,6 +59,18 @@ class Plan:
     def close(self):
         self._fin()
 
+    # slab decomposition: exchange the buffer handles of all ranks (one process per GPU, CUDA IPC)
+    def attach_peers(self, all_gather_bytes):
+        """`all_gather_bytes(b: bytes) -> list[bytes]` returns every rank's blob in rank order
+        (e.g. built on torch.distributed.all_gather_object)."""
+        nb = self.lib.peer_blob_bytes()
+        mine = C.create_string_buffer(nb)
+        self.lib.check(self.lib.peer_export(self.handle, C.cast(mine, C.c_void_p)))
+        blobs = all_gather_bytes(mine.raw)
+        assert len(blobs) == self.nranks and all(len(b) == nb for b in blobs)
+        joined = C.create_string_buffer(b"".join(blobs), nb * self.nranks)
+        self.lib.check(self.lib.peer_import(self.handle, C.cast(joined, C.c_void_p)))
+
     # device-resident path
     def upload(self, wn):
         self.lib.check(self.lib.upload(self.handle, _ptr(wn, (self.nx + 2, self.ny + 2), "wn")))

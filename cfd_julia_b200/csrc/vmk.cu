@@ -197,6 +197,8 @@ struct vmk_plan {
   double* peer_w[3][kMaxPeers];
   double* peer_psi[kMaxPeers];
   double2* peer_T[kMaxPeers];
+  unsigned long long* flags = nullptr;  // [kMaxPeers] epochs published by the peers, [kMaxPeers] own epoch, then error
+  unsigned long long* peer_flags[kMaxPeers];
   bool peers_ready = false;
   std::vector<void*> ipc_opened;
   void (*barrier_fn)(void*) = nullptr;  // enqueues a cross-rank barrier on the plan's stream
@@ -300,11 +302,65 @@ struct Timed {
   }
 };
 
+#ifndef VMK_EMUL
+// Cross-GPU barrier as a one-warp kernel on the plan's stream: every rank bumps its epoch, publishes it in each
+// peer's flag array with a system-scope release store over NVLink and spins (acquire loads on its own array) until
+// every peer has published the same epoch.  Release/acquire are cumulative, so everything the earlier kernels of
+// the publishing rank wrote -- in its own memory or in a peer's -- is visible to the kernels that follow the
+// barrier on the acquiring rank.  The epoch lives in device memory, so the kernel is CUDA-graph replayable.
+// One rank per GPU only: two spinning ranks on one device could wait for each other forever.
+struct BarrierArgs {
+  unsigned long long* peer_flags[kMaxPeers];  // flag arrays of all ranks ([rank] is the local one)
+  unsigned long long* epoch;                  // local epoch counter
+  int* error;                                 // set to 1 on timeout
+  int rank, nranks;
+};
+__global__ void __launch_bounds__(32, 1) barrier_kernel(const __grid_constant__ BarrierArgs a) {
+  const int t = (int)threadIdx.x;
+  const unsigned long long e = *a.epoch + 1;
+  if (t < a.nranks && t != a.rank) {
+    unsigned long long* remote = a.peer_flags[t] + a.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(e) : "memory");
+    const unsigned long long* mine = a.peer_flags[a.rank] + t;
+    unsigned long long seen = 0, t0 = 0, now = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (unsigned spin = 0;; spin++) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+      if (seen >= e) break;
+      if ((spin & 1023u) == 1023u) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 10000000000ull) {  // 10 s: a peer died; do not hang the GPU
+          *a.error = 1;
+          break;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (t == 0) *a.epoch = e;
+}
+#endif
+
 int cross_rank_barrier(vmk_plan* p) {
   if (p->nranks == 1) return 0;
-  if (!p->barrier_fn) return fail(VMK_ESTATE, "slab plan has no barrier hook (vmk_barrier_hook)");
-  p->barrier_fn(p->barrier_user);
+  if (p->barrier_fn) {
+    p->barrier_fn(p->barrier_user);
+    return 0;
+  }
+#ifndef VMK_EMUL
+  BarrierArgs a;
+  for (int r = 0; r < kMaxPeers; r++) a.peer_flags[r] = r < p->nranks ? p->peer_flags[r] : nullptr;
+  a.epoch = p->flags + kMaxPeers;
+  a.error = reinterpret_cast<int*>(p->flags + kMaxPeers + 1);
+  a.rank = p->rank;
+  a.nranks = p->nranks;
+  barrier_kernel<<<1, 32, 0, p->st.s>>>(a);
+  VMK_CUDA_TRY(cudaGetLastError());
+  p->launches++;
   return 0;
+#else
+  return fail(VMK_ESTATE, "emulated slab plans need a barrier hook (vmk_barrier_hook)");
+#endif
 }
 
 // K1/K3 work units: groups of row pairs (see k1_body / k3_body)
@@ -485,6 +541,19 @@ int download_interior(vmk_plan* p, const double* slab, double* host) {
                    sizeof(double) * p->N, (size_t)p->NJ, p->st);
 }
 
+// stream sync + the cross-GPU barrier's timeout flag (a peer that died must surface as an error, not as a hang)
+int sync_and_check(vmk_plan* p) {
+  VMK_TRY(be_sync(p->st));
+#ifndef VMK_EMUL
+  if (p->nranks > 1 && !p->barrier_fn) {
+    int err = 0;
+    VMK_CUDA_TRY(cudaMemcpy(&err, p->flags + kMaxPeers + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return fail(VMK_ECUDA, "cross-GPU barrier timed out: a peer rank did not arrive");
+  }
+#endif
+  return 0;
+}
+
 int collect_profile(vmk_plan* p) {
   VMK_TRY(be_sync(p->st));
   for (auto& e : p->prof_events) {
@@ -541,6 +610,12 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     if ((rc = dev_alloc(p, (void**)&p->psi, sb))) break;
     if ((rc = dev_alloc(p, (void**)&p->T, sizeof(double2) * (size_t)(p->N / 2) * p->NJ))) break;
     if ((rc = dev_alloc(p, (void**)&p->tw, sizeof(double2) * (ops.twn ? ops.twn : 1)))) break;
+    if ((rc = dev_alloc(p, (void**)&p->flags, sizeof(unsigned long long) * (kMaxPeers + 2)))) break;
+#ifndef VMK_EMUL
+    if ((rc = cudaMemset(p->flags, 0, sizeof(unsigned long long) * (kMaxPeers + 2)) != cudaSuccess ? fail(VMK_ECUDA, "cudaMemset(flags)") : 0)) break;
+#else
+    memset(p->flags, 0, sizeof(unsigned long long) * (kMaxPeers + 2));
+#endif
     if ((rc = dev_alloc(p, (void**)&p->bbcos, sizeof(double) * p->N))) break;
     if ((rc = dev_alloc(p, (void**)&p->cccos, sizeof(double) * p->N))) break;
     if ((rc = dev_alloc(p, (void**)&p->ccperm, sizeof(double) * p->N))) break;
@@ -557,10 +632,12 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     for (int b = 0; b < 3; b++) p->peer_w[b][r] = nullptr;
     p->peer_psi[r] = nullptr;
     p->peer_T[r] = nullptr;
+    p->peer_flags[r] = nullptr;
   }
   for (int b = 0; b < 3; b++) p->peer_w[b][rank] = p->w[b];
   p->peer_psi[rank] = p->psi;
   p->peer_T[rank] = p->T;
+  p->peer_flags[rank] = p->flags;
   p->peers_ready = (nranks == 1);
   *out = p;
   return VMK_OK;
@@ -578,6 +655,7 @@ int vmk_plan_destroy(vmk_plan* p) {
   for (int b = 0; b < 3; b++) be_free(p->w[b]);
   be_free(p->psi);
   be_free(p->T);
+  be_free(p->flags);
   be_free(p->tw);
   be_free(p->bbcos);
   be_free(p->cccos);
@@ -591,14 +669,15 @@ int vmk_plan_destroy(vmk_plan* p) {
 }
 
 // ---- slab decomposition: peer buffer exchange ------------------------------------------------------
-// A blob carries the handles of one rank's five exchange buffers (w[0..2], psi, T).
+// A blob carries the handles of one rank's six exchange buffers (w[0..2], psi, T, barrier flags).
+constexpr int kPeerBufs = 6;
 #ifndef VMK_EMUL
 struct PeerBlob {
-  cudaIpcMemHandle_t h[5];
+  cudaIpcMemHandle_t h[kPeerBufs];
 };
 #else
 struct PeerBlob {
-  void* h[5];
+  void* h[kPeerBufs];
 };
 #endif
 
@@ -607,8 +686,8 @@ size_t vmk_peer_blob_bytes(void) { return sizeof(PeerBlob); }
 int vmk_peer_export(vmk_plan* p, void* blob) {
   if (!p || !blob) return fail(VMK_EARG, "NULL argument");
   PeerBlob* b = static_cast<PeerBlob*>(blob);
-  void* ptrs[5] = {p->w[0], p->w[1], p->w[2], p->psi, p->T};
-  for (int i = 0; i < 5; i++) {
+  void* ptrs[kPeerBufs] = {p->w[0], p->w[1], p->w[2], p->psi, p->T, p->flags};
+  for (int i = 0; i < kPeerBufs; i++) {
 #ifndef VMK_EMUL
     VMK_CUDA_TRY(cudaIpcGetMemHandle(&b->h[i], ptrs[i]));
 #else
@@ -624,8 +703,8 @@ int vmk_peer_import(vmk_plan* p, const void* blobs) {
   const PeerBlob* b = static_cast<const PeerBlob*>(blobs);
   for (int r = 0; r < p->nranks; r++) {
     if (r == p->rank) continue;
-    void* ptrs[5];
-    for (int i = 0; i < 5; i++) {
+    void* ptrs[kPeerBufs];
+    for (int i = 0; i < kPeerBufs; i++) {
 #ifndef VMK_EMUL
       VMK_CUDA_TRY(cudaIpcOpenMemHandle(&ptrs[i], b[r].h[i], cudaIpcMemLazyEnablePeerAccess));
       p->ipc_opened.push_back(ptrs[i]);
@@ -636,6 +715,7 @@ int vmk_peer_import(vmk_plan* p, const void* blobs) {
     for (int q = 0; q < 3; q++) p->peer_w[q][r] = (double*)ptrs[q];
     p->peer_psi[r] = (double*)ptrs[3];
     p->peer_T[r] = (double2*)ptrs[4];
+    p->peer_flags[r] = (unsigned long long*)ptrs[5];
   }
   p->peers_ready = true;
   return VMK_OK;
@@ -651,6 +731,7 @@ int vmk_peer_attach_local(vmk_plan* p, vmk_plan* const* plans) {
     for (int q = 0; q < 3; q++) p->peer_w[q][r] = plans[r]->w[q];
     p->peer_psi[r] = plans[r]->psi;
     p->peer_T[r] = plans[r]->T;
+    p->peer_flags[r] = plans[r]->flags;
   }
   p->peers_ready = true;
   return VMK_OK;
@@ -725,7 +806,7 @@ int vmk_step(vmk_plan* p, double dx, double dy, double dt, double re, int64_t ns
   const StepParams sp{dx, dy, dt, re};
   VMK_TRY(be_event_record(p->ev0, p->st));
 #ifndef VMK_EMUL
-  if (p->use_graph && p->nranks == 1 && !p->profiling && nsteps > 0) {
+  if (p->use_graph && !p->barrier_fn && !p->profiling && nsteps > 0) {
     auto it = p->graphs.find(sp);
     if (it == p->graphs.end()) {
       cudaGraph_t g = nullptr;
@@ -743,14 +824,16 @@ int vmk_step(vmk_plan* p, double dx, double dy, double dt, double re, int64_t ns
     }
     for (int64_t k = 0; k < nsteps; k++) {
       VMK_CUDA_TRY(cudaGraphLaunch(it->second, p->st.s));
-      p->launches += 12;
+      p->launches += p->nranks > 1 ? 21 : 12;
     }
+    VMK_TRY(cross_rank_barrier(p));  // the neighbours' last halo rows have landed (vmk_download reads them)
     VMK_TRY(be_event_record(p->ev1, p->st));
     p->ev_valid = true;
     return VMK_OK;
   }
 #endif
   for (int64_t k = 0; k < nsteps; k++) VMK_TRY(enqueue_step(p, sp));
+  VMK_TRY(cross_rank_barrier(p));
   VMK_TRY(be_event_record(p->ev1, p->st));
   p->ev_valid = true;
   return VMK_OK;
@@ -761,12 +844,12 @@ int vmk_download(vmk_plan* p, double* wn, double* psi) {
   if (!p->uploaded) return fail(VMK_ESTATE, "vmk_download before vmk_upload");
   if (wn) VMK_TRY(download_ghosted(p, p->w[0], wn));
   if (psi) VMK_TRY(download_ghosted(p, p->psi, psi));
-  return be_sync(p->st);
+  return sync_and_check(p);
 }
 
 int vmk_sync(vmk_plan* p) {
   VMK_TRY(check_plan(p));
-  return be_sync(p->st);
+  return sync_and_check(p);
 }
 
 int vmk_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, double re, double* wn, double* out,

@@ -118,9 +118,12 @@ VMK_HD void st_stream4(double2* p, double2 a, double2 b) {
   p[1] = b;
 #endif
 }
+#ifndef VMK_GATHER_L2
+#define VMK_GATHER_L2 ""
+#endif
 VMK_HD void ld_stream4(const double2* p, double2& a, double2& b) {
 #ifdef __CUDA_ARCH__
-  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.L1::no_allocate" VMK_GATHER_L2 ".v4.f64 {%0,%1,%2,%3}, [%4];"
                : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y)
                : "l"(p));
 #else
