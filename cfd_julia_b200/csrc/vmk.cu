@@ -186,7 +186,9 @@ struct vmk_plan {
   // device buffers
   double* w[3] = {nullptr, nullptr, nullptr};  // wn, wtA, wtB: slabs with halo rows
   double* psi = nullptr;                       // slab with halo rows
-  double2* T = nullptr;                        // local half spectrum [N/2][NJ]
+  double2* T = nullptr;                        // spectrum rows owned by this rank [N/(2P)][N]   (K1 -> K2)
+  double2* V = nullptr;                        // solution spectrum for this rank's j [N/2][NJ]   (K2 -> K3)
+  double2* S = nullptr;                        // K1 output [N/2][NJ] before the forward transpose (P > 1 only)
   double2* tw = nullptr;
   double* bbcos = nullptr;
   double* cccos = nullptr;
@@ -197,6 +199,7 @@ struct vmk_plan {
   double* peer_w[3][kMaxPeers];
   double* peer_psi[kMaxPeers];
   double2* peer_T[kMaxPeers];
+  double2* peer_V[kMaxPeers];
   unsigned long long* flags = nullptr;  // [kMaxPeers] epochs published by the peers, [kMaxPeers] own epoch, then error
   unsigned long long* peer_flags[kMaxPeers];
   bool peers_ready = false;
@@ -206,11 +209,12 @@ struct vmk_plan {
   // divisor cache (Common.jl:101-113)
   bool div_valid = false;
   double div_dx = 0, div_dy = 0, div_eps = 0, div_aa = 0;
-  Stream st;
-  Event ev0, ev1;
+  Stream st, st_copy;
+  Event ev0, ev1, ev_join, ev_chunk[8];
+  int a2a_chunks = 4;
   bool ev_valid = false;
   bool uploaded = false;
-  int64_t launches = 0;
+  int64_t launches = 0, graph_launches = 12;
   int k4_rows = 32, k4_ahead = 4;
   int k1_group = 1, k3_group = 1, k1_prefetch = 1, k2_prefetch = 1, k3_prefetch = 0;
   int use_graph = 1;
@@ -370,25 +374,55 @@ int rowpair_units(const vmk_plan* p, int npairs, int g) {
   return (nblocks + g - 1) / g;
 }
 
+// K1 + the forward transpose of the distributed FFT.  On P > 1 GPUs the launch is split into `a2a_chunks` ranges
+// of row pairs; as soon as a range is done, its columns of the rows owned by the other ranks are copied into those
+// ranks' T buffers by the copy engines on a second stream (NJ/chunks*16-byte contiguous pieces over NVLink), while
+// the next range is being transformed.
 int launch_k1(vmk_plan* p, const double* src) {
-  K1Args a;
-  a.w = src;
-  a.T = p->T;
-  a.tw = p->tw;
-  a.NJ = p->NJ;
-  a.npairs = p->NJ / 2;
-  a.prefetch = p->k1_prefetch;
-  const int work = rowpair_units(p, a.npairs, 1);
+  const int N = p->N, P = p->nranks, R = (N / 2) / P;
+  const int npairs = p->NJ / 2;
+  int chunks = P > 1 ? p->a2a_chunks : 1;
+  while (chunks > 1 && (npairs % chunks || npairs / chunks < 1)) chunks--;
   Timed t(p, KI_K1);
-  VMK_TRY(p->ops.k1(work < p->res_k1 ? work : p->res_k1, a, p->st));
+  for (int c = 0; c < chunks; c++) {
+    const int pair0 = c * (npairs / chunks), np = npairs / chunks;
+    K1Args a;
+    a.w = src + (size_t)2 * pair0 * N;
+    a.S = P > 1 ? p->S + 2 * pair0 : nullptr;
+    a.Tloc = p->T + p->j0 + 2 * pair0;
+    a.tw = p->tw;
+    a.NJ = p->NJ;
+    a.npairs = np;
+    a.k_own0 = p->rank * R;
+    a.k_own1 = a.k_own0 + R;
+    a.prefetch = p->k1_prefetch;
+    const int work = rowpair_units(p, np, 1);
+    VMK_TRY(p->ops.k1(work < p->res_k1 ? work : p->res_k1, a, p->st));
+    p->launches++;
+    if (P > 1) {
+      VMK_TRY(be_event_record(p->ev_chunk[c], p->st));
+      VMK_TRY(be_stream_wait(p->st_copy, p->ev_chunk[c]));
+      const size_t width = sizeof(double2) * (size_t)(2 * np);
+      for (int q = 0; q + 1 < P; q++) {
+        const int h = (p->rank + 1 + q) % P;  // start with the neighbour so the ranks do not all hit one peer
+        VMK_TRY(be_d2d_2d(p->peer_T[h] + p->j0 + 2 * pair0, sizeof(double2) * (size_t)N,
+                          p->S + (size_t)h * R * p->NJ + 2 * pair0, sizeof(double2) * (size_t)p->NJ, width, (size_t)R,
+                          p->st_copy));
+      }
+    }
+  }
+  if (P > 1) {
+    VMK_TRY(be_event_record(p->ev_join, p->st_copy));
+    VMK_TRY(be_stream_wait(p->st, p->ev_join));
+  }
   t.done();
-  p->launches++;
   return 0;
 }
 
 int launch_k2(vmk_plan* p, double sign) {
   K2Args a;
-  for (int r = 0; r < kMaxPeers; r++) a.T.p[r] = r < p->nranks ? (void*)p->peer_T[r] : nullptr;
+  a.T = p->T;
+  for (int r = 0; r < kMaxPeers; r++) a.V.p[r] = r < p->nranks ? (void*)p->peer_V[r] : nullptr;
   a.tw = p->tw;
   a.bbcos = p->bbcos;
   a.cccos = p->cccos;
@@ -410,7 +444,7 @@ int launch_k2(vmk_plan* p, double sign) {
 
 int launch_k3(vmk_plan* p) {
   K3Args a;
-  a.T = p->T;
+  a.T = p->V;
   a.tw = p->tw;
   a.psi = p->psi;
   const int prev = (p->rank + p->nranks - 1) % p->nranks, next = (p->rank + 1) % p->nranks;
@@ -603,12 +637,19 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     if ((rc = be_num_sms(&p->sms))) break;
     if ((rc = be_stream_create(p->st))) break;
     if ((rc = be_event_create(p->ev0)) || (rc = be_event_create(p->ev1))) break;
+    if (nranks > 1) {
+      if ((rc = be_stream_create(p->st_copy)) || (rc = be_event_create(p->ev_join))) break;
+      for (int c = 0; c < 8 && !rc; c++) rc = be_event_create(p->ev_chunk[c]);
+      if (rc) break;
+    }
     if ((rc = ops.configure(&p->res_k1, &p->res_k2, &p->res_k3))) break;
     const size_t sb = sizeof(double) * slab_elems(p);
     for (int b = 0; b < 3 && !rc; b++) rc = dev_alloc(p, (void**)&p->w[b], sb);
     if (rc) break;
     if ((rc = dev_alloc(p, (void**)&p->psi, sb))) break;
     if ((rc = dev_alloc(p, (void**)&p->T, sizeof(double2) * (size_t)(p->N / 2) * p->NJ))) break;
+    if ((rc = dev_alloc(p, (void**)&p->V, sizeof(double2) * (size_t)(p->N / 2) * p->NJ))) break;
+    if (nranks > 1 && (rc = dev_alloc(p, (void**)&p->S, sizeof(double2) * (size_t)(p->N / 2) * p->NJ))) break;
     if ((rc = dev_alloc(p, (void**)&p->tw, sizeof(double2) * (ops.twn ? ops.twn : 1)))) break;
     if ((rc = dev_alloc(p, (void**)&p->flags, sizeof(unsigned long long) * (kMaxPeers + 2)))) break;
 #ifndef VMK_EMUL
@@ -632,11 +673,13 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     for (int b = 0; b < 3; b++) p->peer_w[b][r] = nullptr;
     p->peer_psi[r] = nullptr;
     p->peer_T[r] = nullptr;
+    p->peer_V[r] = nullptr;
     p->peer_flags[r] = nullptr;
   }
   for (int b = 0; b < 3; b++) p->peer_w[b][rank] = p->w[b];
   p->peer_psi[rank] = p->psi;
   p->peer_T[rank] = p->T;
+  p->peer_V[rank] = p->V;
   p->peer_flags[rank] = p->flags;
   p->peers_ready = (nranks == 1);
   *out = p;
@@ -648,13 +691,13 @@ int vmk_plan_create(int64_t nx, int64_t ny, vmk_plan** out) { return vmk_plan_cr
 int vmk_plan_destroy(vmk_plan* p) {
   if (!p) return VMK_OK;
   if (be_stream_valid(p->st)) be_sync(p->st);
-#ifndef VMK_EMUL
-  for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
-  for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
-#endif
+  drop_graphs(p);
+  for (void* q : p->ipc_opened) be_ipc_close(q);
   for (int b = 0; b < 3; b++) be_free(p->w[b]);
   be_free(p->psi);
   be_free(p->T);
+  be_free(p->V);
+  be_free(p->S);
   be_free(p->flags);
   be_free(p->tw);
   be_free(p->bbcos);
@@ -663,37 +706,28 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_free(p->staging);
   be_event_destroy(p->ev0);
   be_event_destroy(p->ev1);
+  be_event_destroy(p->ev_join);
+  for (int c = 0; c < 8; c++) be_event_destroy(p->ev_chunk[c]);
+  be_stream_destroy(p->st_copy);
   be_stream_destroy(p->st);
   delete p;
   return VMK_OK;
 }
 
 // ---- slab decomposition: peer buffer exchange ------------------------------------------------------
-// A blob carries the handles of one rank's six exchange buffers (w[0..2], psi, T, barrier flags).
-constexpr int kPeerBufs = 6;
-#ifndef VMK_EMUL
+// A blob carries the handles of one rank's seven exchange buffers (w[0..2], psi, T, V, barrier flags).
+constexpr int kPeerBufs = 7;
 struct PeerBlob {
-  cudaIpcMemHandle_t h[kPeerBufs];
+  IpcHandle h[kPeerBufs];
 };
-#else
-struct PeerBlob {
-  void* h[kPeerBufs];
-};
-#endif
 
 size_t vmk_peer_blob_bytes(void) { return sizeof(PeerBlob); }
 
 int vmk_peer_export(vmk_plan* p, void* blob) {
   if (!p || !blob) return fail(VMK_EARG, "NULL argument");
   PeerBlob* b = static_cast<PeerBlob*>(blob);
-  void* ptrs[kPeerBufs] = {p->w[0], p->w[1], p->w[2], p->psi, p->T, p->flags};
-  for (int i = 0; i < kPeerBufs; i++) {
-#ifndef VMK_EMUL
-    VMK_CUDA_TRY(cudaIpcGetMemHandle(&b->h[i], ptrs[i]));
-#else
-    b->h[i] = ptrs[i];
-#endif
-  }
+  void* ptrs[kPeerBufs] = {p->w[0], p->w[1], p->w[2], p->psi, p->T, p->V, p->flags};
+  for (int i = 0; i < kPeerBufs; i++) VMK_TRY(be_ipc_export(ptrs[i], &b->h[i]));
   return VMK_OK;
 }
 
@@ -705,17 +739,14 @@ int vmk_peer_import(vmk_plan* p, const void* blobs) {
     if (r == p->rank) continue;
     void* ptrs[kPeerBufs];
     for (int i = 0; i < kPeerBufs; i++) {
-#ifndef VMK_EMUL
-      VMK_CUDA_TRY(cudaIpcOpenMemHandle(&ptrs[i], b[r].h[i], cudaIpcMemLazyEnablePeerAccess));
+      VMK_TRY(be_ipc_open(b[r].h[i], &ptrs[i]));
       p->ipc_opened.push_back(ptrs[i]);
-#else
-      ptrs[i] = b[r].h[i];
-#endif
     }
     for (int q = 0; q < 3; q++) p->peer_w[q][r] = (double*)ptrs[q];
     p->peer_psi[r] = (double*)ptrs[3];
     p->peer_T[r] = (double2*)ptrs[4];
-    p->peer_flags[r] = (unsigned long long*)ptrs[5];
+    p->peer_V[r] = (double2*)ptrs[5];
+    p->peer_flags[r] = (unsigned long long*)ptrs[6];
   }
   p->peers_ready = true;
   return VMK_OK;
@@ -731,6 +762,7 @@ int vmk_peer_attach_local(vmk_plan* p, vmk_plan* const* plans) {
     for (int q = 0; q < 3; q++) p->peer_w[q][r] = plans[r]->w[q];
     p->peer_psi[r] = plans[r]->psi;
     p->peer_T[r] = plans[r]->T;
+    p->peer_V[r] = plans[r]->V;
     p->peer_flags[r] = plans[r]->flags;
   }
   p->peers_ready = true;
@@ -775,8 +807,8 @@ int vmk_rhs(vmk_plan* p, double dx, double dy, double re, const double* w, doubl
   VMK_TRY(ensure_divisor(p, dx, dy, 1.e-6));  // vm_rhs calls fps with the default eps (Common.jl:136)
   VMK_TRY(upload_ghosted(p, w, p->w[1]));
   if (f) {
-    // T is free until K1 runs: borrow it for f = -w (Common.jl:134)
-    double* fd = reinterpret_cast<double*>(p->T);
+    // V is not written before the first cross-rank barrier of this call: borrow it for f = -w (Common.jl:134)
+    double* fd = reinterpret_cast<double*>(p->V);
     VMK_TRY(launch_k5<K5Negate>(p, p->w[1], fd, (size_t)p->NJ * p->N));
     VMK_TRY(be_d2h(f + (size_t)p->j0 * p->N, fd, sizeof(double) * (size_t)p->N * p->NJ, p->st));
   }
@@ -814,6 +846,7 @@ int vmk_step(vmk_plan* p, double dx, double dy, double dt, double re, int64_t ns
       VMK_CUDA_TRY(cudaStreamBeginCapture(p->st.s, cudaStreamCaptureModeThreadLocal));
       const int64_t before = p->launches;
       int rc = enqueue_step(p, sp);
+      p->graph_launches = p->launches - before;
       p->launches = before;
       cudaError_t e = cudaStreamEndCapture(p->st.s, &g);
       if (rc) return rc;
@@ -824,7 +857,7 @@ int vmk_step(vmk_plan* p, double dx, double dy, double dt, double re, int64_t ns
     }
     for (int64_t k = 0; k < nsteps; k++) {
       VMK_CUDA_TRY(cudaGraphLaunch(it->second, p->st.s));
-      p->launches += p->nranks > 1 ? 21 : 12;
+      p->launches += p->graph_launches;
     }
     VMK_TRY(cross_rank_barrier(p));  // the neighbours' last halo rows have landed (vmk_download reads them)
     VMK_TRY(be_event_record(p->ev1, p->st));
@@ -925,7 +958,7 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
   const std::string k(key);
   int* knob = k == "k1_group" ? &p->k1_group : k == "k3_group" ? &p->k3_group : k == "k1_prefetch" ? &p->k1_prefetch
               : k == "k2_prefetch" ? &p->k2_prefetch : k == "k3_prefetch" ? &p->k3_prefetch
-              : k == "k4_ahead" ? &p->k4_ahead : nullptr;
+              : k == "k4_ahead" ? &p->k4_ahead : k == "a2a_chunks" ? &p->a2a_chunks : nullptr;
   if (knob) {
     if (value < 0 || value > 64 || (value == 0 && k.find("group") != std::string::npos))
       return fail(VMK_EARG, "option value out of range");

@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <string>
 
 #include "vmk_common.cuh"
@@ -82,6 +84,10 @@ inline int be_event_record(Event& e, Stream& s) {
   VMK_CUDA_TRY(cudaEventRecord(e.e, s.s));
   return 0;
 }
+inline int be_stream_wait(Stream& s, Event& e) {
+  VMK_CUDA_TRY(cudaStreamWaitEvent(s.s, e.e, 0));
+  return 0;
+}
 inline int be_event_elapsed(Event& a, Event& b, double* ms) {
   VMK_CUDA_TRY(cudaEventSynchronize(b.e));
   float f = 0.f;
@@ -109,10 +115,26 @@ inline int be_h2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, s
   VMK_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, s.s));
   return 0;
 }
+// device (possibly a peer's) <- device, strided; runs on a copy engine
+inline int be_d2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, Stream& s) {
+  VMK_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, s.s));
+  return 0;
+}
 inline int be_d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, Stream& s) {
   VMK_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, s.s));
   return 0;
 }
+// inter-process handles of device allocations (one process per GPU)
+typedef cudaIpcMemHandle_t IpcHandle;
+inline int be_ipc_export(void* p, IpcHandle* h) {
+  VMK_CUDA_TRY(cudaIpcGetMemHandle(h, p));
+  return 0;
+}
+inline int be_ipc_open(const IpcHandle& h, void** p) {
+  VMK_CUDA_TRY(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+inline void be_ipc_close(void* p) { cudaIpcCloseMemHandle(p); }
 inline int be_num_sms(int* n) {
   int dev = 0;
   VMK_CUDA_TRY(cudaGetDevice(&dev));
@@ -149,13 +171,56 @@ struct Stream {
 struct Event {
   double t = 0;
 };
+// "Device memory" of the emulator lives in POSIX shared-memory segments, so that the slab decomposition can be
+// run by several PROCESSES (one per rank, gloo for the barrier) exactly like the one-process-per-GPU CUDA path:
+// be_ipc_export/open are the stand-ins for cudaIpcGetMemHandle/OpenMemHandle.
+struct IpcHandle {
+  char name[56];
+  size_t bytes;
+};
+struct EmulAlloc {
+  std::string name;
+  size_t bytes;
+  bool owner;
+};
+std::map<void*, EmulAlloc>& emul_allocs();
+std::mutex& emul_alloc_mutex();
+int emul_shm_create(void** p, size_t bytes, std::string* name);
+int emul_shm_open(const char* name, size_t bytes, void** p);
+void emul_shm_release(void* p, size_t bytes, const char* name, bool owner);
+
 inline int be_malloc(void** p, size_t bytes) {
-  *p = aligned_alloc(256, (bytes + 255) / 256 * 256);
-  if (!*p) return fail(2, "emul: out of memory");
+  std::string name;
+  if (emul_shm_create(p, bytes, &name)) return fail(2, "emul: shared-memory allocation failed");
   memset(*p, 0xff, bytes);  // NaN-fill so reads of never-written memory show up
+  std::lock_guard<std::mutex> lk(emul_alloc_mutex());
+  emul_allocs()[*p] = EmulAlloc{name, bytes, true};
   return 0;
 }
-inline void be_free(void* p) { free(p); }
+inline void be_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(emul_alloc_mutex());
+  auto it = emul_allocs().find(p);
+  if (it == emul_allocs().end()) return;
+  emul_shm_release(p, it->second.bytes, it->second.name.c_str(), it->second.owner);
+  emul_allocs().erase(it);
+}
+inline int be_ipc_export(void* p, IpcHandle* h) {
+  std::lock_guard<std::mutex> lk(emul_alloc_mutex());
+  auto it = emul_allocs().find(p);
+  if (it == emul_allocs().end()) return fail(3, "emul: unknown allocation");
+  memset(h, 0, sizeof(*h));
+  strncpy(h->name, it->second.name.c_str(), sizeof(h->name) - 1);
+  h->bytes = it->second.bytes;
+  return 0;
+}
+inline int be_ipc_open(const IpcHandle& h, void** p) {
+  if (emul_shm_open(h.name, h.bytes, p)) return fail(2, "emul: cannot map a peer's shared-memory segment");
+  std::lock_guard<std::mutex> lk(emul_alloc_mutex());
+  emul_allocs()[*p] = EmulAlloc{h.name, h.bytes, false};
+  return 0;
+}
+inline void be_ipc_close(void* p) { be_free(p); }
 inline int be_stream_create(Stream&) { return 0; }
 inline void be_stream_destroy(Stream&) {}
 inline bool be_stream_valid(const Stream&) { return true; }
@@ -166,6 +231,7 @@ inline int be_event_record(Event& e, Stream&) {
   e.t = emul_now_ms();
   return 0;
 }
+inline int be_stream_wait(Stream&, Event&) { return 0; }
 inline int be_event_elapsed(Event& a, Event& b, double* ms) {
   *ms = b.t - a.t;
   return 0;
@@ -188,6 +254,9 @@ inline int be_h2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, s
   return 0;
 }
 inline int be_d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, Stream& s) {
+  return be_h2d_2d(dst, dpitch, src, spitch, width, height, s);
+}
+inline int be_d2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, Stream& s) {
   return be_h2d_2d(dst, dpitch, src, spitch, width, height, s);
 }
 inline int be_num_sms(int* n) {

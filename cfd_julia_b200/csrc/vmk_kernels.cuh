@@ -11,8 +11,18 @@
 // Device layout (one slab per GPU; a single GPU owns the whole grid):
 //   real fields  w, psi : (NJ+2) rows of N doubles; row 0 / NJ+1 are the periodic (or neighbour's)
 //                         halo rows, interior row jl lives at (jl+1)*N.  i (Julia dim 1) is contiguous.
-//   spectrum     T      : N/2 rows (kx) of NJ complex (local j); row 0 packs kx=0 (re) and kx=N/2 (im),
-//                         both of which are real sequences in j after the real-pair unpack.
+//   K1 output    S      : N/2 rows (all kx) of NJ complex (the rank's own j), written by K1 in 32-byte pieces (two
+//                         adjacent j).  Global row 0 packs kx=0 (re) and kx=N/2 (im), both of which are real
+//                         sequences in j after the real-pair unpack.
+//   spectrum     T      : the rank's R = N/(2P) spectrum rows (kx = rank*R ..) of N complex, ALL j, read by the local
+//                         K2 as contiguous rows.  On one GPU T is S.  On P GPUs rank g's S rows [h*R, (h+1)*R) are
+//                         copied (copy engine, NJ*16-byte contiguous pieces, NVLink for h != g) into T_h[..][g*NJ ..]:
+//                         the forward transpose of the distributed 2-D FFT.  (Pushing K1's 32-byte pieces straight
+//                         into the peers' T ran NVLink at ~400 GB/s; the copy moves 16..64 KB pieces.)
+//   solution     V      : N/2 rows (all kx) of NJ complex (the rank's own j): filled by every rank's K2, which pushes
+//                         the NJ-element chunks of its result rows straight to the ranks owning those j (the backward
+//                         transpose, folded into K2's store epilogue); read by the local K3.
+//   Data crosses NVLink only as fire-and-forget stores / engine copies; no kernel ever waits on a remote load.
 #pragma once
 #include "vmk_fft.cuh"
 
@@ -29,10 +39,12 @@ VMK_HD int halfspec_pos(int idx) {
 // ======================================== K1 ====================================================
 struct K1Args {
   const double* w;    // slab with halo rows (or the fps source f in the same layout)
-  double2* T;         // local spectrum [N/2][NJ]
+  double2* S;         // K1 output [N/2][NJ] for the spectrum rows owned by OTHER ranks (nullptr on a single GPU)
+  double2* Tloc;      // own spectrum buffer [R][N], offset to this rank's first column: rows this rank owns go here
   const double2* tw;  // twiddle tables (global)
-  int NJ;             // local rows
-  int npairs;         // NJ/2
+  int NJ;             // local rows (row pitch of S)
+  int npairs;         // row pairs handled by this launch (w, S and Tloc are offset to its first pair)
+  int k_own0, k_own1; // spectrum rows [k_own0, k_own1) are owned by this rank
   int prefetch;       // 0 off, 1: bulk L2 prefetch of the rows of the pair after next
 };
 
@@ -111,7 +123,9 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
           o0 = mk2(zk[i].x + zm[i].x, zk[i].y - zm[i].y);  // 2 X_j[k]   = Z[k] + conj Z[N-k]
           o1 = mk2(zk[i].y + zm[i].y, zm[i].x - zk[i].x);  // 2 X_j+1[k] = -i (Z[k] - conj Z[N-k])
         }
-        st_stream4(a.T + (size_t)k * a.NJ + jl, o0, o1);
+        double2* dst = (k >= a.k_own0 && k < a.k_own1) ? a.Tloc + (size_t)(k - a.k_own0) * N + jl
+                                                       : a.S + (size_t)k * a.NJ + jl;
+        st_stream4(dst, o0, o1);
       });
     }
   }
@@ -120,7 +134,8 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
 
 // ======================================== K2 ====================================================
 struct K2Args {
-  PeerPtrs T;           // per-rank spectrum buffers [N/2][NJ], transformed in place
+  const double2* T;     // local spectrum rows [R][N] (input)
+  PeerPtrs V;           // every rank's solution buffer [N/2][NJ]; element j goes to rank j >> log2NJ
   const double2* tw;    // twiddle tables
   const double* bbcos;  // [N]  bb*cos(kx[i])   Common.jl:120 (kx[1]=eps quirk inside)
   const double* cccos;  // [N]  cc*cos(ky[j])   (ky = kx, Common.jl:113)
@@ -129,7 +144,7 @@ struct K2Args {
   double aa;            // -2/dx^2 - 2/dy^2
   double scale;         // sign / (2 N^2): ifft normalisation, the factor 2 of the unpack, f = -w
   int NJ, log2NJ;
-  int row0, nrows;      // kx rows owned by this rank
+  int row0, nrows;      // kx rows owned by this rank: row0 = rank*R, nrows = R
   int prefetch;         // 0 off, 1: bulk L2 prefetch of the next row (single rank only)
 };
 
@@ -151,13 +166,10 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
   auto issue_row = [&](int rb) {
     const int row = rb * C::FPC + g;
     if (rb < nblocks && row < a.nrows) {
-      const int kx = a.row0 + row;
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
         const int j = F::template own_pos<e>(t);
-        const double2* src =
-            reinterpret_cast<const double2*>(a.T.p[j >> a.log2NJ]) + (size_t)kx * a.NJ + (j & (a.NJ - 1));
-        cp_async16(sm + F::addr(j), src);
+        cp_async16(sm + F::addr(j), a.T + (size_t)row * N + j);
       });
     }
     cp_async_commit();
@@ -168,11 +180,10 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
     const bool active = row < a.nrows;
     const int kx = a.row0 + row;
     const bool cta_has_row0 = (a.row0 + rb * C::FPC) == 0;
-    if (a.prefetch && c.tid == 0 && rb + 2 * c.nblk < nblocks && a.log2NJ == M) {  // single rank: rows are contiguous
+    if (a.prefetch && c.tid == 0 && rb + 2 * c.nblk < nblocks) {
       const int r0n = (rb + 2 * c.nblk) * C::FPC;
       const int nr = (a.nrows - r0n) < C::FPC ? (a.nrows - r0n) : C::FPC;
-      prefetch_l2_bulk(reinterpret_cast<const double2*>(a.T.p[0]) + (size_t)(a.row0 + r0n) * a.NJ,
-                       (unsigned)(nr * N * sizeof(double2)));
+      prefetch_l2_bulk(a.T + (size_t)r0n * N, (unsigned)(nr * N * sizeof(double2)));
     }
     cp_async_wait_all();
     double2 v[E];
@@ -241,7 +252,7 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
         const int j = F::template own_pos<e>(t);
-        double2* dst = reinterpret_cast<double2*>(a.T.p[j >> a.log2NJ]) + (size_t)kx * a.NJ + (j & (a.NJ - 1));
+        double2* dst = reinterpret_cast<double2*>(a.V.p[j >> a.log2NJ]) + (size_t)kx * a.NJ + (j & (a.NJ - 1));
         st_stream2(dst, v[e]);
       });
     }
@@ -251,7 +262,7 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
 
 // ======================================== K3 ====================================================
 struct K3Args {
-  const double2* T;   // local spectrum after K2: U[kx][jl]
+  const double2* T;   // local solution buffer V after K2: U[kx][jl]
   const double2* tw;
   double* psi;        // slab with halo rows
   double* lo_dst;     // where interior row 0 is mirrored: previous rank's top halo row (row NJ+1 there)

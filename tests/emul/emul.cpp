@@ -10,7 +10,12 @@
 // Ctx::sync() yields to the scheduler, which resumes the next fiber -- after a full round every fiber has
 // reached the barrier, exactly __syncthreads() semantics (threads that returned are skipped, as on the
 // device).  CTAs of a grid are distributed over a few OS threads.
+#include <fcntl.h>
 #include <pthread.h>
+#include <stdio.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -91,6 +96,54 @@ extern "C" void vmk_host_barrier_wait(void* bar) {
 }
 
 namespace vmk {
+
+std::map<void*, EmulAlloc>& emul_allocs() {
+  static std::map<void*, EmulAlloc> m;
+  return m;
+}
+
+std::mutex& emul_alloc_mutex() {
+  static std::mutex m;
+  return m;
+}
+
+int emul_shm_create(void** p, size_t bytes, std::string* name) {
+  static std::atomic<unsigned> counter{0};
+  char buf[56];
+  snprintf(buf, sizeof(buf), "/vmke_%d_%u", (int)getpid(), counter.fetch_add(1));
+  const int fd = shm_open(buf, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) return 1;
+  const size_t len = bytes ? bytes : 1;
+  if (ftruncate(fd, (off_t)len)) {
+    close(fd);
+    shm_unlink(buf);
+    return 1;
+  }
+  void* q = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (q == MAP_FAILED) {
+    shm_unlink(buf);
+    return 1;
+  }
+  *p = q;
+  *name = buf;
+  return 0;
+}
+
+int emul_shm_open(const char* name, size_t bytes, void** p) {
+  const int fd = shm_open(name, O_RDWR, 0600);
+  if (fd < 0) return 1;
+  void* q = mmap(nullptr, bytes ? bytes : 1, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (q == MAP_FAILED) return 1;
+  *p = q;
+  return 0;
+}
+
+void emul_shm_release(void* p, size_t bytes, const char* name, bool owner) {
+  munmap(p, bytes ? bytes : 1);
+  if (owner) shm_unlink(name);
+}
 
 double emul_now_ms() {
   timespec ts;
