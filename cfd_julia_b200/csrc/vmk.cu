@@ -216,7 +216,7 @@ struct vmk_plan {
   bool uploaded = false;
   int64_t launches = 0, graph_launches = 12;
   int k4_rows = 32, k4_ahead = 4;
-  int k1_group = 1, k3_group = 1, k1_prefetch = 1, k2_prefetch = 1, k3_prefetch = 0;
+  int k1_group = 1, k3_group = 1, k1_prefetch = 0, k2_prefetch = 0, k3_prefetch = 0;
   int use_graph = 1;
 #ifndef VMK_EMUL
   std::map<StepParams, cudaGraphExec_t> graphs;
