@@ -68,6 +68,10 @@ VMK_HD double2 cmul(double2 a, double2 b) {
 VMK_HD double2 cmulc(double2 a, double2 b) {  // a * conj(b)
   return mk2(fma_(a.x, b.x, a.y * b.y), fma_(a.y, b.x, -(a.x * b.y)));
 }
+VMK_HD double2 csqr(double2 a) {  // a^2: 4 FP64 instructions
+  const double t = a.x * a.y;
+  return mk2(fma_(a.x, a.x, -(a.y * a.y)), t + t);
+}
 VMK_HD double2 cconj(double2 a) { return mk2(a.x, -a.y); }
 VMK_HD double2 cscale(double2 a, double s) { return mk2(a.x * s, a.y * s); }
 

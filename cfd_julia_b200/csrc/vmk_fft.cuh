@@ -220,10 +220,24 @@ struct Fft {
       (void)base_pos<K>(t, u, low);
       static_for<0, r>([&](auto p_) {
         constexpr int p = decltype(p_)::value;
-        double2 y = a[brev(p, b)];
-        if constexpr (K < P - 1 && p > 0) y = cmul(y, twiddle<K>(tw, low * p));
-        v[u * r + p] = y;
+        v[u * r + p] = a[brev(p, b)];
       });
+      if constexpr (K < P - 1) {
+        // W^(low p): only the odd powers are read from the table (lanes hold consecutive `low`, so an odd stride is
+        // bank-conflict free while p = 2, 4, 8 were 2-, 4-, 8-way conflicts); even powers follow by squaring
+        static_for<0, r / 2>([&](auto h_) {
+          constexpr int q = 2 * decltype(h_)::value + 1;
+          double2 w = twiddle<K>(tw, low * q);
+          v[u * r + q] = cmul(v[u * r + q], w);
+          static_for<1, ilog2c(r)>([&](auto s_) {
+            constexpr int m = q << decltype(s_)::value;
+            if constexpr (m < r) {
+              w = csqr(w);
+              v[u * r + m] = cmul(v[u * r + m], w);
+            }
+          });
+        });
+      }
     });
   }
   // inverse pass K: conjugate twiddle, then conjugate network.  v[u*r+q] <- x[q].
@@ -237,10 +251,22 @@ struct Fft {
       (void)base_pos<K>(t, u, low);
       static_for<0, r>([&](auto p_) {
         constexpr int p = decltype(p_)::value;
-        double2 y = v[u * r + p];
-        if constexpr (K < P - 1 && p > 0) y = cmulc(y, twiddle<K>(tw, low * p));
-        a[p] = y;
+        a[p] = v[u * r + p];
       });
+      if constexpr (K < P - 1) {
+        static_for<0, r / 2>([&](auto h_) {
+          constexpr int q = 2 * decltype(h_)::value + 1;
+          double2 w = twiddle<K>(tw, low * q);
+          a[q] = cmulc(a[q], w);
+          static_for<1, ilog2c(r)>([&](auto s_) {
+            constexpr int m = q << decltype(s_)::value;
+            if constexpr (m < r) {
+              w = csqr(w);
+              a[m] = cmulc(a[m], w);
+            }
+          });
+        });
+      }
       Net<r, +1, 0>::run(a);
       static_for<0, r>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
