@@ -92,6 +92,9 @@ template <int MODE>
 struct K4Body {
   VMK_HD static void run(const Ctx& c, const K4Args& a) { k4_body<MODE>(c, a); }
 };
+struct K6Push {
+  VMK_HD static void run(const Ctx& c, const K6Args& a) { k6_push_body(c, a); }
+};
 struct K5Unpack {
   VMK_HD static void run(const Ctx& c, const K5Args& a) { k5_unpack_body(c, a); }
 };
@@ -211,7 +214,7 @@ struct vmk_plan {
   double div_dx = 0, div_dy = 0, div_eps = 0, div_aa = 0;
   Stream st, st_copy;
   Event ev0, ev1, ev_join, ev_chunk[8];
-  int a2a_chunks = 4;
+  int a2a_chunks = 2, a2a_engine = 1, a2a_ctas = 128;
   bool ev_valid = false;
   bool uploaded = false;
   int64_t launches = 0, graph_launches = 12;
@@ -402,12 +405,30 @@ int launch_k1(vmk_plan* p, const double* src) {
     if (P > 1) {
       VMK_TRY(be_event_record(p->ev_chunk[c], p->st));
       VMK_TRY(be_stream_wait(p->st_copy, p->ev_chunk[c]));
-      const size_t width = sizeof(double2) * (size_t)(2 * np);
-      for (int q = 0; q + 1 < P; q++) {
-        const int h = (p->rank + 1 + q) % P;  // start with the neighbour so the ranks do not all hit one peer
-        VMK_TRY(be_d2d_2d(p->peer_T[h] + p->j0 + 2 * pair0, sizeof(double2) * (size_t)N,
-                          p->S + (size_t)h * R * p->NJ + 2 * pair0, sizeof(double2) * (size_t)p->NJ, width, (size_t)R,
-                          p->st_copy));
+      if (p->a2a_engine) {  // copy engines: one strided peer copy per destination
+        const size_t width = sizeof(double2) * (size_t)(2 * np);
+        for (int q = 0; q + 1 < P; q++) {
+          const int h = (p->rank + 1 + q) % P;  // start with the neighbour so the ranks do not all hit one peer
+          VMK_TRY(be_d2d_2d(p->peer_T[h] + p->j0 + 2 * pair0, sizeof(double2) * (size_t)N,
+                            p->S + (size_t)h * R * p->NJ + 2 * pair0, sizeof(double2) * (size_t)p->NJ, width,
+                            (size_t)R, p->st_copy));
+        }
+      } else {  // SM push kernel
+        K6Args k;
+        k.S = p->S;
+        for (int r = 0; r < kMaxPeers; r++) k.T.p[r] = r < P ? (void*)p->peer_T[r] : nullptr;
+        k.N = N;
+        k.NJ = p->NJ;
+        k.R = R;
+        k.j0 = p->j0;
+        k.col0 = 2 * pair0;
+        k.ncols = 2 * np;
+        k.rank = p->rank;
+        k.nranks = P;
+        const int items = (P - 1) * R;
+        const int grid = items < p->a2a_ctas ? items : p->a2a_ctas;
+        VMK_TRY((be_launch<K6Push, K6Args, kK6Threads, 4>(grid, 0, k, p->st_copy)));
+        p->launches++;
       }
     }
   }
@@ -484,6 +505,10 @@ int launch_k4(vmk_plan* p, int mode, int win, int wn, int out, const StepParams&
   a.dt = sp.dt;
   const int cols = p->N / kK4Cols, tw = cols < kK4Threads ? cols : kK4Threads, groups = kK4Threads / tw;
   const int ctas_x = cols / tw;
+  // small slabs: shorter row marches so that the grid is several waves of resident CTAs (3 per SM)
+  while (a.rows_per_cta > 4 &&
+         ctas_x * ((p->NJ + groups * a.rows_per_cta - 1) / (groups * a.rows_per_cta)) < 6 * 3 * p->sms)
+    a.rows_per_cta /= 2;
   const int rows_per = groups * a.rows_per_cta;
   const int grid = ctas_x * ((p->NJ + rows_per - 1) / rows_per);
   Timed t(p, KI_K4);
@@ -958,10 +983,12 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
   const std::string k(key);
   int* knob = k == "k1_group" ? &p->k1_group : k == "k3_group" ? &p->k3_group : k == "k1_prefetch" ? &p->k1_prefetch
               : k == "k2_prefetch" ? &p->k2_prefetch : k == "k3_prefetch" ? &p->k3_prefetch
-              : k == "k4_ahead" ? &p->k4_ahead : k == "a2a_chunks" ? &p->a2a_chunks : nullptr;
+              : k == "k4_ahead" ? &p->k4_ahead : k == "a2a_chunks" ? &p->a2a_chunks
+              : k == "a2a_engine" ? &p->a2a_engine : k == "a2a_ctas" ? &p->a2a_ctas : nullptr;
   if (knob) {
-    if (value < 0 || value > 64 || (value == 0 && k.find("group") != std::string::npos))
-      return fail(VMK_EARG, "option value out of range");
+    const int64_t hi = k == "a2a_ctas" ? 4096 : k == "a2a_chunks" ? 8 : 64;
+    const int64_t lo = (k == "a2a_ctas" || k == "a2a_chunks" || k.find("group") != std::string::npos) ? 1 : 0;
+    if (value < lo || value > hi) return fail(VMK_EARG, "option value out of range");
     *knob = (int)value;
     drop_graphs(p);
   } else if (k == "graph") {

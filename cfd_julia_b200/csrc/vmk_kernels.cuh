@@ -488,6 +488,41 @@ VMK_HD void k4_body(const Ctx& c, const K4Args& a) {
   }
 }
 
+// ======================================== K6 ====================================================
+// Forward transpose of the distributed FFT as an SM copy: rows of S owned by rank h (R rows of NJ complex, columns
+// [col0, col0+ncols) of this launch) are stored into T_h[row][j0 + col0 ...] with coalesced 16-byte lanes -- NVLink
+// stores in runs of ncols*16 bytes.  Runs on a second stream next to the K1 launch that produces the next columns.
+struct K6Args {
+  const double2* S;  // local K1 output [N/2][NJ]
+  PeerPtrs T;        // every rank's spectrum buffer [R][N]
+  int N, NJ, R, j0, col0, ncols, rank, nranks;
+};
+constexpr int kK6Threads = 128;
+
+VMK_HD void k6_push_body(const Ctx& c, const K6Args& a) {
+  const int items = (a.nranks - 1) * a.R;
+  for (int it = c.bid; it < items; it += c.nblk) {
+    const int q = it / a.R, row = it % a.R;
+    const int h = (a.rank + 1 + q) % a.nranks;  // neighbour first: the ranks do not all hit one peer at a time
+    const double2* src = a.S + (size_t)(h * a.R + row) * a.NJ + a.col0;
+    double2* dst = reinterpret_cast<double2*>(a.T.p[h]) + (size_t)row * a.N + a.j0 + a.col0;
+    // 8 independent 16-byte loads in flight per thread before the (remote) stores
+    for (int i0 = 0; i0 < a.ncols; i0 += 8 * kK6Threads) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = i0 + c.tid + u * kK6Threads;
+        if (i < a.ncols) v[u] = ld_stream2(src + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = i0 + c.tid + u * kK6Threads;
+        if (i < a.ncols) st_stream2(dst + i, v[u]);
+      }
+    }
+  }
+}
+
 // ======================================== K5 ====================================================
 // Conversions between the caller's ghosted column-major layout and the device slab (vm.jl:30-38,89,
 // Common.jl:138-146: the ghost fills exist only on the host side of the boundary).
