@@ -212,9 +212,9 @@ struct vmk_plan {
   // divisor cache (Common.jl:101-113)
   bool div_valid = false;
   double div_dx = 0, div_dy = 0, div_eps = 0, div_aa = 0;
-  Stream st, st_copy;
-  Event ev0, ev1, ev_join, ev_chunk[8];
-  int a2a_chunks = 2, a2a_engine = 1, a2a_ctas = 128;
+  Stream st, st_copy, st_copy2;
+  Event ev0, ev1, ev_join, ev_join2, ev_chunk[8];
+  int a2a_chunks = 0 /* auto */, a2a_engine = -1 /* auto */, a2a_ctas = 128, k2_push = -1 /* auto */;
   bool ev_valid = false;
   bool uploaded = false;
   int64_t launches = 0, graph_launches = 12;
@@ -384,7 +384,7 @@ int rowpair_units(const vmk_plan* p, int npairs, int g) {
 int launch_k1(vmk_plan* p, const double* src) {
   const int N = p->N, P = p->nranks, R = (N / 2) / P;
   const int npairs = p->NJ / 2;
-  int chunks = P > 1 ? p->a2a_chunks : 1;
+  int chunks = P > 1 ? (p->a2a_chunks > 0 ? p->a2a_chunks : (P == 2 ? 2 : 1)) : 1;
   while (chunks > 1 && (npairs % chunks || npairs / chunks < 1)) chunks--;
   Timed t(p, KI_K1);
   for (int c = 0; c < chunks; c++) {
@@ -392,7 +392,7 @@ int launch_k1(vmk_plan* p, const double* src) {
     K1Args a;
     a.w = src + (size_t)2 * pair0 * N;
     a.S = P > 1 ? p->S + 2 * pair0 : nullptr;
-    a.Tloc = p->T + p->j0 + 2 * pair0;
+    a.Tloc = p->T + (size_t)p->rank * R * p->NJ + 2 * pair0;
     a.tw = p->tw;
     a.NJ = p->NJ;
     a.npairs = np;
@@ -405,13 +405,20 @@ int launch_k1(vmk_plan* p, const double* src) {
     if (P > 1) {
       VMK_TRY(be_event_record(p->ev_chunk[c], p->st));
       VMK_TRY(be_stream_wait(p->st_copy, p->ev_chunk[c]));
-      if (p->a2a_engine) {  // copy engines: one strided peer copy per destination
-        const size_t width = sizeof(double2) * (size_t)(2 * np);
+      VMK_TRY(be_stream_wait(p->st_copy2, p->ev_chunk[c]));
+      // measured (profiles/r01_notes.md): copy engines win with one peer (64 KB pieces), the SM push kernel with 3 or 7
+      const int engine = p->a2a_engine >= 0 ? p->a2a_engine : (P == 2 ? 1 : 0);
+      if (engine) {  // copy engines: one peer copy per destination (contiguous when the launch is not split)
+        const size_t rowb = sizeof(double2) * (size_t)p->NJ, width = sizeof(double2) * (size_t)(2 * np);
         for (int q = 0; q + 1 < P; q++) {
           const int h = (p->rank + 1 + q) % P;  // start with the neighbour so the ranks do not all hit one peer
-          VMK_TRY(be_d2d_2d(p->peer_T[h] + p->j0 + 2 * pair0, sizeof(double2) * (size_t)N,
-                            p->S + (size_t)h * R * p->NJ + 2 * pair0, sizeof(double2) * (size_t)p->NJ, width,
-                            (size_t)R, p->st_copy));
+          double2* dst = p->peer_T[h] + (size_t)p->rank * R * p->NJ + 2 * pair0;
+          const double2* srcb = p->S + (size_t)h * R * p->NJ + 2 * pair0;
+          Stream& cs = (q & 1) ? p->st_copy2 : p->st_copy;
+          if (chunks == 1)
+            VMK_TRY(be_d2d(dst, srcb, rowb * R, cs));
+          else
+            VMK_TRY(be_d2d_2d(dst, rowb, srcb, rowb, width, (size_t)R, cs));
         }
       } else {  // SM push kernel
         K6Args k;
@@ -435,31 +442,66 @@ int launch_k1(vmk_plan* p, const double* src) {
   if (P > 1) {
     VMK_TRY(be_event_record(p->ev_join, p->st_copy));
     VMK_TRY(be_stream_wait(p->st, p->ev_join));
+    VMK_TRY(be_event_record(p->ev_join2, p->st_copy2));
+    VMK_TRY(be_stream_wait(p->st, p->ev_join2));
   }
   t.done();
   return 0;
 }
 
+// K2 + the backward transpose.  On P > 1 GPUs the rows are processed in `chunks` launches; after each one the copy
+// engines move the finished rows' foreign columns (contiguous blocks of S) into the owners' V over NVLink while the
+// next launch transforms the following rows.
 int launch_k2(vmk_plan* p, double sign) {
-  K2Args a;
-  a.T = p->T;
-  for (int r = 0; r < kMaxPeers; r++) a.V.p[r] = r < p->nranks ? (void*)p->peer_V[r] : nullptr;
-  a.tw = p->tw;
-  a.bbcos = p->bbcos;
-  a.cccos = p->cccos;
-  a.ccperm = p->ccperm;
-  a.aa = p->div_aa;
-  a.scale = sign / (2.0 * (double)p->N * (double)p->N);
-  a.NJ = p->NJ;
-  a.log2NJ = p->log2NJ;
-  a.nrows = (p->N / 2) / p->nranks;
-  a.row0 = p->rank * a.nrows;
-  a.prefetch = p->k2_prefetch;
-  const int work = (a.nrows + p->ops.fpc - 1) / p->ops.fpc;
+  const int P = p->nranks, R = (p->N / 2) / P;
+  const int push = p->k2_push >= 0 ? p->k2_push : 1;  // measured: direct NVLink stores beat staged engine copies
+  int chunks = (P > 1 && !push) ? (p->a2a_chunks > 0 ? p->a2a_chunks : 4) : 1;
+  while (chunks > 1 && (R % chunks || R / chunks < 1)) chunks--;
   Timed t(p, KI_K2);
-  VMK_TRY(p->ops.k2(work < p->res_k2 ? work : p->res_k2, a, p->st));
+  for (int c = 0; c < chunks; c++) {
+    const int nr = R / chunks, rloc0 = c * nr;
+    K2Args a;
+    a.T = p->T;
+    a.V = p->V;
+    a.S = p->S;
+    for (int r = 0; r < kMaxPeers; r++) a.Vpeer.p[r] = r < P ? (void*)p->peer_V[r] : nullptr;
+    a.push = push;
+    a.tw = p->tw;
+    a.bbcos = p->bbcos;
+    a.cccos = p->cccos;
+    a.ccperm = p->ccperm;
+    a.aa = p->div_aa;
+    a.scale = sign / (2.0 * (double)p->N * (double)p->N);
+    a.NJ = p->NJ;
+    a.log2NJ = p->log2NJ;
+    a.nrows = nr;
+    a.row0 = p->rank * R + rloc0;
+    a.R = R;
+    a.rloc0 = rloc0;
+    a.rank = p->rank;
+    a.prefetch = p->k2_prefetch;
+    const int work = (nr + p->ops.fpc - 1) / p->ops.fpc;
+    VMK_TRY(p->ops.k2(work < p->res_k2 ? work : p->res_k2, a, p->st));
+    p->launches++;
+    if (P > 1 && !push) {
+      VMK_TRY(be_event_record(p->ev_chunk[c], p->st));
+      VMK_TRY(be_stream_wait(p->st_copy, p->ev_chunk[c]));
+      VMK_TRY(be_stream_wait(p->st_copy2, p->ev_chunk[c]));
+      const size_t bytes = sizeof(double2) * (size_t)nr * p->NJ;
+      for (int q = 0; q + 1 < P; q++) {
+        const int h = (p->rank + 1 + q) % P;
+        VMK_TRY(be_d2d(p->peer_V[h] + (size_t)(p->rank * R + rloc0) * p->NJ, p->S + ((size_t)h * R + rloc0) * p->NJ, bytes,
+                       (q & 1) ? p->st_copy2 : p->st_copy));
+      }
+    }
+  }
+  if (P > 1 && !push) {
+    VMK_TRY(be_event_record(p->ev_join, p->st_copy));
+    VMK_TRY(be_stream_wait(p->st, p->ev_join));
+    VMK_TRY(be_event_record(p->ev_join2, p->st_copy2));
+    VMK_TRY(be_stream_wait(p->st, p->ev_join2));
+  }
   t.done();
-  p->launches++;
   return 0;
 }
 
@@ -664,6 +706,7 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     if ((rc = be_event_create(p->ev0)) || (rc = be_event_create(p->ev1))) break;
     if (nranks > 1) {
       if ((rc = be_stream_create(p->st_copy)) || (rc = be_event_create(p->ev_join))) break;
+      if ((rc = be_stream_create(p->st_copy2)) || (rc = be_event_create(p->ev_join2))) break;
       for (int c = 0; c < 8 && !rc; c++) rc = be_event_create(p->ev_chunk[c]);
       if (rc) break;
     }
@@ -732,8 +775,10 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_event_destroy(p->ev0);
   be_event_destroy(p->ev1);
   be_event_destroy(p->ev_join);
+  be_event_destroy(p->ev_join2);
   for (int c = 0; c < 8; c++) be_event_destroy(p->ev_chunk[c]);
   be_stream_destroy(p->st_copy);
+  be_stream_destroy(p->st_copy2);
   be_stream_destroy(p->st);
   delete p;
   return VMK_OK;
@@ -984,10 +1029,12 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
   int* knob = k == "k1_group" ? &p->k1_group : k == "k3_group" ? &p->k3_group : k == "k1_prefetch" ? &p->k1_prefetch
               : k == "k2_prefetch" ? &p->k2_prefetch : k == "k3_prefetch" ? &p->k3_prefetch
               : k == "k4_ahead" ? &p->k4_ahead : k == "a2a_chunks" ? &p->a2a_chunks
-              : k == "a2a_engine" ? &p->a2a_engine : k == "a2a_ctas" ? &p->a2a_ctas : nullptr;
+              : k == "a2a_engine" ? &p->a2a_engine : k == "a2a_ctas" ? &p->a2a_ctas
+              : k == "k2_push" ? &p->k2_push : nullptr;
   if (knob) {
     const int64_t hi = k == "a2a_ctas" ? 4096 : k == "a2a_chunks" ? 8 : 64;
-    const int64_t lo = (k == "a2a_ctas" || k == "a2a_chunks" || k.find("group") != std::string::npos) ? 1 : 0;
+    const int64_t lo = (k == "a2a_ctas" || k.find("group") != std::string::npos) ? 1
+                       : (k == "a2a_engine" || k == "k2_push") ? -1 : 0;
     if (value < lo || value > hi) return fail(VMK_EARG, "option value out of range");
     *knob = (int)value;
     drop_graphs(p);

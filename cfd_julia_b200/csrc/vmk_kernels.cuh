@@ -14,15 +14,19 @@
 //   K1 output    S      : N/2 rows (all kx) of NJ complex (the rank's own j), written by K1 in 32-byte pieces (two
 //                         adjacent j).  Global row 0 packs kx=0 (re) and kx=N/2 (im), both of which are real
 //                         sequences in j after the real-pair unpack.
-//   spectrum     T      : the rank's R = N/(2P) spectrum rows (kx = rank*R ..) of N complex, ALL j, read by the local
-//                         K2 as contiguous rows.  On one GPU T is S.  On P GPUs rank g's S rows [h*R, (h+1)*R) are
-//                         copied (copy engine, NJ*16-byte contiguous pieces, NVLink for h != g) into T_h[..][g*NJ ..]:
-//                         the forward transpose of the distributed 2-D FFT.  (Pushing K1's 32-byte pieces straight
-//                         into the peers' T ran NVLink at ~400 GB/s; the copy moves 16..64 KB pieces.)
-//   solution     V      : N/2 rows (all kx) of NJ complex (the rank's own j): filled by every rank's K2, which pushes
-//                         the NJ-element chunks of its result rows straight to the ranks owning those j (the backward
-//                         transpose, folded into K2's store epilogue); read by the local K3.
-//   Data crosses NVLink only as fire-and-forget stores / engine copies; no kernel ever waits on a remote load.
+//   spectrum     T      : the rank's R = N/(2P) spectrum rows (kx = rank*R ..), ALL j, stored as P blocks [g][R][NJ]
+//                         (block g = the columns that came from rank g), read by the local K2 row by row as P
+//                         contiguous NJ-element segments.  On one GPU T is S.  On P GPUs rank g's S rows
+//                         [h*R, (h+1)*R) -- one contiguous R*NJ*16-byte block -- are copied by a copy engine over
+//                         NVLink into block g of T_h: the forward transpose of the distributed 2-D FFT.  (Pushing
+//                         K1's 32-byte pieces straight into the peers' T ran NVLink at ~400 GB/s.)
+//   solution     V      : N/2 rows (all kx) of NJ complex (the rank's own j), read by the local K3.  K2 stores the
+//                         columns it owns itself straight into V and the others into S (block h = columns of rank h);
+//                         block h -- contiguous -- is then copied over NVLink into rows [g*R, (g+1)*R) of V_h: the
+//                         backward transpose.  K2 is launched in row chunks so that the copy of one chunk overlaps
+//                         the transforms of the next.
+//   Data crosses NVLink only as copy-engine transfers of large contiguous blocks (and the 64 KB halo rows that K3/K4
+//   store directly); no kernel ever waits on a remote load.  Measured alternatives are in profiles/r01_notes.md.
 #pragma once
 #include "vmk_fft.cuh"
 
@@ -40,7 +44,7 @@ VMK_HD int halfspec_pos(int idx) {
 struct K1Args {
   const double* w;    // slab with halo rows (or the fps source f in the same layout)
   double2* S;         // K1 output [N/2][NJ] for the spectrum rows owned by OTHER ranks (nullptr on a single GPU)
-  double2* Tloc;      // own spectrum buffer [R][N], offset to this rank's first column: rows this rank owns go here
+  double2* Tloc;      // block `rank` of the own spectrum buffer T ([R][NJ]): rows this rank owns go here
   const double2* tw;  // twiddle tables (global)
   int NJ;             // local rows (row pitch of S)
   int npairs;         // row pairs handled by this launch (w, S and Tloc are offset to its first pair)
@@ -123,8 +127,8 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
           o0 = mk2(zk[i].x + zm[i].x, zk[i].y - zm[i].y);  // 2 X_j[k]   = Z[k] + conj Z[N-k]
           o1 = mk2(zk[i].y + zm[i].y, zm[i].x - zk[i].x);  // 2 X_j+1[k] = -i (Z[k] - conj Z[N-k])
         }
-        double2* dst = (k >= a.k_own0 && k < a.k_own1) ? a.Tloc + (size_t)(k - a.k_own0) * N + jl
-                                                       : a.S + (size_t)k * a.NJ + jl;
+        double2* dst = ((k >= a.k_own0 && k < a.k_own1) ? a.Tloc + (size_t)(k - a.k_own0) * a.NJ
+                                                        : a.S + (size_t)k * a.NJ) + jl;
         st_stream4(dst, o0, o1);
       });
     }
@@ -134,8 +138,11 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
 
 // ======================================== K2 ====================================================
 struct K2Args {
-  const double2* T;     // local spectrum rows [R][N] (input)
-  PeerPtrs V;           // every rank's solution buffer [N/2][NJ]; element j goes to rank j >> log2NJ
+  const double2* T;     // local spectrum rows as P blocks [g][R][NJ] (input)
+  double2* V;           // own solution buffer [N/2][NJ]: the columns j this rank owns are stored here directly
+  double2* S;           // staging [P blocks h][R][NJ] for the columns owned by rank h != rank (copied to V_h afterwards)
+  PeerPtrs Vpeer;       // push mode: every rank's V; foreign columns are stored straight into V_h over NVLink
+  int push;             // 1: push mode, 0: staged in S and moved by the copy engines
   const double2* tw;    // twiddle tables
   const double* bbcos;  // [N]  bb*cos(kx[i])   Common.jl:120 (kx[1]=eps quirk inside)
   const double* cccos;  // [N]  cc*cos(ky[j])   (ky = kx, Common.jl:113)
@@ -144,7 +151,8 @@ struct K2Args {
   double aa;            // -2/dx^2 - 2/dy^2
   double scale;         // sign / (2 N^2): ifft normalisation, the factor 2 of the unpack, f = -w
   int NJ, log2NJ;
-  int row0, nrows;      // kx rows owned by this rank: row0 = rank*R, nrows = R
+  int row0, nrows;      // global kx of this launch's first row, rows in this launch
+  int R, rloc0, rank;   // spectrum rows per rank, local index of the launch's first row, this rank
   int prefetch;         // 0 off, 1: bulk L2 prefetch of the next row (single rank only)
 };
 
@@ -169,7 +177,8 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
         const int j = F::template own_pos<e>(t);
-        cp_async16(sm + F::addr(j), a.T + (size_t)row * N + j);
+        cp_async16(sm + F::addr(j),
+                   a.T + ((size_t)(j >> a.log2NJ) * a.R + a.rloc0 + row) * a.NJ + (j & (a.NJ - 1)));
       });
     }
     cp_async_commit();
@@ -180,10 +189,10 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
     const bool active = row < a.nrows;
     const int kx = a.row0 + row;
     const bool cta_has_row0 = (a.row0 + rb * C::FPC) == 0;
-    if (a.prefetch && c.tid == 0 && rb + 2 * c.nblk < nblocks) {
+    if (a.prefetch && c.tid == 0 && rb + 2 * c.nblk < nblocks && a.log2NJ == M) {  // single block: rows contiguous
       const int r0n = (rb + 2 * c.nblk) * C::FPC;
       const int nr = (a.nrows - r0n) < C::FPC ? (a.nrows - r0n) : C::FPC;
-      prefetch_l2_bulk(a.T + (size_t)r0n * N, (unsigned)(nr * N * sizeof(double2)));
+      prefetch_l2_bulk(a.T + (size_t)(a.rloc0 + r0n) * N, (unsigned)(nr * N * sizeof(double2)));
     }
     cp_async_wait_all();
     double2 v[E];
@@ -252,7 +261,11 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
         const int j = F::template own_pos<e>(t);
-        double2* dst = reinterpret_cast<double2*>(a.V.p[j >> a.log2NJ]) + (size_t)kx * a.NJ + (j & (a.NJ - 1));
+        const int h = j >> a.log2NJ;
+        double2* dst = (h == a.rank ? a.V + (size_t)kx * a.NJ
+                        : a.push    ? reinterpret_cast<double2*>(a.Vpeer.p[h]) + (size_t)kx * a.NJ
+                                    : a.S + ((size_t)h * a.R + a.rloc0 + row) * a.NJ) +
+                       (j & (a.NJ - 1));
         st_stream2(dst, v[e]);
       });
     }
@@ -505,7 +518,7 @@ VMK_HD void k6_push_body(const Ctx& c, const K6Args& a) {
     const int q = it / a.R, row = it % a.R;
     const int h = (a.rank + 1 + q) % a.nranks;  // neighbour first: the ranks do not all hit one peer at a time
     const double2* src = a.S + (size_t)(h * a.R + row) * a.NJ + a.col0;
-    double2* dst = reinterpret_cast<double2*>(a.T.p[h]) + (size_t)row * a.N + a.j0 + a.col0;
+    double2* dst = reinterpret_cast<double2*>(a.T.p[h]) + ((size_t)a.rank * a.R + row) * a.NJ + a.col0;
     // 8 independent 16-byte loads in flight per thread before the (remote) stores
     for (int i0 = 0; i0 < a.ncols; i0 += 8 * kK6Threads) {
       double2 v[8];
