@@ -114,7 +114,8 @@ void fill_twiddles(double2* tw) {
     for (int x = 0; x < len; x++) {
       const long double ang = tau * (long double)x / (long double)B;
       tw[off + x].x = (double)cosl(ang);
-      tw[off + x].y = (double)(-sinl(ang));
+      // octant tables hold (cos, +sin) of the first octant (the lookup reflects and signs them), the others W = cos - i sin
+      tw[off + x].y = C::tw_oct(k) ? (double)sinl(ang) : (double)(-sinl(ang));
     }
   }
 }
@@ -219,7 +220,7 @@ struct vmk_plan {
   bool uploaded = false;
   int64_t launches = 0, graph_launches = 12;
   int k4_rows = 32, k4_ahead = 4;
-  int k1_group = 1, k3_group = 1, k1_prefetch = 0, k2_prefetch = 0, k3_prefetch = 0;
+  int k1_prefetch = 0, k2_prefetch = 0;
   int use_graph = 1;
 #ifndef VMK_EMUL
   std::map<StepParams, cudaGraphExec_t> graphs;
@@ -515,9 +516,7 @@ int launch_k3(vmk_plan* p) {
   a.hi_dst = p->peer_psi[next];
   a.NJ = p->NJ;
   a.npairs = p->NJ / 2;
-  a.group = p->k3_group;
-  a.prefetch = p->k3_prefetch;
-  const int work = rowpair_units(p, a.npairs, a.group);
+  const int work = rowpair_units(p, a.npairs, 1);
   Timed t(p, KI_K3);
   VMK_TRY(p->ops.k3(work < p->res_k3 ? work : p->res_k3, a, p->st));
   t.done();
@@ -1026,8 +1025,7 @@ int64_t vmk_launch_count(vmk_plan* p) { return p ? p->launches : 0; }
 int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
   if (!p || !key) return fail(VMK_EARG, "NULL argument");
   const std::string k(key);
-  int* knob = k == "k1_group" ? &p->k1_group : k == "k3_group" ? &p->k3_group : k == "k1_prefetch" ? &p->k1_prefetch
-              : k == "k2_prefetch" ? &p->k2_prefetch : k == "k3_prefetch" ? &p->k3_prefetch
+  int* knob = k == "k1_prefetch" ? &p->k1_prefetch : k == "k2_prefetch" ? &p->k2_prefetch
               : k == "k4_ahead" ? &p->k4_ahead : k == "a2a_chunks" ? &p->a2a_chunks
               : k == "a2a_engine" ? &p->a2a_engine : k == "a2a_ctas" ? &p->a2a_ctas
               : k == "k2_push" ? &p->k2_push : nullptr;

@@ -96,8 +96,13 @@ struct Net<1, SIGN, OFF> {
 };
 
 // ---- configuration ---------------------------------------------------------------------------
-template <int M_, int LE_, int P_, int B0_, int B1_, int B2_, int CT_, int MINB_, int B3_ = 0>
+// SPLIT_: the exchange buffer holds one double per position (real parts, then imaginary parts, three barriers per
+// exchange instead of one) and the table of the first pass is stored as one octant.  Both shrink shared memory so that
+// a separate full-row LANDING buffer fits next to them: the next row's asynchronous copies are then issued a whole
+// row ahead instead of only during the last butterflies (used for N = 8192, where one row fills an SM).
+template <int M_, int LE_, int P_, int B0_, int B1_, int B2_, int CT_, int MINB_, int B3_ = 0, bool SPLIT_ = false>
 struct FftCfg {
+  static constexpr bool SPLIT = SPLIT_;
   static constexpr int M = M_, N = 1 << M_, LE = LE_, E = 1 << LE_, T = N >> LE_, P = P_;
   static constexpr int CT = CT_ > T ? CT_ : T;  // CTA threads
   static constexpr int FPC = CT / T;            // transforms per CTA
@@ -113,15 +118,22 @@ struct FftCfg {
   static constexpr int SMN = N + (N >> PADSH);  // padded complex slots per transform
   // twiddle tables: pass k < P-1 uses W_{Bk}^x, Bk = 2^hi(k); full wave if small, else half wave
   VMK_HD static constexpr bool tw_full(int k) { return (1 << hi(k)) <= 1024; }
-  VMK_HD static constexpr int tw_len(int k) { return k >= P_ - 1 ? 0 : (tw_full(k) ? (1 << hi(k)) : (1 << (hi(k) - 1))); }
+  VMK_HD static constexpr bool tw_oct(int k) { return SPLIT_ && !tw_full(k); }  // one octant + 1 entries (+1 pad)
+  VMK_HD static constexpr int tw_len(int k) {
+    return k >= P_ - 1 ? 0 : (tw_full(k) ? (1 << hi(k)) : (tw_oct(k) ? (1 << (hi(k) - 3)) + 2 : (1 << (hi(k) - 1))));
+  }
   VMK_HD static constexpr int tw_off(int k) {
     int o = 0;
     for (int m = 0; m < k; m++) o += tw_len(m);
     return o;
   }
   static constexpr int TWN = tw_off(P_);  // total table entries (complex)
-  static constexpr size_t SMEM_DATA = sizeof(double2) * (size_t)SMN * FPC;
+  static constexpr size_t XBYTES = (SPLIT_ ? sizeof(double) : sizeof(double2)) * (size_t)SMN;  // exchange buffer
+  static constexpr size_t LANDBYTES = SPLIT_ ? sizeof(double2) * (size_t)N : 0;                // landing buffer
+  static constexpr size_t XSTRIDE = XBYTES + LANDBYTES;                                         // per transform
+  static constexpr size_t SMEM_DATA = XSTRIDE * FPC;
   static constexpr size_t SMEM_BYTES = SMEM_DATA + sizeof(double2) * (size_t)TWN;
+  static_assert(XBYTES % 16 == 0, "alignment");
   static_assert(B0_ + B1_ + (P_ > 2 ? B2_ : 0) + (P_ > 3 ? B3_ : 0) == M_, "pass bits must sum to M");
   static_assert(B0_ <= LE_ && B1_ <= LE_ && B2_ <= LE_ && B3_ <= LE_, "radix exceeds per-thread elements");
 };
@@ -134,12 +146,21 @@ template <> struct CfgFor<5>  { using type = FftCfg<5, 4, 2, 2, 3, 0, 128, 4>; }
 template <> struct CfgFor<6>  { using type = FftCfg<6, 4, 2, 3, 3, 0, 128, 4>; };
 template <> struct CfgFor<7>  { using type = FftCfg<7, 4, 2, 3, 4, 0, 128, 4>; };
 template <> struct CfgFor<8>  { using type = FftCfg<8, 4, 2, 4, 4, 0, 128, 4>; };
+#ifdef VMK_SPLIT_TEST  // test builds only: run the split-exchange / landing-buffer / octant-table path at small sizes too
+template <> struct CfgFor<9>  { using type = FftCfg<9, 4, 3, 3, 3, 3, 128, 1, 0, true>; };
+template <> struct CfgFor<10> { using type = FftCfg<10, 4, 3, 3, 3, 4, 128, 1, 0, true>; };
+template <> struct CfgFor<11> { using type = FftCfg<11, 4, 3, 3, 4, 4, 128, 1, 0, true>; };
+template <> struct CfgFor<12> { using type = FftCfg<12, 4, 3, 4, 4, 4, 256, 1, 0, true>; };
+#else
 template <> struct CfgFor<9>  { using type = FftCfg<9, 4, 3, 3, 3, 3, 128, 4>; };
 template <> struct CfgFor<10> { using type = FftCfg<10, 4, 3, 3, 3, 4, 128, 4>; };
 template <> struct CfgFor<11> { using type = FftCfg<11, 4, 3, 3, 4, 4, 128, 3>; };
 template <> struct CfgFor<12> { using type = FftCfg<12, 4, 3, 4, 4, 4, 256, 2>; };
-#ifdef VMK_M13_T512
+#endif
+#if defined(VMK_M13_T512)
 template <> struct CfgFor<13> { using type = FftCfg<13, 4, 4, 3, 3, 3, 512, 1, 4>; };
+#elif defined(VMK_M13_SPLIT)  // measured alternative (profiles/r01_notes.md): K1 -2 %, K2 +-0, K3 +12 %
+template <> struct CfgFor<13> { using type = FftCfg<13, 5, 3, 4, 4, 5, 256, 1, 0, true>; };
 #else
 template <> struct CfgFor<13> { using type = FftCfg<13, 5, 3, 4, 4, 5, 256, 1>; };
 #endif
@@ -150,6 +171,17 @@ struct Fft {
   static constexpr int E = C::E, T = C::T, P = C::P, M = C::M, N = C::N;
 
   VMK_HD static int addr(int pos) { return pos + (pos >> C::PADSH); }
+
+  // shared-memory carving: [transform g: exchange buffer | landing buffer] ... [twiddle tables]
+  VMK_HD static double2* xbuf(unsigned char* smem, int g) {
+    return reinterpret_cast<double2*>(smem + C::XSTRIDE * (size_t)g);
+  }
+  // where asynchronous copies of the next row land: a buffer of its own (SPLIT) or the exchange buffer itself
+  VMK_HD static double2* landing(unsigned char* smem, int g) {
+    return reinterpret_cast<double2*>(smem + C::XSTRIDE * (size_t)g + (C::SPLIT ? C::XBYTES : 0));
+  }
+  VMK_HD static int land_addr(int pos) { return C::SPLIT ? pos : addr(pos); }
+  VMK_HD static double2* tables(unsigned char* smem) { return reinterpret_cast<double2*>(smem + C::SMEM_DATA); }
 
   // position of element q of butterfly u of thread t in pass K
   template <int K>
@@ -187,12 +219,74 @@ struct Fft {
     });
   }
 
+  // one component (PART 0: real, 1: imaginary) of the registers to / from the split exchange buffer
+  template <int K, int PART>
+  VMK_HD static void store_part(const double2 (&v)[E], double* sd, int t) {
+    constexpr int b = C::bits(K), r = 1 << b, l = C::lo(K);
+    static_for<0, E / r>([&](auto u_) {
+      constexpr int u = decltype(u_)::value;
+      int low;
+      const int bp = base_pos<K>(t, u, low);
+      static_for<0, r>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        sd[addr(bp | (q << l))] = PART ? v[u * r + q].y : v[u * r + q].x;
+      });
+    });
+  }
+  template <int K, int PART>
+  VMK_HD static void load_part(double2 (&v)[E], const double* sd, int t) {
+    constexpr int b = C::bits(K), r = 1 << b, l = C::lo(K);
+    static_for<0, E / r>([&](auto u_) {
+      constexpr int u = decltype(u_)::value;
+      int low;
+      const int bp = base_pos<K>(t, u, low);
+      static_for<0, r>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        if constexpr (PART)
+          v[u * r + q].y = sd[addr(bp | (q << l))];
+        else
+          v[u * r + q].x = sd[addr(bp | (q << l))];
+      });
+    });
+  }
+  // registers in pass-KS layout -> registers in pass-KL layout.  A thread writes exactly the slots it read in the
+  // previous exchange, so no barrier is needed before the first store.
+  template <int KS, int KL>
+  VMK_HD static void exchange(const Ctx& c, double2 (&v)[E], double2* sm, int t) {
+    if constexpr (C::SPLIT) {
+      double* sd = reinterpret_cast<double*>(sm);
+      store_part<KS, 0>(v, sd, t);
+      c.sync();
+      load_part<KL, 0>(v, sd, t);
+      c.sync();
+      store_part<KS, 1>(v, sd, t);
+      c.sync();
+      load_part<KL, 1>(v, sd, t);
+    } else {
+      store_smem<KS>(v, sm, t);
+      c.sync();
+      load_smem<KL>(v, sm, t);
+    }
+  }
+
   // W_{2^hi(K)}^x, x < 2^hi(K); tw points at the start of all tables
   template <int K>
   VMK_HD static double2 twiddle(const double2* tw, int x) {
     const double2* tk = tw + C::tw_off(K);
     if constexpr (C::tw_full(K)) {
       return tk[x];
+    } else if constexpr (C::tw_oct(K)) {
+      // table: (cos, sin)(2 pi r / B), r = 0 .. B/8; the other seven octants by reflection
+      constexpr int ob = C::hi(K) - 3;
+      const int o = x >> ob;
+      int r = x & ((1 << ob) - 1);
+      if (o & 1) r = (1 << ob) - r;
+      const double2 cs = tk[r];
+      const bool swap = ((o ^ (o >> 1)) & 1) != 0;
+      double co = swap ? cs.y : cs.x, si = swap ? cs.x : cs.y;
+      if (((o + 2) >> 2) & 1) co = -co;
+      if (!((o >> 2) & 1)) si = -si;  // W = cos - i sin
+      return mk2(co, si);
     } else {
       constexpr int half = 1 << (C::hi(K) - 1);
       double2 w = tk[x & (half - 1)];
@@ -280,11 +374,7 @@ struct Fft {
     static_for<0, P>([&](auto k_) {
       constexpr int K = decltype(k_)::value;
       fwd_compute<K>(v, tw, t);
-      if constexpr (K < P - 1) {
-        store_smem<K>(v, sm, t);
-        c.sync();
-        load_smem<K + 1>(v, sm, t);
-      }
+      if constexpr (K < P - 1) exchange<K, K + 1>(c, v, sm, t);
     });
   }
   // registers hold last-pass layout on entry, pass-0 layout (natural positions) on exit
@@ -297,9 +387,7 @@ struct Fft {
       constexpr int K = P - 1 - decltype(k_)::value;
       inv_compute<K>(v, tw, t);
       if constexpr (K > 0) {
-        store_smem<K>(v, sm, t);
-        c.sync();
-        load_smem<K - 1>(v, sm, t);
+        exchange<K, K - 1>(c, v, sm, t);
         if constexpr (K == 1) after_last_exchange();
       }
     });

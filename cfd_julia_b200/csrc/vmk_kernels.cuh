@@ -59,19 +59,19 @@ template <class C>
 VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
   using F = Fft<C>;
   constexpr int N = C::N, E = C::E, T = C::T, P = C::P, NI = N / 2 / T;
-  double2* sm_all = reinterpret_cast<double2*>(c.smem);
-  double2* tw = sm_all + (size_t)C::SMN * C::FPC;
+  double2* tw = F::tables(c.smem);
   F::load_tables(c, tw, a.tw);
   c.sync();
   const int g = c.tid / T, t = c.tid % T;
-  double2* sm = sm_all + (size_t)C::SMN * g;
+  double2* sm = F::xbuf(c.smem, g);
+  double* rows = reinterpret_cast<double*>(F::landing(c.smem, g));  // the pair's two rows as [2][N] doubles
   const int nblocks = (a.npairs + C::FPC - 1) / C::FPC;
   // the T threads of a transform copy its two rows (contiguous 2N doubles) as N 16-byte chunks
   auto issue_rows = [&](int pb) {
     const int pair = pb * C::FPC + g;
     if (pb < nblocks && pair < a.npairs) {
       const char* src = reinterpret_cast<const char*>(a.w + (size_t)(2 * pair + 1) * N);
-      char* dst = reinterpret_cast<char*>(sm);
+      char* dst = reinterpret_cast<char*>(rows);
       static_for<0, E>([&](auto i_) {
         constexpr int i = decltype(i_)::value;
         cp_async16(dst + 16 * (t + T * i), src + 16 * (t + T * i));
@@ -93,7 +93,7 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
     c.sync();
     double2 v[E];
     {
-      const double* r0 = reinterpret_cast<const double*>(sm);
+      const double* r0 = rows;
       const double* r1 = r0 + N;
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
@@ -101,20 +101,47 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
         v[e] = active ? mk2(r0[pos], r1[pos]) : mk2(0.0, 0.0);
       });
     }
-    c.sync();  // all rows are in registers before the first exchange overwrites the buffer
+    c.sync();  // all rows are in registers
+    // SPLIT: the landing buffer is a buffer of its own, so the next pair's rows start streaming in right away;
+    // otherwise they share the exchange buffer and have to wait until the spectrum has been read back (below)
+    if constexpr (C::SPLIT) issue_rows(pb + c.nblk);
     F::forward(c, v, sm, tw, t);
-    F::template store_smem<P - 1>(v, sm, t);
-    c.sync();
     double2 zk[NI], zm[NI];
-    static_for<0, NI>([&](auto i_) {
-      constexpr int i = decltype(i_)::value;
-      const int pos = halfspec_pos<C>(t + T * i);
-      const int k = F::k_of_pos(pos);
-      zk[i] = sm[F::addr(pos)];                                  // k == 0: Z[0]
-      zm[i] = sm[F::addr(F::pos_of_k(k == 0 ? N / 2 : N - k))];  // k == 0: Z[N/2]
-    });
-    c.sync();  // the spectrum is in registers: the buffer is free for the next pair's rows
-    issue_rows(pb + c.nblk);
+    if constexpr (C::SPLIT) {
+      double* sd = reinterpret_cast<double*>(sm);
+      F::template store_part<P - 1, 0>(v, sd, t);
+      c.sync();
+      static_for<0, NI>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        const int pos = halfspec_pos<C>(t + T * i);
+        const int k = F::k_of_pos(pos);
+        zk[i].x = sd[F::addr(pos)];
+        zm[i].x = sd[F::addr(F::pos_of_k(k == 0 ? N / 2 : N - k))];
+      });
+      c.sync();
+      F::template store_part<P - 1, 1>(v, sd, t);
+      c.sync();
+      static_for<0, NI>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        const int pos = halfspec_pos<C>(t + T * i);
+        const int k = F::k_of_pos(pos);
+        zk[i].y = sd[F::addr(pos)];
+        zm[i].y = sd[F::addr(F::pos_of_k(k == 0 ? N / 2 : N - k))];
+      });
+      c.sync();  // the next pair's first exchange may overwrite the buffer
+    } else {
+      F::template store_smem<P - 1>(v, sm, t);
+      c.sync();
+      static_for<0, NI>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        const int pos = halfspec_pos<C>(t + T * i);
+        const int k = F::k_of_pos(pos);
+        zk[i] = sm[F::addr(pos)];                                  // k == 0: Z[0]
+        zm[i] = sm[F::addr(F::pos_of_k(k == 0 ? N / 2 : N - k))];  // k == 0: Z[N/2]
+      });
+      c.sync();  // the spectrum is in registers: the buffer is free for the next pair's rows
+      issue_rows(pb + c.nblk);
+    }
     if (active) {
       static_for<0, NI>([&](auto i_) {
         constexpr int i = decltype(i_)::value;
@@ -161,23 +188,23 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
   using F = Fft<C>;
   constexpr int N = C::N, E = C::E, T = C::T, P = C::P, M = C::M;
   constexpr int bl = C::bits(P - 1), rl = 1 << bl;
-  double2* sm_all = reinterpret_cast<double2*>(c.smem);
-  double2* tw = sm_all + (size_t)C::SMN * C::FPC;
+  double2* tw = F::tables(c.smem);
   F::load_tables(c, tw, a.tw);
   c.sync();
   const int g = c.tid / T, t = c.tid % T;
-  double2* sm = sm_all + (size_t)C::SMN * g;
+  double2* sm = F::xbuf(c.smem, g);
+  double2* land = F::landing(c.smem, g);
   const int nblocks = (a.nrows + C::FPC - 1) / C::FPC;
-  // A thread owns the same E slots of the exchange buffer (its pass-0 positions) at the start and at the end of a
-  // row's transform, so the NEXT row is copied there asynchronously, element by element from the owning ranks,
-  // while the current row's last butterflies and stores run; no barrier is involved.
+  // A thread owns the same E landing slots (its pass-0 positions) for every row, so the NEXT row is copied there
+  // asynchronously, element by element, without any barrier: right after the current row has been read out when
+  // the landing buffer is a buffer of its own (SPLIT), else during the current row's last butterflies and stores.
   auto issue_row = [&](int rb) {
     const int row = rb * C::FPC + g;
     if (rb < nblocks && row < a.nrows) {
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
         const int j = F::template own_pos<e>(t);
-        cp_async16(sm + F::addr(j),
+        cp_async16(land + F::land_addr(j),
                    a.T + ((size_t)(j >> a.log2NJ) * a.R + a.rloc0 + row) * a.NJ + (j & (a.NJ - 1)));
       });
     }
@@ -198,14 +225,42 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
     double2 v[E];
     static_for<0, E>([&](auto e_) {
       constexpr int e = decltype(e_)::value;
-      v[e] = active ? sm[F::addr(F::template own_pos<e>(t))] : mk2(0.0, 0.0);
+      v[e] = active ? land[F::land_addr(F::template own_pos<e>(t))] : mk2(0.0, 0.0);
     });
+    if constexpr (C::SPLIT) issue_row(rb + c.nblk);
     F::forward(c, v, sm, tw, t);
     // ---- divide (registers hold the last-pass layout: butterfly id = t + T*u, digit p) ----------
     if (cta_has_row0) {
-      // packed DC/Nyquist row: C[ky] = A^[ky] + i B^[ky]; separate, divide each by its own divisor, repack
-      F::template store_smem<P - 1>(v, sm, t);
-      c.sync();
+      // packed DC/Nyquist row: C[ky] = A^[ky] + i B^[ky]; separate, divide each by its own divisor, repack.
+      // cm[] <- the value at the mirrored index (N - k) & (N - 1) of every register slot, via the exchange buffer
+      double2 cm[E];
+      auto mirror = [&](int e_rt, int u, int p) {
+        (void)e_rt;
+        return F::addr(F::pos_of_k((N - F::k_of_pos(((t + T * u) << bl) | p)) & (N - 1)));
+      };
+      if constexpr (C::SPLIT) {
+        double* sd = reinterpret_cast<double*>(sm);
+        F::template store_part<P - 1, 0>(v, sd, t);
+        c.sync();
+        static_for<0, E>([&](auto e_) {
+          constexpr int e = decltype(e_)::value;
+          cm[e].x = sd[mirror(e, e / rl, e % rl)];
+        });
+        c.sync();
+        F::template store_part<P - 1, 1>(v, sd, t);
+        c.sync();
+        static_for<0, E>([&](auto e_) {
+          constexpr int e = decltype(e_)::value;
+          cm[e].y = sd[mirror(e, e / rl, e % rl)];
+        });
+      } else {
+        F::template store_smem<P - 1>(v, sm, t);
+        c.sync();
+        static_for<0, E>([&](auto e_) {
+          constexpr int e = decltype(e_)::value;
+          cm[e] = sm[mirror(e, e / rl, e % rl)];
+        });
+      }
       if (kx == 0) {
         const double ab0 = a.aa + ld_ro(a.bbcos + 0), abn = a.aa + ld_ro(a.bbcos + N / 2);
         static_for<0, E / rl>([&](auto u_) {
@@ -214,12 +269,12 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
           static_for<0, rl>([&](auto p_) {
             constexpr int p = decltype(p_)::value;
             const int k = F::k_of_pos((id << bl) | p);
-            const double2 cm = sm[F::addr(F::pos_of_k((N - k) & (N - 1)))];
+            const double2 cmv = cm[u * rl + p];
             const double2 ck = v[u * rl + p];
             const double cc = ld_ro(a.cccos + k);
             const double g0 = 0.5 * a.scale * rcp_rn(ab0 + cc), gn = 0.5 * a.scale * rcp_rn(abn + cc);
-            double2 pp = cscale(mk2(ck.x + cm.x, ck.y - cm.y), g0);  // A^' = (C + conj Cm)/2 * g
-            const double2 qq = cscale(mk2(ck.y + cm.y, cm.x - ck.x), gn);  // B^' = -i(C - conj Cm)/2 * g
+            double2 pp = cscale(mk2(ck.x + cmv.x, ck.y - cmv.y), g0);  // A^' = (C + conj Cm)/2 * g
+            const double2 qq = cscale(mk2(ck.y + cmv.y, cmv.x - ck.x), gn);  // B^' = -i(C - conj Cm)/2 * g
             if (k == 0) pp = mk2(0.0, 0.0);                              // e[1,1] = 0, Common.jl:118
             v[u * rl + p] = mk2(pp.x - qq.y, pp.y + qq.x);               // A^' + i B^'
           });
@@ -256,7 +311,9 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
         v[i] = cscale(v[i], a.scale * rcp_fast(dd[i]));
       });
     }
-    F::inverse(c, v, sm, tw, t, [&] { issue_row(rb + c.nblk); });
+    F::inverse(c, v, sm, tw, t, [&] {
+      if constexpr (!C::SPLIT) issue_row(rb + c.nblk);
+    });
     if (active) {
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
@@ -281,79 +338,118 @@ struct K3Args {
   double* lo_dst;     // where interior row 0 is mirrored: previous rank's top halo row (row NJ+1 there)
   double* hi_dst;     // where interior row NJ-1 is mirrored: next rank's bottom halo row (row 0 there)
   int NJ, npairs;
-  int group;          // consecutive row pairs per work unit (tuning)
-  int prefetch;       // 0 off, 1: per-line L2 prefetch of the next unit's T columns
 };
 
 template <class C>
 VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
   using F = Fft<C>;
-  constexpr int N = C::N, E = C::E, T = C::T, P = C::P;
-  double2* sm_all = reinterpret_cast<double2*>(c.smem);
-  double2* tw = sm_all + (size_t)C::SMN * C::FPC;
+  constexpr int N = C::N, E = C::E, T = C::T, P = C::P, NI = N / 2 / T;
+  double2* tw = F::tables(c.smem);
   F::load_tables(c, tw, a.tw);
   c.sync();
   const int g = c.tid / T, t = c.tid % T;
-  double2* sm = sm_all + (size_t)C::SMN * g;
-  // units of kGroup consecutive row pairs: the CTA reads whole 128-byte lines of every T row over the unit, and
-  // prefetches the lines of its next unit into L2 while it transforms the current one
-  const int G = a.group;
-  const int LPU = (G * C::FPC * 2 * (int)sizeof(double2) + 127) / 128;  // lines per T row per unit
+  double2* sm = F::xbuf(c.smem, g);
+  double2* land = F::landing(c.smem, g);
   const int nblocks = (a.npairs + C::FPC - 1) / C::FPC;
-  const int nunits = (nblocks + G - 1) / G;
-  for (int un = c.bid; un < nunits; un += c.nblk) {
-    if (a.prefetch && un + c.nblk < nunits) {
-      const double2* nxt = a.T + (size_t)2 * (un + c.nblk) * G * C::FPC;
-      for (int idx = c.tid; idx < (N / 2) * LPU; idx += C::CT)
-        prefetch_l2(nxt + (size_t)(idx / LPU) * a.NJ + (idx % LPU) * 8);
-    }
-    for (int sub = 0; sub < G; sub++) {
-      const int pb = un * G + sub;
-      if (pb >= nblocks) break;
+  // SPLIT: the 32-byte pieces (U[k][j], U[k][j+1]) of the NEXT pair are gathered asynchronously into the landing
+  // buffer (first halves at [idx], second halves at [N/2 + idx]; a thread only touches its own idx = t + T*i) while
+  // the current pair is transformed; otherwise the gather is synchronous (the exchange buffer is all there is).
+  auto issue_gather = [&](int pb) {
+    if constexpr (C::SPLIT) {
       const int pair = pb * C::FPC + g;
-      const bool active = pair < a.npairs;
-      const int jl = 2 * pair;
-      if (active) {
-        for (int idx = t; idx < N / 2; idx += T) {
-          const int pos = halfspec_pos<C>(idx);
-          const int k = F::k_of_pos(pos);
-          double2 ua, ub;
-          ld_stream4(a.T + (size_t)k * a.NJ + jl, ua, ub);
-          if (k == 0) {
-            sm[F::addr(0)] = mk2(ua.x, ub.x);                   // Z[0]   = u0_j + i u0_j+1
-            sm[F::addr(F::pos_of_k(N / 2))] = mk2(ua.y, ub.y);  // Z[N/2] = uN2_j + i uN2_j+1
-          } else {
-            sm[F::addr(pos)] = mk2(ua.x - ub.y, ua.y + ub.x);                 // U_j[k] + i U_j+1[k]
-            sm[F::addr(F::pos_of_k(N - k))] = mk2(ua.x + ub.y, ub.x - ua.y);  // conj U_j[k] + i conj U_j+1[k]
-          }
-        }
+      if (pb < nblocks && pair < a.npairs) {
+        static_for<0, NI>([&](auto i_) {
+          constexpr int i = decltype(i_)::value;
+          const int idx = t + T * i;
+          const double2* src = a.T + (size_t)F::k_of_pos(halfspec_pos<C>(idx)) * a.NJ + 2 * pair;
+          cp_async16(land + idx, src);
+          cp_async16(land + N / 2 + idx, src + 1);
+        });
       }
-      c.sync();
-      double2 v[E];
-      F::template load_smem<P - 1>(v, sm, t);
-      F::inverse(c, v, sm, tw, t);
+      cp_async_commit();
+    }
+  };
+  issue_gather(c.bid);
+  for (int pb = c.bid; pb < nblocks; pb += c.nblk) {
+    const int pair = pb * C::FPC + g;
+    const bool active = pair < a.npairs;
+    const int jl = 2 * pair;
+    double2 ua[NI], ub[NI];
+    if constexpr (C::SPLIT) {
+      cp_async_wait_all();
+      static_for<0, NI>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        ua[i] = land[t + T * i];
+        ub[i] = land[N / 2 + t + T * i];
+      });
+      issue_gather(pb + c.nblk);
+    } else if (active) {
+      static_for<0, NI>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        ld_stream4(a.T + (size_t)F::k_of_pos(halfspec_pos<C>(t + T * i)) * a.NJ + jl, ua[i], ub[i]);
+      });
+    }
+    c.sync();  // the previous pair's last exchange has been read everywhere: the buffer may be overwritten
+    // Z = U_j + i U_j+1 in position order (Z[N-k] from the conjugates), straight into the last-pass layout
+    auto zval = [&](int i, bool mirror) {
+      const int k = F::k_of_pos(halfspec_pos<C>(t + T * i));
+      if (k == 0) return mirror ? mk2(ua[i].y, ub[i].y) : mk2(ua[i].x, ub[i].x);  // Z[N/2], Z[0] (packed row)
+      return mirror ? mk2(ua[i].x + ub[i].y, ub[i].x - ua[i].y) : mk2(ua[i].x - ub[i].y, ua[i].y + ub[i].x);
+    };
+    auto zpos = [&](int i, bool mirror) {
+      const int pos = halfspec_pos<C>(t + T * i);
+      const int k = F::k_of_pos(pos);
+      return F::addr(mirror ? F::pos_of_k(k == 0 ? N / 2 : N - k) : pos);
+    };
+    double2 v[E];
+    if constexpr (C::SPLIT) {
+      double* sd = reinterpret_cast<double*>(sm);
       if (active) {
-        constexpr int r = 1 << C::bits(0), l = C::lo(0);
-        double* r0 = a.psi + (size_t)(jl + 1) * N;
-        double* r1 = r0 + N;
-        const bool first = (jl == 0), last = (jl + 2 == a.NJ);
-        static_for<0, E / r>([&](auto u_) {
-          constexpr int u = decltype(u_)::value;
-          int low;
-          const int bp = F::template base_pos<0>(t, u, low);
-          static_for<0, r>([&](auto q_) {
-            constexpr int q = decltype(q_)::value;
-            const int pos = bp | (q << l);
-            st_stream1(r0 + pos, v[u * r + q].x);
-            st_stream1(r1 + pos, v[u * r + q].y);
-            if (first) st_stream1(a.lo_dst + pos, v[u * r + q].x);
-            if (last) st_stream1(a.hi_dst + pos, v[u * r + q].y);
-          });
+        static_for<0, NI>([&](auto i_) {
+          constexpr int i = decltype(i_)::value;
+          sd[zpos(i, false)] = zval(i, false).x;
+          sd[zpos(i, true)] = zval(i, true).x;
         });
       }
       c.sync();
+      F::template load_part<P - 1, 0>(v, sd, t);
+      c.sync();
+      if (active) {
+        static_for<0, NI>([&](auto i_) {
+          constexpr int i = decltype(i_)::value;
+          sd[zpos(i, false)] = zval(i, false).y;
+          sd[zpos(i, true)] = zval(i, true).y;
+        });
+      }
+      c.sync();
+      F::template load_part<P - 1, 1>(v, sd, t);
+    } else {
+      if (active) {
+        static_for<0, NI>([&](auto i_) {
+          constexpr int i = decltype(i_)::value;
+          sm[zpos(i, false)] = zval(i, false);
+          sm[zpos(i, true)] = zval(i, true);
+        });
+      }
+      c.sync();
+      F::template load_smem<P - 1>(v, sm, t);
+    }
+    F::inverse(c, v, sm, tw, t);
+    if (active) {
+      double* r0 = a.psi + (size_t)(jl + 1) * N;
+      double* r1 = r0 + N;
+      const bool first = (jl == 0), last = (jl + 2 == a.NJ);
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        const int pos = F::template own_pos<e>(t);
+        st_stream1(r0 + pos, v[e].x);
+        st_stream1(r1 + pos, v[e].y);
+        if (first) st_stream1(a.lo_dst + pos, v[e].x);
+        if (last) st_stream1(a.hi_dst + pos, v[e].y);
+      });
     }
   }
+  cp_async_wait_all();
 }
 
 // ======================================== K4 ====================================================

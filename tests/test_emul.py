@@ -22,6 +22,40 @@ def emul():
     return Common(VmkLibrary(os.path.join(d, "libvmk_emul.so"), "vmke_"))
 
 
+@pytest.fixture(scope="module")
+def emul_split(emul):
+    """The N = 8192 code path (split re/im exchange, separate landing buffer, octant twiddle table) compiled for
+    512 .. 4096 as well, so that it is covered at sizes the CPU suite can afford."""
+    from cfd_julia_b200._lib import VmkLibrary
+    from cfd_julia_b200.common import Common
+    return Common(VmkLibrary(os.path.join(ROOT, "tests", "emul", "libvmk_emul_split.so"), "vmke_"))
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+def test_split_path_fps(emul_split, oracle_c, n):
+    pc.check_fps_noise(emul_split, oracle_c, n)
+    emul_split.clear_plans()
+
+
+@pytest.mark.parametrize("n,nt", [(512, 3), (1024, 2), (2048, 1)])
+def test_split_path_numerical(emul_split, oracle_c, n, nt):
+    pc.check_rhs(emul_split, oracle_c, noise_field(n, seed=n + 1))
+    pc.check_numerical(emul_split, oracle_c, vm_field(n), nt, stable_dt(n, 1000.), 1000.)
+    emul_split.clear_plans()
+
+
+def test_split_path_slab(emul_split, oracle_c):
+    _slab_run(emul_split, oracle_c, 512, 4)
+    _slab_run(emul_split, oracle_c, 1024, 2)
+
+
+def test_full_size_8192_fps(emul, oracle_c):
+    """BASELINE's grid size through the emulator (one Poisson solve; ~20 s)."""
+    emul.clear_plans()
+    pc.check_fps_noise(emul, oracle_c, 8192)
+    emul.clear_plans()
+
+
 @pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048])
 def test_fps_noise(emul, oracle_c, n):
     pc.check_fps_noise(emul, oracle_c, n)
@@ -95,6 +129,10 @@ def test_device_path_and_options(emul, oracle_c):
 def test_slab_decomposition(emul, oracle_c, n, nranks):
     """Ranks as plans in one process (vmk_peer_attach_local); the emulator runs launches synchronously,
     so stepping the ranks kernel by kernel in lock-step stands in for the cross-rank barrier."""
+    _slab_run(emul, oracle_c, n, nranks)
+
+
+def _slab_run(emul, oracle_c, n, nranks):
     from cfd_julia_b200.common import Plan
     from cfd_julia_b200._lib import BARRIER_FN
     lib = emul.lib

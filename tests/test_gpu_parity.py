@@ -77,6 +77,23 @@ def test_tgv_1024(gpu, oracle_c):
     assert abs(compute_l2norm_bnds(n, n, out - ue) - 3.1647889878e-6) < 1e-12
 
 
+def test_tgv_1024_full_config(gpu):
+    """Config 3 in full: tgv.jl at 1024^2, Re=10, nq=4, tf=1 with dt=1e-4 (10 000 steps; the script's dt=.01 is unstable
+    at this resolution).  No oracle run (it would take minutes): the analytic Taylor-Green decay
+    (tgv.jl:82-90) is the reference, as in the script's own self-check (tgv.jl:131-139); second-order accuracy of the
+    scheme gives an L2 error ~ (64/1024)^2 of the 64^2 default-case error."""
+    from cfd_julia_b200.common import compute_l2norm_bnds, exact_tgv
+    n, nt, dt, re = 1024, 10000, 1e-4, 10.
+    dx, dy, x, y = grid(n)
+    wn = tgv_field(n)
+    out = gpu.numerical_tgv(n, n, nt, dx, dy, dt, re, wn)
+    ue = exact_tgv(n, n, x, y, nt * dt, re)
+    l2 = compute_l2norm_bnds(n, n, out - ue)
+    assert np.isfinite(out).all()
+    assert l2 < 5e-5 and np.max(np.abs(out - ue)) < 1e-4  # 64^2 case: L2 6.9e-3 (dt error included)
+    assert abs(np.max(np.abs(out)) - 8. * np.exp(-32. / re)) < 1e-3  # amplitude 2 nq exp(-2 nq^2 t / re)
+
+
 def test_golden(gpu):
     pc.check_golden(gpu)
 
