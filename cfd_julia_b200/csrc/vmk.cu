@@ -80,13 +80,13 @@ template <class C>
 struct K1Body {
   VMK_HD static void run(const Ctx& c, const K1Args& a) { k1_body<C>(c, a); }
 };
-template <class C>
+template <class C, bool PIECES = false>
 struct K2Body {
-  VMK_HD static void run(const Ctx& c, const K2Args& a) { k2_body<C>(c, a); }
+  VMK_HD static void run(const Ctx& c, const K2Args& a) { k2_body<C, PIECES>(c, a); }
 };
-template <class C>
+template <class C, bool PIECES = false>
 struct K3Body {
-  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C>(c, a); }
+  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, PIECES>(c, a); }
 };
 template <int MODE>
 struct K4Body {
@@ -143,16 +143,21 @@ SizeOps make_ops() {
     VMK_TRY((be_configure<K1Body<C>, K1Args, C::CT, C::MINB>(C::SMEM_BYTES, r1)));
     VMK_TRY((be_configure<K2Body<C>, K2Args, C::CT, C::MINB>(C::SMEM_BYTES, r2)));
     VMK_TRY((be_configure<K3Body<C>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, r3)));
+    int dummy = 0;
+    VMK_TRY((be_configure<K2Body<C, true>, K2Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
+    VMK_TRY((be_configure<K3Body<C, true>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
     return 0;
   };
   o.k1 = [](int grid, const K1Args& a, Stream& s) -> int {
     return be_launch<K1Body<C>, K1Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
   };
   o.k2 = [](int grid, const K2Args& a, Stream& s) -> int {
-    return be_launch<K2Body<C>, K2Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    return a.pieces ? be_launch<K2Body<C, true>, K2Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s)
+                    : be_launch<K2Body<C>, K2Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
   };
   o.k3 = [](int grid, const K3Args& a, Stream& s) -> int {
-    return be_launch<K3Body<C>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    return a.pieces ? be_launch<K3Body<C, true>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s)
+                    : be_launch<K3Body<C>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
   };
   return o;
 }
@@ -220,7 +225,7 @@ struct vmk_plan {
   bool uploaded = false;
   int64_t launches = 0, graph_launches = 12;
   int k4_rows = 32, k4_ahead = 4;
-  int k1_prefetch = 0, k2_prefetch = 0;
+  int k1_prefetch = 0, k2_prefetch = 0, v_pieces = 1;
   int use_graph = 1;
 #ifndef VMK_EMUL
   std::map<StepParams, cudaGraphExec_t> graphs;
@@ -467,6 +472,7 @@ int launch_k2(vmk_plan* p, double sign) {
     a.S = p->S;
     for (int r = 0; r < kMaxPeers; r++) a.Vpeer.p[r] = r < P ? (void*)p->peer_V[r] : nullptr;
     a.push = push;
+    a.pieces = (P == 1 && p->v_pieces) ? 1 : 0;
     a.tw = p->tw;
     a.bbcos = p->bbcos;
     a.cccos = p->cccos;
@@ -509,6 +515,7 @@ int launch_k2(vmk_plan* p, double sign) {
 int launch_k3(vmk_plan* p) {
   K3Args a;
   a.T = p->V;
+  a.pieces = (p->nranks == 1 && p->v_pieces) ? 1 : 0;
   a.tw = p->tw;
   a.psi = p->psi;
   const int prev = (p->rank + p->nranks - 1) % p->nranks, next = (p->rank + 1) % p->nranks;
@@ -1025,7 +1032,7 @@ int64_t vmk_launch_count(vmk_plan* p) { return p ? p->launches : 0; }
 int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
   if (!p || !key) return fail(VMK_EARG, "NULL argument");
   const std::string k(key);
-  int* knob = k == "k1_prefetch" ? &p->k1_prefetch : k == "k2_prefetch" ? &p->k2_prefetch
+  int* knob = k == "v_pieces" ? &p->v_pieces : k == "k1_prefetch" ? &p->k1_prefetch : k == "k2_prefetch" ? &p->k2_prefetch
               : k == "k4_ahead" ? &p->k4_ahead : k == "a2a_chunks" ? &p->a2a_chunks
               : k == "a2a_engine" ? &p->a2a_engine : k == "a2a_ctas" ? &p->a2a_ctas
               : k == "k2_push" ? &p->k2_push : nullptr;

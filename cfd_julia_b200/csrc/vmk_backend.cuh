@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(CT, MINB) body_kernel(const __grid_constant__ 
   c.nblk = (int)gridDim.x;
   c.smem = smem_raw;
   c.hbar = nullptr;
+  c.hscratch = nullptr;
   Body::run(c, a);
 }
 

@@ -25,10 +25,25 @@ struct Ctx {
   int nblk;             // number of CTAs in the grid
   unsigned char* smem;  // dynamic shared memory base (16-byte aligned)
   void* hbar;           // host emulation barrier (unused on device)
+  double* hscratch;     // host emulation: two doubles per thread for warp-shuffle emulation (unused on device)
   VMK_HD void sync() const {
 #ifdef __CUDA_ARCH__
     __syncthreads();
 #else
+    vmk_host_barrier_wait(hbar);
+#endif
+  }
+  // exchange a complex value with lane ^ mask (all threads of the CTA call it together)
+  VMK_HD void shfl_xor2(double& x, double& y, int mask) const {
+#ifdef __CUDA_ARCH__
+    x = __shfl_xor_sync(0xffffffffu, x, mask);
+    y = __shfl_xor_sync(0xffffffffu, y, mask);
+#else
+    hscratch[2 * tid] = x;
+    hscratch[2 * tid + 1] = y;
+    vmk_host_barrier_wait(hbar);
+    x = hscratch[2 * (tid ^ mask)];
+    y = hscratch[2 * (tid ^ mask) + 1];
     vmk_host_barrier_wait(hbar);
 #endif
   }

@@ -40,6 +40,14 @@ VMK_HD int halfspec_pos(int idx) {
   return (idx & ((1 << (bl - 1)) - 1)) | ((idx >> (bl - 1)) << bl);
 }
 
+// inverse map: spectral index k < N/2 -> idx
+template <class C>
+VMK_HD int halfspec_idx_of_k(int k) {
+  constexpr int bl = C::bits(C::P - 1);
+  const int pos = Fft<C>::pos_of_k(k);
+  return (pos & ((1 << (bl - 1)) - 1)) | ((pos >> bl) << (bl - 1));
+}
+
 // ======================================== K1 ====================================================
 struct K1Args {
   const double* w;    // slab with halo rows (or the fps source f in the same layout)
@@ -170,6 +178,10 @@ struct K2Args {
   double2* S;           // staging [P blocks h][R][NJ] for the columns owned by rank h != rank (copied to V_h afterwards)
   PeerPtrs Vpeer;       // push mode: every rank's V; foreign columns are stored straight into V_h over NVLink
   int push;             // 1: push mode, 0: staged in S and moved by the copy engines
+  int pieces;           // single GPU: 1 = store V as [row pair][idx][2], idx = the order in which K3's threads consume the
+                        // spectrum rows: K3 then reads one contiguous, coalesced 16N-byte block per pair (bulk-
+                        // prefetched into L2) instead of gathering 32-byte pieces from N/2 rows; the transposing
+                        // access is K2's fire-and-forget store (full 32-byte sectors via a lane-pair shuffle)
   const double2* tw;    // twiddle tables
   const double* bbcos;  // [N]  bb*cos(kx[i])   Common.jl:120 (kx[1]=eps quirk inside)
   const double* cccos;  // [N]  cc*cos(ky[j])   (ky = kx, Common.jl:113)
@@ -183,7 +195,7 @@ struct K2Args {
   int prefetch;         // 0 off, 1: bulk L2 prefetch of the next row (single rank only)
 };
 
-template <class C>
+template <class C, bool PIECES>
 VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
   using F = Fft<C>;
   constexpr int N = C::N, E = C::E, T = C::T, P = C::P, M = C::M;
@@ -201,11 +213,13 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
   auto issue_row = [&](int rb) {
     const int row = rb * C::FPC + g;
     if (rb < nblocks && row < a.nrows) {
+      // PIECES (single GPU): work item `row` is the piece index; its spectrum row is kx = k(idx = row)
+      const int trow = PIECES ? F::k_of_pos(halfspec_pos<C>(row)) : a.rloc0 + row;
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
         const int j = F::template own_pos<e>(t);
         cp_async16(land + F::land_addr(j),
-                   a.T + ((size_t)(j >> a.log2NJ) * a.R + a.rloc0 + row) * a.NJ + (j & (a.NJ - 1)));
+                   a.T + ((size_t)(j >> a.log2NJ) * a.R + trow) * a.NJ + (j & (a.NJ - 1)));
       });
     }
     cp_async_commit();
@@ -214,7 +228,10 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
   for (int rb = c.bid; rb < nblocks; rb += c.nblk) {
     const int row = rb * C::FPC + g;
     const bool active = row < a.nrows;
-    const int kx = a.row0 + row;
+    // PIECES: consecutive work items (= concurrently running CTAs) take the spectrum rows in the order in which K3
+    // consumes them, so their 32-byte stores fill the same 128-byte lines of V at about the same time (the L2 merges
+    // them; with far-apart writers the partial lines were evicted and K2 cost +0.12 ms)
+    const int kx = (PIECES && active) ? F::k_of_pos(halfspec_pos<C>(row)) : a.row0 + row;
     const bool cta_has_row0 = (a.row0 + rb * C::FPC) == 0;
     if (a.prefetch && c.tid == 0 && rb + 2 * c.nblk < nblocks && a.log2NJ == M) {  // single block: rows contiguous
       const int r0n = (rb + 2 * c.nblk) * C::FPC;
@@ -314,7 +331,21 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
     F::inverse(c, v, sm, tw, t, [&] {
       if constexpr (!C::SPLIT) issue_row(rb + c.nblk);
     });
-    if (active) {
+    if constexpr (PIECES) {
+      // lanes 2m, 2m+1 hold columns j, j+1 of every register: one shuffle per register pair gives each lane both
+      // halves of one 32-byte piece (even lane: register e, odd lane: register e+1)
+      const bool odd = (t & 1) != 0;
+      const size_t piece = (size_t)(active ? row : 0) * 2;
+      static_for<0, E / 2>([&](auto h_) {
+        constexpr int e = 2 * decltype(h_)::value;
+        double2 send = odd ? v[e] : v[e + 1];
+        c.shfl_xor2(send.x, send.y, 1);
+        const double2 keep = odd ? v[e + 1] : v[e];
+        const int j = odd ? F::template own_pos<e + 1>(t) : F::template own_pos<e>(t);
+        if (active)
+          st_stream4(a.V + (size_t)(j >> 1) * N + piece, odd ? send : keep, odd ? keep : send);
+      });
+    } else if (active) {
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
         const int j = F::template own_pos<e>(t);
@@ -338,9 +369,10 @@ struct K3Args {
   double* lo_dst;     // where interior row 0 is mirrored: previous rank's top halo row (row NJ+1 there)
   double* hi_dst;     // where interior row NJ-1 is mirrored: next rank's bottom halo row (row 0 there)
   int NJ, npairs;
+  int pieces;         // 1: T is laid out [pair][idx][2] (see K2Args::pieces): contiguous, coalesced reads
 };
 
-template <class C>
+template <class C, bool PIECES>
 VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
   using F = Fft<C>;
   constexpr int N = C::N, E = C::E, T = C::T, P = C::P, NI = N / 2 / T;
@@ -361,7 +393,8 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
         static_for<0, NI>([&](auto i_) {
           constexpr int i = decltype(i_)::value;
           const int idx = t + T * i;
-          const double2* src = a.T + (size_t)F::k_of_pos(halfspec_pos<C>(idx)) * a.NJ + 2 * pair;
+          const double2* src = PIECES ? a.T + (size_t)pair * N + 2 * idx
+                                      : a.T + (size_t)F::k_of_pos(halfspec_pos<C>(idx)) * a.NJ + 2 * pair;
           cp_async16(land + idx, src);
           cp_async16(land + N / 2 + idx, src + 1);
         });
@@ -383,6 +416,20 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
         ub[i] = land[N / 2 + t + T * i];
       });
       issue_gather(pb + c.nblk);
+    } else if constexpr (PIECES) {
+      // the pair's N/2 pieces are one contiguous 16N-byte block in consumption order; the next pair's block is
+      // pulled into L2 by a single bulk prefetch while this pair is transformed
+      if (c.tid == 0 && pb + c.nblk < nblocks) {
+        const int p0 = (pb + c.nblk) * C::FPC;
+        const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
+        prefetch_l2_bulk(a.T + (size_t)p0 * N, (unsigned)(np * N * sizeof(double2)));
+      }
+      if (active) {
+        static_for<0, NI>([&](auto i_) {
+          constexpr int i = decltype(i_)::value;
+          ld_stream4(a.T + (size_t)pair * N + 2 * (t + T * i), ua[i], ub[i]);
+        });
+      }
     } else if (active) {
       static_for<0, NI>([&](auto i_) {
         constexpr int i = decltype(i_)::value;

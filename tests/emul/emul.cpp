@@ -46,6 +46,7 @@ struct Worker {
   vmk::emul_body_fn fn = nullptr;
   const void* args = nullptr;
   unsigned char* smem = nullptr;
+  std::vector<double> scratch;  // warp-shuffle emulation
   int bid = 0, nblk = 0;
 };
 
@@ -60,6 +61,7 @@ void fiber_entry(unsigned lo, unsigned hi) {
   c.nblk = w->nblk;
   c.smem = w->smem;
   c.hbar = w;
+  c.hscratch = w->scratch.data();
   w->fn(c, w->args);
   w->fibers[tid].done = true;
   swapcontext(&w->fibers[tid].ctx, &w->sched);
@@ -165,6 +167,7 @@ int emul_run(int grid, int block, size_t smem, emul_body_fn fn, const void* args
     w.args = args;
     w.nblk = grid;
     w.fibers.resize(block);
+    w.scratch.assign(2 * (size_t)block, 0.0);
     void* sm = nullptr;
     if (posix_memalign(&sm, 256, smem ? smem : 256)) {
       failed = 1;
