@@ -407,8 +407,9 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
     const int pair = pb * C::FPC + g;
     const bool active = pair < a.npairs;
     const int jl = 2 * pair;
-    double2 ua[NI], ub[NI];
+    double2 v[E];
     if constexpr (C::SPLIT) {
+      double2 ua[NI], ub[NI];
       cp_async_wait_all();
       static_for<0, NI>([&](auto i_) {
         constexpr int i = decltype(i_)::value;
@@ -416,40 +417,18 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
         ub[i] = land[N / 2 + t + T * i];
       });
       issue_gather(pb + c.nblk);
-    } else if constexpr (PIECES) {
-      // the pair's N/2 pieces are one contiguous 16N-byte block in consumption order; the next pair's block is
-      // pulled into L2 by a single bulk prefetch while this pair is transformed
-      if (c.tid == 0 && pb + c.nblk < nblocks) {
-        const int p0 = (pb + c.nblk) * C::FPC;
-        const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
-        prefetch_l2_bulk(a.T + (size_t)p0 * N, (unsigned)(np * N * sizeof(double2)));
-      }
-      if (active) {
-        static_for<0, NI>([&](auto i_) {
-          constexpr int i = decltype(i_)::value;
-          ld_stream4(a.T + (size_t)pair * N + 2 * (t + T * i), ua[i], ub[i]);
-        });
-      }
-    } else if (active) {
-      static_for<0, NI>([&](auto i_) {
-        constexpr int i = decltype(i_)::value;
-        ld_stream4(a.T + (size_t)F::k_of_pos(halfspec_pos<C>(t + T * i)) * a.NJ + jl, ua[i], ub[i]);
-      });
-    }
-    c.sync();  // the previous pair's last exchange has been read everywhere: the buffer may be overwritten
-    // Z = U_j + i U_j+1 in position order (Z[N-k] from the conjugates), straight into the last-pass layout
-    auto zval = [&](int i, bool mirror) {
-      const int k = F::k_of_pos(halfspec_pos<C>(t + T * i));
-      if (k == 0) return mirror ? mk2(ua[i].y, ub[i].y) : mk2(ua[i].x, ub[i].x);  // Z[N/2], Z[0] (packed row)
-      return mirror ? mk2(ua[i].x + ub[i].y, ub[i].x - ua[i].y) : mk2(ua[i].x - ub[i].y, ua[i].y + ub[i].x);
-    };
-    auto zpos = [&](int i, bool mirror) {
-      const int pos = halfspec_pos<C>(t + T * i);
-      const int k = F::k_of_pos(pos);
-      return F::addr(mirror ? F::pos_of_k(k == 0 ? N / 2 : N - k) : pos);
-    };
-    double2 v[E];
-    if constexpr (C::SPLIT) {
+      c.sync();  // the previous pair's last exchange has been read everywhere: the buffer may be overwritten
+      // Z = U_j + i U_j+1 in position order (Z[N-k] from the conjugates), straight into the last-pass layout
+      auto zval = [&](int i, bool mirror) {
+        const int k = F::k_of_pos(halfspec_pos<C>(t + T * i));
+        if (k == 0) return mirror ? mk2(ua[i].y, ub[i].y) : mk2(ua[i].x, ub[i].x);  // Z[N/2], Z[0] (packed row)
+        return mirror ? mk2(ua[i].x + ub[i].y, ub[i].x - ua[i].y) : mk2(ua[i].x - ub[i].y, ua[i].y + ub[i].x);
+      };
+      auto zpos = [&](int i, bool mirror) {
+        const int pos = halfspec_pos<C>(t + T * i);
+        const int k = F::k_of_pos(pos);
+        return F::addr(mirror ? F::pos_of_k(k == 0 ? N / 2 : N - k) : pos);
+      };
       double* sd = reinterpret_cast<double*>(sm);
       if (active) {
         static_for<0, NI>([&](auto i_) {
@@ -471,13 +450,46 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
       c.sync();
       F::template load_part<P - 1, 1>(v, sd, t);
     } else {
-      if (active) {
-        static_for<0, NI>([&](auto i_) {
-          constexpr int i = decltype(i_)::value;
-          sm[zpos(i, false)] = zval(i, false);
-          sm[zpos(i, true)] = zval(i, true);
-        });
+      if constexpr (PIECES) {
+        // the pair's N/2 pieces are one contiguous 16N-byte block in consumption order; the next pair's block is
+        // pulled into L2 by a single bulk prefetch while this pair is transformed
+        if (c.tid == 0 && pb + c.nblk < nblocks) {
+          const int p0 = (pb + c.nblk) * C::FPC;
+          const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
+          prefetch_l2_bulk(a.T + (size_t)p0 * N, (unsigned)(np * N * sizeof(double2)));
+        }
       }
+      // two half batches (loads of a half in flight together, then its repack) keep the register peak below the cap
+      constexpr int NB = NI >= 8 ? 2 : 1, NH = NI / NB;
+      static_for<0, NB>([&](auto b_) {
+        constexpr int b = decltype(b_)::value;
+        double2 ua[NH], ub[NH];
+        if (active) {
+          static_for<0, NH>([&](auto i_) {
+            constexpr int i = b * NH + decltype(i_)::value;
+            const int idx = t + T * i;
+            const double2* src = PIECES ? a.T + (size_t)pair * N + 2 * idx
+                                        : a.T + (size_t)F::k_of_pos(halfspec_pos<C>(idx)) * a.NJ + jl;
+            ld_stream4(src, ua[i - b * NH], ub[i - b * NH]);
+          });
+        }
+        if constexpr (b == 0) c.sync();  // the previous pair's last exchange has been read everywhere
+        // Z = U_j + i U_j+1 in position order (Z[N-k] from the conjugates), straight into the last-pass layout
+        if (active) {
+          static_for<0, NH>([&](auto i_) {
+            constexpr int ii = decltype(i_)::value, i = b * NH + ii;
+            const int pos = halfspec_pos<C>(t + T * i);
+            const int k = F::k_of_pos(pos);
+            if (k == 0) {
+              sm[F::addr(0)] = mk2(ua[ii].x, ub[ii].x);                   // Z[0]   = u0_j + i u0_j+1
+              sm[F::addr(F::pos_of_k(N / 2))] = mk2(ua[ii].y, ub[ii].y);  // Z[N/2] = uN2_j + i uN2_j+1
+            } else {
+              sm[F::addr(pos)] = mk2(ua[ii].x - ub[ii].y, ua[ii].y + ub[ii].x);                 // U_j[k] + i U_j+1[k]
+              sm[F::addr(F::pos_of_k(N - k))] = mk2(ua[ii].x + ub[ii].y, ub[ii].x - ua[ii].y);  // conj(..) + i conj(..)
+            }
+          });
+        }
+      });
       c.sync();
       F::template load_smem<P - 1>(v, sm, t);
     }
