@@ -40,6 +40,20 @@ VMK_HD int halfspec_pos(int idx) {
   return (idx & ((1 << (bl - 1)) - 1)) | ((idx >> (bl - 1)) << bl);
 }
 
+// Half-spectrum index held by thread t in its i-th lower-half register of the last-pass layout (i = u*(r_last/2) + p,
+// p < r_last/2: the last-pass digit is the top digit of k, so these are exactly the k < N/2): what a thread needs from the half spectrum is what it already
+// holds in registers, and only the mirror values Z[N-k] go through shared memory.  (Used by K1's unpack; the same
+// scheme for K3's repack was measured slower -- its hoisted address registers made ptxas spill 360 bytes per thread.)
+template <class C>
+VMK_HD int own_half_k(int t, int i) {
+  constexpr int bl = C::bits(C::P - 1), hl = 1 << (bl - 1);
+  return Fft<C>::k_of_pos(((t + C::T * (i / hl)) << bl) | (i % hl));
+}
+template <class C>
+VMK_HD int piece_k(int idx) {  // idx = t + T*i
+  return own_half_k<C>(idx % C::T, idx / C::T);
+}
+
 // inverse map: spectral index k < N/2 -> idx
 template <class C>
 VMK_HD int halfspec_idx_of_k(int k) {
@@ -138,13 +152,18 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
       });
       c.sync();  // the next pair's first exchange may overwrite the buffer
     } else {
-      F::template store_smem<P - 1>(v, sm, t);
+      // own layout: the thread already holds Z[k] for its k < N/2 (lower-half registers); only the upper halves are
+      // published, and each thread fetches the mirror values Z[N-k] of its own k (half the shared-memory traffic)
+      constexpr int bl = C::bits(P - 1), rl = 1 << bl, hl = rl / 2;
+      static_for<0, NI>([&](auto i_) {
+        constexpr int i = decltype(i_)::value, u = i / hl, p = hl + i % hl;
+        sm[F::addr(((t + T * u) << bl) | p)] = v[u * rl + p];
+      });
       c.sync();
       static_for<0, NI>([&](auto i_) {
-        constexpr int i = decltype(i_)::value;
-        const int pos = halfspec_pos<C>(t + T * i);
-        const int k = F::k_of_pos(pos);
-        zk[i] = sm[F::addr(pos)];                                  // k == 0: Z[0]
+        constexpr int i = decltype(i_)::value, u = i / hl, p = i % hl;
+        const int k = own_half_k<C>(t, i);
+        zk[i] = v[u * rl + p];                                     // k == 0: Z[0]
         zm[i] = sm[F::addr(F::pos_of_k(k == 0 ? N / 2 : N - k))];  // k == 0: Z[N/2]
       });
       c.sync();  // the spectrum is in registers: the buffer is free for the next pair's rows
@@ -153,7 +172,7 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
     if (active) {
       static_for<0, NI>([&](auto i_) {
         constexpr int i = decltype(i_)::value;
-        const int k = F::k_of_pos(halfspec_pos<C>(t + T * i));
+        const int k = C::SPLIT ? F::k_of_pos(halfspec_pos<C>(t + T * i)) : own_half_k<C>(t, i);
         double2 o0, o1;
         if (k == 0) {
           o0 = mk2(2.0 * zk[i].x, 2.0 * zm[i].x);
