@@ -104,7 +104,16 @@ int vmk_profile_steps(vmk_plan* plan, double dx, double dy, double dt, double re
                       int64_t* launches);
 /* kernels launched by this plan since creation */
 int64_t vmk_launch_count(vmk_plan* plan);
-/* tuning knobs (integers): "graph" (0/1 CUDA-graph the step), "k4_rows" */
+/* tuning knobs (integers; defaults are the measured best, see profiles/r01_notes.md):
+ *   "graph"       1      replay the step (kernels, copies, barriers) from a CUDA graph
+ *   "k4_rows"     32     rows marched by one K4 thread column (shortened automatically on small slabs)
+ *   "k4_ahead"    4      rows ahead of the march that K4 prefetches into L2 (0 = off)
+ *   "v_pieces"    1      single GPU: K2 stores the solution spectrum as per-row-pair blocks in K3's read order
+ *   "k1_prefetch", "k2_prefetch"  0   extra L2 bulk prefetch two rows ahead (no gain once cp.async existed)
+ *   "a2a_chunks"  0=auto launches K1 (and a staged K2) is split into so that the transpose overlaps with it
+ *   "a2a_engine"  -1=auto forward transpose by copy engines (1; best at 2 GPUs) or the SM push kernel (0; best at 4, 8)
+ *   "a2a_ctas"    128    CTAs of the push kernel
+ *   "k2_push"     -1=auto backward transpose by direct NVLink stores from K2 (1) or staged + copy engines (0) */
 int vmk_set_option(vmk_plan* plan, const char* key, int64_t value);
 /* bytes of device memory held by the plan */
 int64_t vmk_device_bytes(vmk_plan* plan);

@@ -4,6 +4,8 @@ recorded numbers; and size-independent properties at BASELINE.json's full 8192^2
 
 Tolerance (north_star): relative L2 <= 1e-10 on vorticity and streamfunction; single operator calls
 are held to 1e-12."""
+import os
+
 import numpy as np
 import pytest
 
@@ -186,3 +188,24 @@ def test_full_size_properties(gpu):
            (s1[1:-1, 2:] - 2 * s1[1:-1, 1:-1] + s1[1:-1, :-2]) / dy**2)
     assert rel_l2(lap, f1 - f1.mean()) < 1e-7  # conditioning of the second difference at 8192^2 (~ 1e-16 * N^2)
     gpu.clear_plans()
+
+
+def test_bench_contract_line(tmp_path):
+    """bench.py prints ONE JSON line with the keys the driver reads (run on a small grid to keep it short)."""
+    import json
+    import subprocess
+    import sys
+    from helpers import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--n", "1024", "--steps", "3", "--warmup", "3",
+                        "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["value"] > 0 and d["gpu_launches"] == 36 and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["peak"] > 0 and 0 < rf["frac"] < 1.2 and rf["achieved"] > 0
