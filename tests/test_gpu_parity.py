@@ -147,9 +147,9 @@ def test_graph_and_plain_launch_agree(gpu):
 
 # ---- full-size (8192^2) properties: the oracle takes ~6 s per step there, so one step is compared directly
 # and longer runs are checked through size-independent properties ------------------------------------
-def test_full_size_one_step_vs_oracle(gpu, oracle_c):
+def test_full_size_two_steps_vs_oracle(gpu, oracle_c):
     n = 8192
-    pc.check_numerical(gpu, oracle_c, vm_field(n), 1, 1e-4, 1000.)
+    pc.check_numerical(gpu, oracle_c, vm_field(n), 2, 1e-4, 1000.)
     gpu.clear_plans()
 
 
