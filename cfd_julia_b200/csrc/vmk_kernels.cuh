@@ -41,25 +41,14 @@ VMK_HD int halfspec_pos(int idx) {
 }
 
 // Half-spectrum index held by thread t in its i-th lower-half register of the last-pass layout (i = u*(r_last/2) + p,
-// p < r_last/2: the last-pass digit is the top digit of k, so these are exactly the k < N/2): what a thread needs from the half spectrum is what it already
-// holds in registers, and only the mirror values Z[N-k] go through shared memory.  (Used by K1's unpack; the same
-// scheme for K3's repack was measured slower -- its hoisted address registers made ptxas spill 360 bytes per thread.)
+// p < r_last/2: the last-pass digit is the top digit of k, so these are exactly the k < N/2): what a thread needs
+// from the half spectrum is what it already holds in registers, and only the mirror values Z[N-k] go through shared
+// memory.  (Used by K1's unpack; the same scheme for K3's repack was measured slower -- its hoisted address registers
+// made ptxas spill 360 bytes per thread.)
 template <class C>
 VMK_HD int own_half_k(int t, int i) {
   constexpr int bl = C::bits(C::P - 1), hl = 1 << (bl - 1);
   return Fft<C>::k_of_pos(((t + C::T * (i / hl)) << bl) | (i % hl));
-}
-template <class C>
-VMK_HD int piece_k(int idx) {  // idx = t + T*i
-  return own_half_k<C>(idx % C::T, idx / C::T);
-}
-
-// inverse map: spectral index k < N/2 -> idx
-template <class C>
-VMK_HD int halfspec_idx_of_k(int k) {
-  constexpr int bl = C::bits(C::P - 1);
-  const int pos = Fft<C>::pos_of_k(k);
-  return (pos & ((1 << (bl - 1)) - 1)) | ((pos >> bl) << (bl - 1));
 }
 
 // ======================================== K1 ====================================================

@@ -50,8 +50,6 @@ struct Worker {
   int bid = 0, nblk = 0;
 };
 
-thread_local Worker* tl_worker = nullptr;
-
 void fiber_entry(unsigned lo, unsigned hi) {
   Worker* w = reinterpret_cast<Worker*>(((uintptr_t)hi << 32) | (uintptr_t)lo);
   const int tid = w->current;
