@@ -24,6 +24,7 @@ _PROTOS = {
     "last_error": (C.c_char_p, []),
     "plan_create": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(_P)]),
     "plan_create_slab": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
+    "plan_create_on": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
     "plan_destroy": (C.c_int, [_P]),
     "peer_blob_bytes": (C.c_size_t, []),
     "peer_export": (C.c_int, [_P, _P]),

@@ -15,6 +15,7 @@
 #define vmk_last_error vmke_last_error
 #define vmk_plan_create vmke_plan_create
 #define vmk_plan_create_slab vmke_plan_create_slab
+#define vmk_plan_create_on vmke_plan_create_on
 #define vmk_plan_destroy vmke_plan_destroy
 #define vmk_fps vmke_fps
 #define vmk_ps_fft vmke_ps_fft
@@ -190,6 +191,7 @@ enum { KI_K1 = 0, KI_K2, KI_K3, KI_K4, KI_COUNT };
 struct vmk_plan {
   int N = 0, M = 0, rank = 0, nranks = 1, NJ = 0, log2NJ = 0, j0 = 0;
   int sms = 0;
+  int device = 0;  // CUDA device the plan lives on (the one current at creation)
   SizeOps ops{};
   int res_k1 = 0, res_k2 = 0, res_k3 = 0;
   // device buffers
@@ -615,6 +617,7 @@ int enqueue_step(vmk_plan* p, const StepParams& sp) {
 
 int check_plan(vmk_plan* p) {
   if (!p) return fail(VMK_EARG, "plan is NULL");
+  VMK_TRY(be_set_device(p->device));  // a host thread may drive several plans on different devices
   if (p->nranks > 1 && !p->peers_ready) return fail(VMK_ESTATE, "slab plan: peers not attached yet");
   return 0;
 }
@@ -707,6 +710,7 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
   p->ops = ops;
   int rc = 0;
   do {
+    if ((rc = be_get_device(&p->device))) break;
     if ((rc = be_num_sms(&p->sms))) break;
     if ((rc = be_stream_create(p->st))) break;
     if ((rc = be_event_create(p->ev0)) || (rc = be_event_create(p->ev1))) break;
@@ -762,8 +766,14 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
 
 int vmk_plan_create(int64_t nx, int64_t ny, vmk_plan** out) { return vmk_plan_create_slab(nx, ny, 0, 1, out); }
 
+int vmk_plan_create_on(int device, int64_t nx, int64_t ny, int rank, int nranks, vmk_plan** out) {
+  VMK_TRY(be_set_device(device));
+  return vmk_plan_create_slab(nx, ny, rank, nranks, out);
+}
+
 int vmk_plan_destroy(vmk_plan* p) {
   if (!p) return VMK_OK;
+  be_set_device(p->device);
   if (be_stream_valid(p->st)) be_sync(p->st);
   drop_graphs(p);
   for (void* q : p->ipc_opened) be_ipc_close(q);
@@ -832,9 +842,11 @@ int vmk_peer_import(vmk_plan* p, const void* blobs) {
 // plans[r] is rank r's plan; peer access must already be enabled between the devices
 int vmk_peer_attach_local(vmk_plan* p, vmk_plan* const* plans) {
   if (!p || !plans) return fail(VMK_EARG, "NULL argument");
+  VMK_TRY(be_set_device(p->device));
   for (int r = 0; r < p->nranks; r++) {
     if (!plans[r] || plans[r]->N != p->N || plans[r]->nranks != p->nranks || plans[r]->rank != r)
       return fail(VMK_EARG, "plans[] does not hold one matching plan per rank");
+    VMK_TRY(be_enable_peer(p->device, plans[r]->device));
     for (int q = 0; q < 3; q++) p->peer_w[q][r] = plans[r]->w[q];
     p->peer_psi[r] = plans[r]->psi;
     p->peer_T[r] = plans[r]->T;

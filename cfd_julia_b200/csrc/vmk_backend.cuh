@@ -136,6 +136,28 @@ inline int be_ipc_open(const IpcHandle& h, void** p) {
   return 0;
 }
 inline void be_ipc_close(void* p) { cudaIpcCloseMemHandle(p); }
+inline int be_get_device(int* dev) {
+  VMK_CUDA_TRY(cudaGetDevice(dev));
+  return 0;
+}
+inline int be_set_device(int dev) {
+  VMK_CUDA_TRY(cudaSetDevice(dev));
+  return 0;
+}
+// one host thread driving several devices: let `dev` (current) load from / store to `peer`
+inline int be_enable_peer(int dev, int peer) {
+  if (dev == peer) return 0;
+  int can = 0;
+  VMK_CUDA_TRY(cudaDeviceCanAccessPeer(&can, dev, peer));
+  if (!can) return fail(2, "devices cannot access each other's memory (no NVLink/PCIe peer path)");
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return 0;
+  }
+  VMK_CUDA_TRY(e);
+  return 0;
+}
 inline int be_num_sms(int* n) {
   int dev = 0;
   VMK_CUDA_TRY(cudaGetDevice(&dev));
@@ -260,6 +282,12 @@ inline int be_d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, s
 inline int be_d2d_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, Stream& s) {
   return be_h2d_2d(dst, dpitch, src, spitch, width, height, s);
 }
+inline int be_get_device(int* dev) {
+  *dev = 0;
+  return 0;
+}
+inline int be_set_device(int) { return 0; }
+inline int be_enable_peer(int, int) { return 0; }
 inline int be_num_sms(int* n) {
   *n = 4;  // a small "GPU" so that the persistent loops are exercised
   return 0;

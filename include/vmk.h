@@ -50,11 +50,15 @@ int vmk_plan_destroy(vmk_plan* plan);
  * storing to the other ranks' buffers directly over NVLink (halo rows of w and psi; the j-direction FFT
  * reads the whole spectrum row from all ranks), so every rank needs the others' buffer addresses:
  *   one process per GPU : vmk_peer_export -> all-gather the blobs -> vmk_peer_import (CUDA IPC)
- *   one process, N GPUs : vmk_peer_attach_local (peer access enabled by the caller)
+ *   one process, N GPUs : vmk_peer_attach_local (enables peer access between the plans' devices itself; every
+ *                         entry point makes its plan's device current, so one host thread can drive all ranks:
+ *                         call vmk_step for every rank -- it is asynchronous -- before any vmk_download)
  * and a cross-rank barrier that the plan enqueues on its stream between dependent kernels
  * (vmk_barrier_hook; e.g. a 1-element NCCL all-reduce on that stream).
  * Host-array entry points of a slab plan read/write only the rank's own columns of the caller's arrays. */
 int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan** plan);
+/* same, on CUDA device `device` (made current): for a single host process that owns all ranks */
+int vmk_plan_create_on(int device, int64_t nx, int64_t ny, int rank, int nranks, vmk_plan** plan);
 size_t vmk_peer_blob_bytes(void);
 int vmk_peer_export(vmk_plan* plan, void* blob);
 int vmk_peer_import(vmk_plan* plan, const void* blobs /* nranks blobs in rank order */);

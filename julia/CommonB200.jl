@@ -16,7 +16,7 @@
 # the same ABI is exercised in CI through ctypes (cfd_julia_b200/common.py), which this file mirrors line by line.
 module CommonB200
 
-export fps, vm_rhs, numerical, ps_fft, vmk_plan, vmk_upload, vmk_step, vmk_download
+export fps, vm_rhs, numerical, ps_fft, vmk_plan, vmk_upload, vmk_step, vmk_download, vmk_plans_multi, numerical_multi
 
 const libvmk = get(ENV, "VMK_LIB", joinpath(@__DIR__, "..", "cfd_julia_b200", "libvmk.so"))
 
@@ -108,6 +108,33 @@ numerical(nx, ny, nt, Δx, Δy, Δt, re, wn::Matrix{Float64}) = begin
                Ptr{Cvoid}),
               vmk_plan(nx, ny).handle, nt, Δx, Δy, Δt, re, wn, out, 0, C_NULL, C_NULL))
   return out
+end
+
+# ---- several GPUs driven by this one Julia process (slab decomposition along j) ---------------------------------------
+# plans = vmk_plans_multi(nx, ny, ngpu); numerical_multi(plans, nt, Δx, Δy, Δt, re, wn) steps all ranks concurrently
+# (vmk_step is asynchronous) and gathers every rank's rows back into wn.
+vmk_plans_multi(nx::Integer, ny::Integer, ngpu::Integer) = begin
+  plans = Plan[]
+  for r in 0:ngpu-1
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:vmk_plan_create_on, libvmk), Cint, (Cint, Int64, Int64, Cint, Cint, Ptr{Ptr{Cvoid}}), r, nx, ny, r, ngpu, h))
+    p = Plan(h[])
+    finalizer(q -> ccall((:vmk_plan_destroy, libvmk), Cint, (Ptr{Cvoid},), q.handle), p)
+    push!(plans, p)
+  end
+  handles = [p.handle for p in plans]
+  for p in plans
+    check(ccall((:vmk_peer_attach_local, libvmk), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), p.handle, handles))
+  end
+  plans
+end
+
+numerical_multi(plans::Vector{Plan}, nt, Δx, Δy, Δt, re, wn::Matrix{Float64}) = begin
+  for p in plans; vmk_upload(p, wn); end                 # every rank takes its own columns of wn
+  for p in plans; vmk_step(p, Δx, Δy, Δt, re, nt); end    # asynchronous: the ranks run concurrently
+  for p in plans; vmk_download(p, wn); end               # every rank writes its own columns (and ghosts) back
+  nx, ny = size(wn, 1) - 2, size(wn, 2) - 2
+  return wn[2:nx+2, 2:ny+2]
 end
 
 # device-resident pieces, for callers that want to keep the field on the GPU between calls
