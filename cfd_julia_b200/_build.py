@@ -24,6 +24,11 @@ NVCC_FLAGS = [
 ]
 
 
+# Test build of the SAME CUDA sources with the thread-block-cluster kernels (production: 16384, 32768) enabled for
+# 64 .. 8192, so that the GPU suite can compare them with the CPU oracle at sizes the oracle can afford.
+SO_CLUSTER_TEST = os.path.join(HERE, "libvmk_cltest.so")
+
+
 def _nvcc() -> str:
     cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(cand):
@@ -47,6 +52,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
         subprocess.check_call(cmd, cwd=ROOT)
     return SO
+
+
+def build_cluster_test(force: bool = False) -> str:
+    if force or not os.path.exists(SO_CLUSTER_TEST) or any(
+            os.path.getmtime(x) > os.path.getmtime(SO_CLUSTER_TEST) for x in sources()):
+        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-DVMK_CLUSTER_TEST", "-o", SO_CLUSTER_TEST, SRC], cwd=ROOT)
+    return SO_CLUSTER_TEST
 
 
 if __name__ == "__main__":

@@ -46,6 +46,7 @@
 #include <vector>
 
 #include "vmk_backend.cuh"
+#include "vmk_cluster.cuh"
 #include "vmk_kernels.cuh"
 
 using namespace vmk;
@@ -66,9 +67,10 @@ struct StepParams {
 };
 
 struct SizeOps {
-  size_t twn;       // twiddle table entries
+  size_t twn;       // twiddle table entries (cluster sizes: the CTA-level tables, then W_N^n for n < N/cluster)
   size_t smem;      // dynamic shared memory of K1/K2/K3
-  int fpc;          // transforms per CTA
+  int fpc;          // transforms per CTA (per cluster for the cluster sizes)
+  int cluster;      // CTAs that share one transform (1: the row fits one SM; 2, 4: vmk_cluster.cuh)
   void (*fill_tw)(double2*);
   void (*fill_ccperm)(const double* cccos, double* ccperm);
   int (*configure)(int* res_k1, int* res_k2, int* res_k3);
@@ -131,6 +133,79 @@ void fill_ccperm(const double* cccos, double* out) {
       for (int t = 0; t < C::T; t++) out[(u * rl + p) * C::T + t] = cccos[F::k_of_pos(((t + C::T * u) << bl) | p)];
 }
 
+// ---- rows spanning a thread-block cluster (vmk_cluster.cuh) ----------------------------------------------------
+template <class C, int Q>
+struct K1CBody {
+  VMK_HD static void run(const Ctx& c, const K1Args& a) { k1c_body<C, Q>(c, a); }
+};
+template <class C, int Q, bool PIECES = false>
+struct K2CBody {
+  VMK_HD static void run(const Ctx& c, const K2Args& a) { k2c_body<C, Q, PIECES>(c, a); }
+};
+template <class C, int Q, bool PIECES = false>
+struct K3CBody {
+  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3c_body<C, Q, PIECES>(c, a); }
+};
+
+template <class C, int Q>
+void fill_twiddles_cluster(double2* tw) {
+  fill_twiddles<C>(tw);
+  const long double tau = 6.283185307179586476925286766559005768L;
+  const int N = Q * C::N;
+  for (int n = 0; n < C::N; n++) {  // W_N^n: the twiddles of the radix-Q pass across the cluster
+    const long double ang = tau * (long double)n / (long double)N;
+    tw[C::TWN + n].x = (double)cosl(ang);
+    tw[C::TWN + n].y = (double)(-sinl(ang));
+  }
+}
+
+// CTA r of the cluster holds ky = Q k' + r: one permuted table per r
+template <class C, int Q>
+void fill_ccperm_cluster(const double* cccos, double* out) {
+  using F = Fft<C>;
+  constexpr int bl = C::bits(C::P - 1), rl = 1 << bl;
+  for (int r = 0; r < Q; r++)
+    for (int u = 0; u < C::E / rl; u++)
+      for (int p = 0; p < rl; p++)
+        for (int t = 0; t < C::T; t++)
+          out[(size_t)r * C::N + (u * rl + p) * C::T + t] = cccos[Q * F::k_of_pos(((t + C::T * u) << bl) | p) + r];
+}
+
+template <int MSUB, int Q>
+SizeOps make_cluster_ops() {
+  using C = typename CfgFor<MSUB>::type;
+  SizeOps o;
+  o.twn = C::TWN + C::N;
+  o.smem = C::SMEM_BYTES;
+  o.fpc = C::FPC;
+  o.cluster = Q;
+  o.fill_tw = &fill_twiddles_cluster<C, Q>;
+  o.fill_ccperm = &fill_ccperm_cluster<C, Q>;
+  o.configure = [](int* r1, int* r2, int* r3) -> int {
+    VMK_TRY((be_configure_cluster<K1CBody<C, Q>, K1Args, C::CT, 1>(Q, C::SMEM_BYTES, r1)));
+    VMK_TRY((be_configure_cluster<K2CBody<C, Q>, K2Args, C::CT, 1>(Q, C::SMEM_BYTES, r2)));
+    VMK_TRY((be_configure_cluster<K3CBody<C, Q>, K3Args, C::CT, 1>(Q, C::SMEM_BYTES, r3)));
+    int d2 = 0, d3 = 0;
+    VMK_TRY((be_configure_cluster<K2CBody<C, Q, true>, K2Args, C::CT, 1>(Q, C::SMEM_BYTES, &d2)));
+    VMK_TRY((be_configure_cluster<K3CBody<C, Q, true>, K3Args, C::CT, 1>(Q, C::SMEM_BYTES, &d3)));
+    if (d2 < *r2) *r2 = d2;
+    if (d3 < *r3) *r3 = d3;
+    return 0;
+  };
+  o.k1 = [](int grid, const K1Args& a, Stream& s) -> int {
+    return be_launch_cluster<K1CBody<C, Q>, K1Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
+  };
+  o.k2 = [](int grid, const K2Args& a, Stream& s) -> int {
+    return a.pieces ? be_launch_cluster<K2CBody<C, Q, true>, K2Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s)
+                    : be_launch_cluster<K2CBody<C, Q>, K2Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
+  };
+  o.k3 = [](int grid, const K3Args& a, Stream& s) -> int {
+    return a.pieces ? be_launch_cluster<K3CBody<C, Q, true>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s)
+                    : be_launch_cluster<K3CBody<C, Q>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
+  };
+  return o;
+}
+
 template <int M>
 SizeOps make_ops() {
   using C = typename CfgFor<M>::type;
@@ -138,6 +213,7 @@ SizeOps make_ops() {
   o.twn = C::TWN;
   o.smem = C::SMEM_BYTES;
   o.fpc = C::FPC;
+  o.cluster = 1;
   o.fill_tw = &fill_twiddles<C>;
   o.fill_ccperm = &fill_ccperm<C>;
   o.configure = [](int* r1, int* r2, int* r3) -> int {
@@ -166,6 +242,16 @@ SizeOps make_ops() {
 bool ops_for(int M, SizeOps* o) {
   switch (M) {
     case 5: *o = make_ops<5>(); return true;
+#ifdef VMK_CLUSTER_TEST  // test builds only: the cluster kernels at sizes the oracle (and the emulator) can afford
+    case 6: *o = make_cluster_ops<5, 2>(); return true;
+    case 7: *o = make_cluster_ops<5, 4>(); return true;
+    case 8: *o = make_cluster_ops<7, 2>(); return true;
+    case 9: *o = make_cluster_ops<7, 4>(); return true;
+    case 10: *o = make_cluster_ops<9, 2>(); return true;
+    case 11: *o = make_cluster_ops<9, 4>(); return true;
+    case 12: *o = make_cluster_ops<11, 2>(); return true;
+    case 13: *o = make_cluster_ops<11, 4>(); return true;
+#else
     case 6: *o = make_ops<6>(); return true;
     case 7: *o = make_ops<7>(); return true;
     case 8: *o = make_ops<8>(); return true;
@@ -174,6 +260,9 @@ bool ops_for(int M, SizeOps* o) {
     case 11: *o = make_ops<11>(); return true;
     case 12: *o = make_ops<12>(); return true;
     case 13: *o = make_ops<13>(); return true;
+    case 14: *o = make_cluster_ops<13, 2>(); return true;  // 16384 = 2 x 8192
+    case 15: *o = make_cluster_ops<13, 4>(); return true;  // 32768 = 4 x 8192
+#endif
     default: return false;
   }
 }
@@ -407,7 +496,7 @@ int launch_k1(vmk_plan* p, const double* src) {
     a.k_own0 = p->rank * R;
     a.k_own1 = a.k_own0 + R;
     a.prefetch = p->k1_prefetch;
-    const int work = rowpair_units(p, np, 1);
+    const int work = rowpair_units(p, np, 1) * p->ops.cluster;
     VMK_TRY(p->ops.k1(work < p->res_k1 ? work : p->res_k1, a, p->st));
     p->launches++;
     if (P > 1) {
@@ -489,7 +578,7 @@ int launch_k2(vmk_plan* p, double sign) {
     a.rloc0 = rloc0;
     a.rank = p->rank;
     a.prefetch = p->k2_prefetch;
-    const int work = (nr + p->ops.fpc - 1) / p->ops.fpc;
+    const int work = (nr + p->ops.fpc - 1) / p->ops.fpc * p->ops.cluster;
     VMK_TRY(p->ops.k2(work < p->res_k2 ? work : p->res_k2, a, p->st));
     p->launches++;
     if (P > 1 && !push) {
@@ -525,7 +614,7 @@ int launch_k3(vmk_plan* p) {
   a.hi_dst = p->peer_psi[next];
   a.NJ = p->NJ;
   a.npairs = p->NJ / 2;
-  const int work = rowpair_units(p, a.npairs, 1);
+  const int work = rowpair_units(p, a.npairs, 1) * p->ops.cluster;
   Timed t(p, KI_K3);
   VMK_TRY(p->ops.k3(work < p->res_k3 ? work : p->res_k3, a, p->st));
   t.done();
@@ -694,7 +783,7 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
   const int M = ilog2_exact(nx);
   SizeOps ops;
   if (M < 0 || !ops_for(M, &ops))
-    return fail(VMK_ESIZE, "grid size must be a power of two in [32, 8192]");
+    return fail(VMK_ESIZE, "grid size must be a power of two in [32, 32768]");
   if (nranks < 1 || nranks > kMaxPeers || rank < 0 || rank >= nranks || ilog2_exact(nranks) < 0)
     return fail(VMK_EARG, "nranks must be 1, 2, 4 or 8 and 0 <= rank < nranks");
   if ((nx / nranks) < 2 || ((nx / 2) % nranks) != 0)

@@ -54,6 +54,12 @@ __global__ void __launch_bounds__(CT, MINB) body_kernel(const __grid_constant__ 
   c.smem = smem_raw;
   c.hbar = nullptr;
   c.hscratch = nullptr;
+  c.hcsmem = nullptr;
+  unsigned cr, cs;  // 0 / 1 when the kernel is launched without a cluster dimension
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
+  c.crank = (int)cr;
+  c.csize = (int)cs;
   Body::run(c, a);
 }
 
@@ -186,6 +192,48 @@ inline int be_launch(int grid, size_t smem, const Args& a, Stream& s) {
   return 0;
 }
 
+// ---- thread-block clusters: `q` consecutive CTAs of the grid form a cluster (same GPC, distributed shared memory) ----
+template <class Body, class Args, int CT, int MINB>
+inline void cluster_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute& at, int grid, int q, size_t smem,
+                           cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(CT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = (unsigned)q;
+  at.val.clusterDim.y = 1;
+  at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+}
+// resident = CTAs of the clusters that can be co-resident on the device (a multiple of q)
+template <class Body, class Args, int CT, int MINB>
+inline int be_configure_cluster(int q, size_t smem, int* resident) {
+  auto kfn = body_kernel<Body, Args, CT, MINB>;
+  if (smem > 48 * 1024)
+    VMK_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0;
+  if (be_num_sms(&sms)) return 2;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at;
+  cluster_config<Body, Args, CT, MINB>(cfg, at, (sms / q) * q, q, smem, nullptr);
+  int ncl = 0;
+  VMK_CUDA_TRY(cudaOccupancyMaxActiveClusters(&ncl, kfn, &cfg));
+  if (ncl < 1) return fail(2, "cluster kernel does not fit on the device (shared memory / registers / GPC size)");
+  *resident = ncl * q;
+  return 0;
+}
+template <class Body, class Args, int CT, int MINB>
+inline int be_launch_cluster(int grid, int q, size_t smem, const Args& a, Stream& s) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at;
+  cluster_config<Body, Args, CT, MINB>(cfg, at, grid, q, smem, s.s);
+  VMK_CUDA_TRY(cudaLaunchKernelEx(&cfg, body_kernel<Body, Args, CT, MINB>, a));
+  return 0;
+}
+
 #else
 // ================================ host emulation backend (tests only) ================================
 struct Stream {
@@ -293,7 +341,7 @@ inline int be_num_sms(int* n) {
   return 0;
 }
 typedef void (*emul_body_fn)(const Ctx&, const void*);
-int emul_run(int grid, int block, size_t smem, emul_body_fn fn, const void* args);
+int emul_run(int grid, int block, int cluster, size_t smem, emul_body_fn fn, const void* args);
 
 template <class Body, class Args, int CT, int MINB>
 inline int be_configure(size_t, int* resident) {
@@ -305,7 +353,17 @@ inline int be_configure(size_t, int* resident) {
 template <class Body, class Args, int CT, int MINB>
 inline int be_launch(int grid, size_t smem, const Args& a, Stream&) {
   return emul_run(
-      grid, CT, smem, [](const Ctx& c, const void* p) { Body::run(c, *static_cast<const Args*>(p)); }, &a);
+      grid, CT, 1, smem, [](const Ctx& c, const void* p) { Body::run(c, *static_cast<const Args*>(p)); }, &a);
+}
+template <class Body, class Args, int CT, int MINB>
+inline int be_configure_cluster(int q, size_t, int* resident) {
+  *resident = 2 * q;  // two co-resident clusters, so that the persistent loops are exercised
+  return 0;
+}
+template <class Body, class Args, int CT, int MINB>
+inline int be_launch_cluster(int grid, int q, size_t smem, const Args& a, Stream&) {
+  return emul_run(
+      grid, CT, q, smem, [](const Ctx& c, const void* p) { Body::run(c, *static_cast<const Args*>(p)); }, &a);
 }
 #endif
 

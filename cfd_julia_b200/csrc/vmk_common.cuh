@@ -16,7 +16,8 @@
 namespace vmk {
 
 #ifndef __CUDA_ARCH__
-extern "C" void vmk_host_barrier_wait(void* bar);  // defined in the emulator only
+extern "C" void vmk_host_barrier_wait(void* bar);          // defined in the emulator only
+extern "C" void vmk_host_cluster_barrier_wait(void* bar);  // ditto: barrier over all CTAs of a thread-block cluster
 #endif
 
 struct Ctx {
@@ -26,6 +27,30 @@ struct Ctx {
   unsigned char* smem;  // dynamic shared memory base (16-byte aligned)
   void* hbar;           // host emulation barrier (unused on device)
   double* hscratch;     // host emulation: two doubles per thread for warp-shuffle emulation (unused on device)
+  int crank;            // rank of the CTA in its thread-block cluster (0 for plain launches)
+  int csize;            // CTAs per cluster (1 for plain launches)
+  unsigned char* const* hcsmem;  // host emulation: shared-memory bases of the cluster's CTAs (unused on device)
+  // barrier over every thread of the cluster; release/acquire: shared-memory writes made before it -- to the own
+  // CTA's memory or to a peer CTA's through remote() -- are visible to every thread of the cluster after it
+  VMK_HD void cluster_sync() const {
+#ifdef __CUDA_ARCH__
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
+    vmk_host_cluster_barrier_wait(hbar);
+#endif
+  }
+  // address of the same shared-memory location in CTA `rank` of the cluster (distributed shared memory); the result
+  // is a generic pointer, ordinary loads and stores through it travel over the SM-to-SM network
+  template <class T>
+  VMK_HD T* remote(T* p, int rank) const {
+#ifdef __CUDA_ARCH__
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(rank));
+    return reinterpret_cast<T*>(out);
+#else
+    return reinterpret_cast<T*>(hcsmem[rank] + (reinterpret_cast<unsigned char*>(p) - smem));
+#endif
+  }
   VMK_HD void sync() const {
 #ifdef __CUDA_ARCH__
     __syncthreads();
@@ -172,6 +197,13 @@ VMK_HD void cp_async_wait_all() {
 #endif
 }
 VMK_HD double ld_ro(const double* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+VMK_HD double2 ld_ro2(const double2* p) {
 #ifdef __CUDA_ARCH__
   return __ldg(p);
 #else

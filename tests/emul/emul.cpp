@@ -6,10 +6,14 @@
 // decomposition) can be checked against the oracle in the "-m 'not gpu'" suite.  It proves nothing about
 // the CUDA build's performance, and the parity claims are made by the "-m gpu" tests on the real library.
 //
-// Execution model: one CTA at a time per worker; the CTA's threads are ucontext fibers run round-robin,
-// Ctx::sync() yields to the scheduler, which resumes the next fiber -- after a full round every fiber has
-// reached the barrier, exactly __syncthreads() semantics (threads that returned are skipped, as on the
-// device).  CTAs of a grid are distributed over a few OS threads.
+// Execution model: one CTA (or one thread-block cluster) at a time per worker; the threads are ucontext fibers run
+// round-robin, Ctx::sync() yields to the scheduler, which resumes the next fiber -- after a full round every fiber
+// of the CTA has reached the barrier, exactly __syncthreads() semantics (threads that returned are skipped, as on
+// the device).  In a cluster each CTA runs AHEAD as far as it can -- round after round, until all its threads wait
+// at a cluster barrier -- before the next CTA of the cluster gets to run, in alternating CTA order from one cluster
+// barrier to the next: a missing cluster barrier around a distributed-shared-memory access shows up as a read of
+// poisoned or stale data instead of being hidden by lock-step execution.  CTAs / clusters of a grid are
+// distributed over a few OS threads.
 #include <fcntl.h>
 #include <pthread.h>
 #include <stdio.h>
@@ -45,28 +49,35 @@ struct Worker {
   // launch description
   vmk::emul_body_fn fn = nullptr;
   const void* args = nullptr;
-  unsigned char* smem = nullptr;
+  unsigned char* smem = nullptr;  // shared memory of all CTAs of the cluster, `smem_stride` apart
+  size_t smem_stride = 0;
+  std::vector<unsigned char*> csmem;  // per-CTA bases
   std::vector<double> scratch;  // warp-shuffle emulation
-  int bid = 0, nblk = 0;
+  int bid = 0, nblk = 0;        // first CTA of the cluster, CTAs in the grid
+  int block = 0, cluster = 1;
+  int yield_kind = 0;           // what the fiber that just yielded waits for: 0 CTA barrier, 1 cluster barrier
 };
 
 void fiber_entry(unsigned lo, unsigned hi) {
   Worker* w = reinterpret_cast<Worker*>(((uintptr_t)hi << 32) | (uintptr_t)lo);
-  const int tid = w->current;
+  const int fid = w->current, cr = fid / w->block;
   vmk::Ctx c;
-  c.tid = tid;
-  c.bid = w->bid;
+  c.tid = fid % w->block;
+  c.bid = w->bid + cr;
   c.nblk = w->nblk;
-  c.smem = w->smem;
+  c.smem = w->csmem[cr];
   c.hbar = w;
-  c.hscratch = w->scratch.data();
+  c.hscratch = w->scratch.data() + 2 * (size_t)cr * w->block;
+  c.crank = cr;
+  c.csize = w->cluster;
+  c.hcsmem = w->csmem.data();
   w->fn(c, w->args);
-  w->fibers[tid].done = true;
-  swapcontext(&w->fibers[tid].ctx, &w->sched);
+  w->fibers[fid].done = true;
+  swapcontext(&w->fibers[fid].ctx, &w->sched);
 }
 
-void run_cta(Worker* w, int block) {
-  for (int t = 0; t < block; t++) {
+void run_cluster(Worker* w, int block, int cluster) {
+  for (int t = 0; t < block * cluster; t++) {
     Fiber& f = w->fibers[t];
     f.done = false;
     getcontext(&f.ctx);
@@ -76,15 +87,36 @@ void run_cta(Worker* w, int block) {
     const uintptr_t p = (uintptr_t)w;
     makecontext(&f.ctx, (void (*)())fiber_entry, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
   }
-  int alive = block;
-  while (alive > 0) {
-    for (int t = 0; t < block; t++) {
-      Fiber& f = w->fibers[t];
-      if (f.done) continue;
-      w->current = t;
-      swapcontext(&w->sched, &f.ctx);
-      if (f.done) alive--;
+  std::vector<int> alive(cluster, block);
+  int total = block * cluster;
+  bool flip = false;
+  while (total > 0) {
+    // every CTA runs until it is blocked at a cluster barrier (or has finished); then the barrier opens
+    for (int k = 0; k < cluster; k++) {
+      const int cr = flip ? cluster - 1 - k : k;
+      bool blocked = false;
+      while (alive[cr] > 0 && !blocked) {
+        int kinds[2] = {0, 0};
+        for (int t = 0; t < block; t++) {
+          Fiber& f = w->fibers[cr * block + t];
+          if (f.done) continue;
+          w->current = cr * block + t;
+          swapcontext(&w->sched, &f.ctx);
+          if (f.done) {
+            alive[cr]--;
+            total--;
+          } else {
+            kinds[w->yield_kind]++;
+          }
+        }
+        if (kinds[0] && kinds[1]) {
+          fprintf(stderr, "emul: threads of one CTA wait at a CTA barrier and at a cluster barrier at once\n");
+          abort();
+        }
+        blocked = kinds[1] > 0;
+      }
     }
+    flip = !flip;
   }
 }
 
@@ -92,6 +124,12 @@ void run_cta(Worker* w, int block) {
 
 extern "C" void vmk_host_barrier_wait(void* bar) {
   Worker* w = static_cast<Worker*>(bar);
+  w->yield_kind = 0;
+  swapcontext(&w->fibers[w->current].ctx, &w->sched);
+}
+extern "C" void vmk_host_cluster_barrier_wait(void* bar) {
+  Worker* w = static_cast<Worker*>(bar);
+  w->yield_kind = 1;
   swapcontext(&w->fibers[w->current].ctx, &w->sched);
 }
 
@@ -151,11 +189,13 @@ double emul_now_ms() {
   return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
 }
 
-int emul_run(int grid, int block, size_t smem, emul_body_fn fn, const void* args) {
-  if (grid < 1 || block < 1) return fail(2, "emul: empty launch");
+int emul_run(int grid, int block, int cluster, size_t smem, emul_body_fn fn, const void* args) {
+  if (grid < 1 || block < 1 || cluster < 1 || grid % cluster) return fail(2, "emul: bad launch dimensions");
+  const int nclusters = grid / cluster;
+  const size_t stride = ((smem ? smem : 256) + 255) / 256 * 256;
   unsigned hw = std::thread::hardware_concurrency();
   int nworkers = (int)(hw ? hw : 1);
-  if (nworkers > grid) nworkers = grid;
+  if (nworkers > nclusters) nworkers = nclusters;
   if (nworkers > 8) nworkers = 8;
   std::atomic<int> next{0};
   std::atomic<int> failed{0};
@@ -164,14 +204,18 @@ int emul_run(int grid, int block, size_t smem, emul_body_fn fn, const void* args
     w.fn = fn;
     w.args = args;
     w.nblk = grid;
-    w.fibers.resize(block);
-    w.scratch.assign(2 * (size_t)block, 0.0);
+    w.block = block;
+    w.cluster = cluster;
+    w.fibers.resize((size_t)block * cluster);
+    w.scratch.assign(2 * (size_t)block * cluster, 0.0);
     void* sm = nullptr;
-    if (posix_memalign(&sm, 256, smem ? smem : 256)) {
+    if (posix_memalign(&sm, 256, stride * cluster)) {
       failed = 1;
       return;
     }
     w.smem = static_cast<unsigned char*>(sm);
+    w.smem_stride = stride;
+    for (int r = 0; r < cluster; r++) w.csmem.push_back(w.smem + stride * r);
     for (auto& f : w.fibers) {
       f.stack = malloc(kStackBytes);
       if (!f.stack) failed = 1;
@@ -179,10 +223,10 @@ int emul_run(int grid, int block, size_t smem, emul_body_fn fn, const void* args
     if (!failed) {
       for (;;) {
         const int b = next.fetch_add(1);
-        if (b >= grid) break;
-        w.bid = b;
-        memset(w.smem, 0xff, smem);  // shared memory is uninitialised on the device: poison it
-        run_cta(&w, block);
+        if (b >= nclusters) break;
+        w.bid = b * cluster;
+        memset(w.smem, 0xff, stride * cluster);  // shared memory is uninitialised on the device: poison it
+        run_cluster(&w, block, cluster);
       }
     }
     for (auto& f : w.fibers) free(f.stack);

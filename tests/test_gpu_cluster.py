@@ -1,0 +1,197 @@
+"""GPU suite (-m gpu) for the thread-block-cluster kernels (csrc/vmk_cluster.cuh): rows of 16384 and 32768 points
+are transformed by a cluster of 2 / 4 CTAs that exchange data through distributed shared memory.
+
+Two libraries are exercised, both built from the same CUDA sources and called through the C ABI:
+  * libvmk_cltest.so (-DVMK_CLUSTER_TEST): the cluster kernels enabled for 64 .. 8192, where the CPU oracle is cheap --
+    direct comparison with the oracle on noise (every Fourier mode), rhs and multi-step runs;
+  * libvmk.so, the product, at 16384^2 (BASELINE config 5's per-GPU row length is 32768) and 32768^2: direct oracle
+    comparison of one Poisson solve at 16384^2, and at both sizes the size-independent properties
+      - periodic tiling: a field of period n0 in both directions, solved / stepped on the N-grid with the same dx, is
+        the tiled n0-grid solution (same divisor values cos(2 pi k'/n0), same eps quirk), which the oracle provides;
+      - analytic modes: f = sum of a few Fourier modes -> s = sum of the modes divided by the reference's divisor
+        (aa + bb cos kx) + cc cos ky with kx[1] = eps (Common.jl:101-121), built with libm cos like the reference.
+
+Tolerance (north_star): relative L2 <= 1e-10; single operator calls are held to 1e-12 / 1e-11."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from helpers import ghost_fill, grid, noise_field, rel_l2, stable_dt, vm_field
+
+pytestmark = pytest.mark.gpu
+
+
+def _host_gb():
+    """usable host memory in GB (cgroup limit if there is one)"""
+    avail = 0.
+    with open("/proc/meminfo") as fh:
+        for line in fh:
+            if line.startswith("MemAvailable:"):
+                avail = float(line.split()[1]) / 1e6
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v != "max":
+                avail = min(avail, float(v) / 1e9)
+        except OSError:
+            pass
+    return avail
+
+
+@pytest.fixture(scope="module")
+def cltest():
+    import torch
+    assert torch.cuda.is_available(), "GPU suite needs a CUDA device"
+    from cfd_julia_b200 import _build
+    from cfd_julia_b200._lib import VmkLibrary
+    from cfd_julia_b200.common import Common
+    so = _build.build_cluster_test()
+    cm = Common(VmkLibrary(so, "vmk_"))
+    yield cm
+    cm.clear_plans()
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU suite needs a CUDA device"
+    import cfd_julia_b200
+    from cfd_julia_b200.common import Common
+    lib = cfd_julia_b200.default_library()
+    assert lib.path.endswith("libvmk.so")
+    cm = Common(lib)
+    yield cm
+    cm.clear_plans()
+
+
+# ---- the cluster kernels against the oracle at small sizes (test build) -----------------------------------------
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_cluster_fps_noise(cltest, oracle_c, n):
+    pc.check_fps_noise(cltest, oracle_c, n)
+    if n >= 2048:
+        cltest.clear_plans()
+
+
+@pytest.mark.parametrize("n", [64, 128, 512, 1024, 2048, 4096])
+def test_cluster_rhs_noise(cltest, oracle_c, n):
+    pc.check_rhs(cltest, oracle_c, noise_field(n, seed=n))
+    if n >= 2048:
+        cltest.clear_plans()
+
+
+@pytest.mark.parametrize("n,nt", [(64, 50), (256, 20), (1024, 50), (2048, 10), (4096, 3)])
+def test_cluster_numerical_vm(cltest, oracle_c, n, nt):
+    pc.check_numerical(cltest, oracle_c, vm_field(n), nt, stable_dt(n, 1000.), 1000.)
+    if n >= 2048:
+        cltest.clear_plans()
+
+
+def test_cluster_v_layouts_agree(cltest):
+    """single-GPU "pieces" layout of V (K2 stores in K3's read order) against the row-major layout"""
+    n = 1024
+    dx, dy, _, _ = grid(n)
+    w0 = noise_field(n, 11)
+    res = []
+    for pieces in (1, 0):
+        p = cltest.plan(n, n)
+        p.set_option("v_pieces", pieces)
+        p.upload(w0)
+        p.step(dx, dy, 1e-4, 1000., 2)
+        wn = np.zeros_like(w0)
+        p.download(wn)
+        res.append(wn)
+    cltest.plan(n, n).set_option("v_pieces", 1)
+    assert rel_l2(res[0], res[1]) < 1e-14
+
+
+# ---- the product library at 16384^2 and 32768^2 ----------------------------------------------------------------
+def test_fps_16384_vs_oracle(gpu, oracle_c):
+    if _host_gb() < 40:
+        pytest.skip("needs ~25 GB of host memory for the oracle's complex arrays")
+    pc.check_fps_noise(gpu, oracle_c, 16384)
+    gpu.clear_plans()
+
+
+def _modes_problem(n, modes, dx, eps=1e-6):
+    """f^T and the expected s^T (C-contiguous transposes of the column-major arrays) for
+    f[i,j] = c0 + sum_m A cos(2 pi (a i + b j)/n + phi), by one matrix product each."""
+    i = np.arange(n)
+    cosk = np.array([math.cos(eps if k == 0 else (2 * math.pi / n) * (k if k < n // 2 else k - n)) for k in range(n)])
+    aa, bb, cc = -2. / dx**2 - 2. / dx**2, 2. / dx**2, 2. / dx**2
+    cj = np.empty((n, 2 * len(modes)))
+    cjs = np.empty((n, 2 * len(modes)))
+    ci = np.empty((2 * len(modes), n))
+    for m, (a, b, amp, phi) in enumerate(modes):
+        th, ps = 2 * np.pi * ((a * i) % n) / n + phi, 2 * np.pi * ((b * i) % n) / n
+        d = (aa + bb * cosk[a]) + cc * cosk[b]  # Common.jl:120, kx[1] = eps (:112), ky = kx (:113)
+        cj[:, 2 * m], cj[:, 2 * m + 1] = amp * np.cos(ps), -amp * np.sin(ps)
+        ci[2 * m], ci[2 * m + 1] = np.cos(th), np.sin(th)
+        cjs[:, 2 * m:2 * m + 2] = cj[:, 2 * m:2 * m + 2] / d
+    return cj @ ci, cjs @ ci
+
+
+def _check_modes(gpu, n, modes, tol):
+    dx = 2 * np.pi / n
+    ft, st = _modes_problem(n, modes, dx)
+    ft += 0.37  # the zero mode is dropped (Common.jl:118)
+    s = np.zeros((n + 2, n + 2), order="F")
+    gpu.fps(n, n, dx, dx, None, None, None, None, ft.T, s)
+    del ft
+    err = rel_l2(s[1:n + 1, 1:n + 1], st.T)
+    assert err < tol, err
+
+
+def _mode_sets(n):
+    rng = np.random.default_rng(n)
+    hi = [(int(rng.integers(n // 8, n // 2)), int(rng.integers(n // 8, n - n // 8)), float(rng.uniform(.5, 1.5)),
+           float(rng.uniform(0, 6.28))) for _ in range(10)]
+    hi += [(n // 2, n // 2, 1., 0.), (n // 2, n // 4 + 1, 1., .3), (n // 4 + 3, n // 2, 1., .7), (n // 2 - 1, n - 1, 1., 1.)]
+    lo = [(0, 1, 1., .2), (1, 0, 1., .4), (0, 5, 1., 1.), (3, 0, 1., 2.), (1, 1, 1., .1), (2, n - 3, 1., .5), (5, 7, 1., 3.),
+          (7, n - 2, 1., 4.), (6, 4, 1., 5.)]
+    return hi, lo
+
+
+@pytest.mark.parametrize("n", [16384, 32768])
+def test_fps_analytic_modes(gpu, n):
+    if _host_gb() < (30 if n == 16384 else 70):
+        pytest.skip("not enough host memory for the full-size arrays")
+    hi, lo = _mode_sets(n)
+    _check_modes(gpu, n, hi, 1e-11)
+    _check_modes(gpu, n, lo, 1e-11)
+    gpu.clear_plans()
+
+
+def _tiled_run(cm, oracle_c, n, n0, nt):
+    rep = n // n0
+    dx = 2 * np.pi / n0  # the same dx on both grids: the big domain is rep periods long
+    small = vm_field(n0) + 0.2 * noise_field(n0, 7)
+    dt = stable_dt(n0, 1000.)
+    ref = small.copy(order="F")
+    oracle_c.numerical(n0, n0, nt, dx, dx, dt, 1000., ref)
+    big = np.zeros((n + 2, n + 2), order="F")
+    big[1:n + 1, 1:n + 1] = np.tile(small[1:n0 + 1, 1:n0 + 1], (rep, rep))
+    ghost_fill(n, big)
+    out = cm.numerical_tgv(n, n, nt, dx, dx, dt, 1000., big)
+    assert out.shape == (n + 1, n + 1)
+    exp = np.tile(ref[1:n0 + 1, 1:n0 + 1], (rep, rep))
+    assert rel_l2(big[1:n + 1, 1:n + 1], exp) < 1e-10
+    assert np.array_equal(big, ghost_fill(n, big.copy(order="F")))  # ghosts valid on return (vm.jl:68-76)
+    assert np.array_equal(out, big[1:n + 2, 1:n + 2])
+
+
+@pytest.mark.parametrize("n,n0,nt", [(16384, 2048, 2), (32768, 1024, 2)])
+def test_tiled_run_matches_small_grid_oracle(gpu, oracle_c, n, n0, nt):
+    """the whole RK3 step: `numerical` on a field of period n0, N-grid vs the oracle's n0-grid run"""
+    if _host_gb() < (30 if n == 16384 else 70):
+        pytest.skip("not enough host memory for the full-size arrays")
+    _tiled_run(gpu, oracle_c, n, n0, nt)
+    gpu.clear_plans()
+
+
+def test_size_limits(gpu):
+    from cfd_julia_b200 import VmkError
+    with pytest.raises(VmkError):
+        gpu.plan(65536, 65536)
