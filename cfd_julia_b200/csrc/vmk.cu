@@ -316,7 +316,7 @@ struct vmk_plan {
   bool uploaded = false;
   int64_t launches = 0, graph_launches = 12;
   int k4_rows = 32, k4_ahead = 4;
-  int k1_prefetch = 0, k2_prefetch = 0, v_pieces = 1;
+  int k1_prefetch = 0, k2_prefetch = 0, v_pieces = 1, cl_prefetch = -1 /* auto */;
   int use_graph = 1;
 #ifndef VMK_EMUL
   std::map<StepParams, cudaGraphExec_t> graphs;
@@ -467,6 +467,10 @@ int cross_rank_barrier(vmk_plan* p) {
 #endif
 }
 
+// cluster kernels: which of K1 (1), K2 (2), K3 (4) bulk-prefetch their share of the next row into L2.  Measured
+// (profiles/r01_notes.md): K3's single contiguous block always pays, K1's runs only with 4 CTAs per row, K2's never.
+int cl_prefetch_mask(const vmk_plan* p) { return p->cl_prefetch >= 0 ? p->cl_prefetch : (p->ops.cluster == 4 ? 5 : 4); }
+
 // K1/K3 work units: groups of row pairs (see k1_body / k3_body)
 int rowpair_units(const vmk_plan* p, int npairs, int g) {
   const int fpc = p->ops.fpc;
@@ -495,7 +499,7 @@ int launch_k1(vmk_plan* p, const double* src) {
     a.npairs = np;
     a.k_own0 = p->rank * R;
     a.k_own1 = a.k_own0 + R;
-    a.prefetch = p->k1_prefetch;
+    a.prefetch = p->ops.cluster > 1 ? (cl_prefetch_mask(p) & 1) : p->k1_prefetch;
     const int work = rowpair_units(p, np, 1) * p->ops.cluster;
     VMK_TRY(p->ops.k1(work < p->res_k1 ? work : p->res_k1, a, p->st));
     p->launches++;
@@ -577,7 +581,7 @@ int launch_k2(vmk_plan* p, double sign) {
     a.R = R;
     a.rloc0 = rloc0;
     a.rank = p->rank;
-    a.prefetch = p->k2_prefetch;
+    a.prefetch = p->ops.cluster > 1 ? (cl_prefetch_mask(p) & 2) : p->k2_prefetch;
     const int work = (nr + p->ops.fpc - 1) / p->ops.fpc * p->ops.cluster;
     VMK_TRY(p->ops.k2(work < p->res_k2 ? work : p->res_k2, a, p->st));
     p->launches++;
@@ -607,6 +611,7 @@ int launch_k3(vmk_plan* p) {
   K3Args a;
   a.T = p->V;
   a.pieces = (p->nranks == 1 && p->v_pieces) ? 1 : 0;
+  a.prefetch = p->ops.cluster > 1 ? (cl_prefetch_mask(p) & 4) : 0;
   a.tw = p->tw;
   a.psi = p->psi;
   const int prev = (p->rank + p->nranks - 1) % p->nranks, next = (p->rank + 1) % p->nranks;
@@ -1134,13 +1139,14 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
   if (!p || !key) return fail(VMK_EARG, "NULL argument");
   const std::string k(key);
   int* knob = k == "v_pieces" ? &p->v_pieces : k == "k1_prefetch" ? &p->k1_prefetch : k == "k2_prefetch" ? &p->k2_prefetch
+              : k == "cl_prefetch" ? &p->cl_prefetch
               : k == "k4_ahead" ? &p->k4_ahead : k == "a2a_chunks" ? &p->a2a_chunks
               : k == "a2a_engine" ? &p->a2a_engine : k == "a2a_ctas" ? &p->a2a_ctas
               : k == "k2_push" ? &p->k2_push : nullptr;
   if (knob) {
     const int64_t hi = k == "a2a_ctas" ? 4096 : k == "a2a_chunks" ? 8 : 64;
     const int64_t lo = (k == "a2a_ctas" || k.find("group") != std::string::npos) ? 1
-                       : (k == "a2a_engine" || k == "k2_push") ? -1 : 0;
+                       : (k == "a2a_engine" || k == "k2_push" || k == "cl_prefetch") ? -1 : 0;
     if (value < lo || value > hi) return fail(VMK_EARG, "option value out of range");
     *knob = (int)value;
     drop_graphs(p);

@@ -154,6 +154,16 @@ VMK_HD void k1c_body(const Ctx& c, const K1Args& a) {
     const int pair = pb * C::FPC + g;
     const bool active = pair < a.npairs;
     const int jl = 2 * pair;
+    // the CTA's share of the NEXT pair's rows (EQ*Q runs of T doubles per row) is pulled into L2 while this pair is
+    // transformed: the loads at the top of the next iteration are synchronous (registers and shared memory are full)
+    if (a.prefetch && pair + ncl * C::FPC < a.npairs) {
+      const double* nx0 = a.w + (size_t)(jl + 2 * ncl * C::FPC + 1) * N;
+      for (int b = t; b < EQ * Q; b += T) {
+        const int off = L::own_pos_rt(0, c.crank * EQ + b / Q) + (b % Q) * NP;
+        prefetch_l2_bulk(nx0 + off, (unsigned)(T * sizeof(double)));
+        prefetch_l2_bulk(nx0 + N + off, (unsigned)(T * sizeof(double)));
+      }
+    }
     double2 v[E];
     {
       double2 x[EQ][Q];
@@ -237,6 +247,15 @@ VMK_HD void k2c_body(const Ctx& c, const K2Args& a) {
       cluster_has_row0 = rb == 0;  // item 0 is kx = 0
     } else {
       cluster_has_row0 = (a.row0 + rb * C::FPC) == 0;
+    }
+    if (a.prefetch && row + ncl * C::FPC < a.nrows && a.NJ >= T) {  // next row of this transform slot -> L2 (see k1c_body)
+      const int nrow = row + ncl * C::FPC;
+      const int ntrow = PIECES ? L::kx_of_item(nrow) : a.rloc0 + nrow;
+      for (int b = t; b < EQ * Q; b += T) {
+        const int j = L::own_pos_rt(0, c.crank * EQ + b / Q) + (b % Q) * NP;
+        prefetch_l2_bulk(a.T + ((size_t)(j >> a.log2NJ) * a.R + ntrow) * a.NJ + (j & (a.NJ - 1)),
+                         (unsigned)(T * sizeof(double2)));
+      }
     }
     double2 v[E];
     {
@@ -359,6 +378,10 @@ VMK_HD void k3c_body(const Ctx& c, const K3Args& a) {
     const int pair = pb * C::FPC + g;
     const bool active = pair < a.npairs;
     const int jl = 2 * pair;
+    if constexpr (PIECES) {  // the CTA's pieces of the next pair are one contiguous 16 N' byte block
+      if (a.prefetch && t == 0 && pair + ncl * C::FPC < a.npairs)
+        prefetch_l2_bulk(a.T + (size_t)(pair + ncl * C::FPC) * N + (size_t)c.crank * NP, (unsigned)(NP * sizeof(double2)));
+    }
     double2 v[E];
     {
       // the pieces (U[k][j], U[k][j+1]) of this CTA's k = Q k' + r, k' < N'/2

@@ -378,6 +378,7 @@ struct K3Args {
   double* hi_dst;     // where interior row NJ-1 is mirrored: next rank's bottom halo row (row 0 there)
   int NJ, npairs;
   int pieces;         // 1: T is laid out [pair][idx][2] (see K2Args::pieces): contiguous, coalesced reads
+  int prefetch;       // cluster kernels: bulk L2 prefetch of the next pair's pieces
 };
 
 template <class C, bool PIECES>

@@ -9,7 +9,8 @@
  * Conventions
  *   - All host arrays are column-major Float64 exactly as Julia lays them out.  "ghosted" means
  *     (nx+2) x (ny+2) with interior [2:nx+1, 2:ny+1] (1-based), element (i,j) at [(i-1) + (nx+2)*(j-1)].
- *   - nx == ny (the reference aliases ky = kx, Common.jl:113) and a power of two in [32, 8192].
+ *   - nx == ny (the reference aliases ky = kx, Common.jl:113) and a power of two in [32, 32768] (16384 and 32768: one row per
+ *     thread-block cluster of 2 / 4 SMs, csrc/vmk_cluster.cuh).
  *   - Every function returns 0 on success; otherwise a VMK_E* code, and vmk_last_error() (thread-local)
  *     describes it.  The library never falls back to a CPU path: without a usable CUDA device every
  *     compute entry point fails with VMK_ECUDA.
@@ -114,6 +115,8 @@ int64_t vmk_launch_count(vmk_plan* plan);
  *   "k4_ahead"    4      rows ahead of the march that K4 prefetches into L2 (0 = off)
  *   "v_pieces"    1      single GPU: K2 stores the solution spectrum as per-row-pair blocks in K3's read order
  *   "k1_prefetch", "k2_prefetch"  0   extra L2 bulk prefetch two rows ahead (no gain once cp.async existed)
+ *   "cl_prefetch" -1=auto 16384 / 32768 (cluster kernels): bit mask of the kernels (1 K1, 2 K2, 4 K3) that bulk-prefetch
+ *                        their CTA's share of the next row into L2
  *   "a2a_chunks"  0=auto launches K1 (and a staged K2) is split into so that the transpose overlaps with it
  *   "a2a_engine"  -1=auto forward transpose by copy engines (1; best at 2 GPUs) or the SM push kernel (0; best at 4, 8)
  *   "a2a_ctas"    128    CTAs of the push kernel

@@ -134,6 +134,7 @@ def _modes_problem(n, modes, dx, eps=1e-6):
 
 
 def _check_modes(gpu, n, modes, tol):
+    """low modes: the solution against the analytic one (s is dominated by them, so the comparison is sharp)"""
     dx = 2 * np.pi / n
     ft, st = _modes_problem(n, modes, dx)
     ft += 0.37  # the zero mode is dropped (Common.jl:118)
@@ -141,6 +142,30 @@ def _check_modes(gpu, n, modes, tol):
     gpu.fps(n, n, dx, dx, None, None, None, None, ft.T, s)
     del ft
     err = rel_l2(s[1:n + 1, 1:n + 1], st.T)
+    assert err < tol, err
+
+
+def _check_modes_residual(gpu, n, modes, tol):
+    """high modes: s is ~1/d ~ 1e-8 there, and the rounding noise of the input, amplified by 1/d ~ 1 in the LOW modes,
+    swamps a direct comparison (the oracle shows the same 3e-13 (512) ... 2e-11 (4096) ~ N^2 growth); applying the
+    5-point Laplacian -- whose symbol is the divisor, Common.jl:101-103,120 -- whitens it again: lap(s) = f - mean(f)"""
+    dx = 2 * np.pi / n
+    ft, _ = _modes_problem(n, modes, dx)
+    ft += 0.37
+    s = np.zeros((n + 2, n + 2), order="F")
+    gpu.fps(n, n, dx, dx, None, None, None, None, ft.T, s)
+    ghost_fill(n, s)
+    ft -= ft.mean()
+    num = den = 0.
+    st = s.T  # C-contiguous view [j, i]
+    for j0 in range(1, n + 1, 1024):  # row blocks keep the temporaries small at 32768^2
+        j1 = min(j0 + 1024, n + 1)
+        c = st[j0:j1, 1:n + 1]
+        lap = (st[j0:j1, 2:n + 2] + st[j0:j1, 0:n] + st[j0 + 1:j1 + 1, 1:n + 1] + st[j0 - 1:j1 - 1, 1:n + 1] - 4. * c) / dx**2
+        fb = ft[j0 - 1:j1 - 1]
+        num += float(np.sum((lap - fb)**2))
+        den += float(np.sum(fb**2))
+    err = (num / den)**.5
     assert err < tol, err
 
 
@@ -159,8 +184,8 @@ def test_fps_analytic_modes(gpu, n):
     if _host_gb() < (30 if n == 16384 else 70):
         pytest.skip("not enough host memory for the full-size arrays")
     hi, lo = _mode_sets(n)
-    _check_modes(gpu, n, hi, 1e-11)
-    _check_modes(gpu, n, lo, 1e-11)
+    _check_modes_residual(gpu, n, hi, 1e-13)
+    _check_modes(gpu, n, lo, 1e-13)
     gpu.clear_plans()
 
 

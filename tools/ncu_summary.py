@@ -1,5 +1,5 @@
 """Turn an .ncu-rep (ncu --set full) into the committed evidence: profiles/<tag>_ncu_summary.md and traffic.json.
-usage: python tools/ncu_summary.py gpurun_out/r01_prof.ncu-rep r01"""
+usage: python tools/ncu_summary.py gpurun_out/r01_prof.ncu-rep r01 ["title"]   (a title also keeps traffic.json as is)"""
 import csv
 import io
 import json
@@ -47,9 +47,10 @@ def main():
     h, units, body = rows[0], rows[1], rows[2:]
     names = []
     for r in body:
-        m = re.search(r"K(\d)Body(?:<\(int\)(\d)>)?", r[h.index("Kernel Name")])
-        names.append(f"k{m.group(1)}" + (f" (stage {m.group(2)})" if m.group(2) else ""))
-    out = [f"# ncu --set full, {tag}: one RK3 step at 8192^2 (12 launches), `python bench.py --steps 2 --warmup 3`",
+        m = re.search(r"K(\d)(C?)Body(?:<\(int\)(\d)>)?", r[h.index("Kernel Name")])
+        names.append(f"k{m.group(1)}" + ("c" if m.group(2) else "") + (f" (stage {m.group(3)})" if m.group(3) else ""))
+    title = sys.argv[3] if len(sys.argv) > 3 else "one RK3 step at 8192^2 (12 launches), `python bench.py --steps 2 --warmup 3`"
+    out = [f"# ncu --set full, {tag}: {title}",
            "", "Cold-cache, serialised launches under the profiler: compare shares and counters, not absolute times.", "",
            "| metric | " + " | ".join(names) + " |", "|---|" + "---|" * len(names)]
     for key, label in WANT:
@@ -67,8 +68,9 @@ def main():
             "```", json.dumps(traffic, indent=1), "```"]
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w") as f:
         f.write("\n".join(out) + "\n")
-    with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
-        json.dump(traffic, f, indent=1)
+    if len(sys.argv) <= 3:
+        with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
     print("\n".join(out[-8:]))
 
 
