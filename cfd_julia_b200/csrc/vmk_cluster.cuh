@@ -177,7 +177,9 @@ VMK_HD void k1c_body(const Ctx& c, const K1Args& a) {
           x[i][q] = active ? mk2(ld_stream1(r0 + n + q * NP), ld_stream1(r1 + n + q * NP)) : mk2(0.0, 0.0);
         });
       });
-      c.cluster_sync();  // every CTA is done with its buffer (mirror reads of the previous pair)
+      // every CTA is done with its buffer: the partner's mirror reads of the previous pair were consumed by that pair's
+      // stores.  Nothing to publish, so no release fence -- the global loads just issued stay in flight across it
+      c.cluster_sync_relaxed();
       L::scatter_forward(c, x, rsm, ctw, t);
       c.cluster_sync();
       L::gather_forward(v, sm, t, true);
@@ -270,7 +272,7 @@ VMK_HD void k2c_body(const Ctx& c, const K2Args& a) {
                            : mk2(0.0, 0.0);
         });
       });
-      c.cluster_sync();  // the previous row's gather_inverse has read every buffer
+      c.cluster_sync_relaxed();  // the previous row's gather_inverse has read every buffer (values consumed)
       L::scatter_forward(c, x, rsm, ctw, t);
       c.cluster_sync();
       L::gather_forward(v, sm, t, true);
@@ -320,7 +322,7 @@ VMK_HD void k2c_body(const Ctx& c, const K2Args& a) {
     }
     F::inverse(c, v, sm, tw, t);
     double2 x[EQ][Q];
-    c.cluster_sync();  // every thread of the cluster has read its last exchange
+    c.cluster_sync_relaxed();  // every thread of the cluster has read its last exchange (and used the values)
     L::scatter_inverse(c, v, rsm, t);
     c.cluster_sync();
     L::gather_inverse(c, x, sm, ctw, t);
@@ -397,7 +399,7 @@ VMK_HD void k3c_body(const Ctx& c, const K3Args& a) {
           ua[i] = ub[i] = mk2(0.0, 0.0);
         }
       });
-      c.cluster_sync();  // the previous pair's gather_inverse has read every buffer
+      c.cluster_sync_relaxed();  // the previous pair's gather_inverse has read every buffer (values consumed)
       // Z = U_j + i U_j+1: Z[k] into the own buffer, Z[N-k] (from the conjugates) into the partner's
       static_for<0, NI>([&](auto i_) {
         constexpr int i = decltype(i_)::value;
@@ -417,7 +419,7 @@ VMK_HD void k3c_body(const Ctx& c, const K3Args& a) {
     }
     F::inverse(c, v, sm, tw, t);
     double2 x[EQ][Q];
-    c.cluster_sync();
+    c.cluster_sync_relaxed();  // every thread of the cluster has read its last exchange (and used the values)
     L::scatter_inverse(c, v, rsm, t);
     c.cluster_sync();
     L::gather_inverse(c, x, sm, ctw, t);

@@ -39,6 +39,16 @@ struct Ctx {
     vmk_host_cluster_barrier_wait(hbar);
 #endif
   }
+  // same barrier without the release fence on the arriving side: for "this buffer may now be overwritten" hand-offs,
+  // where the arriving thread has nothing to publish (its reads are complete: their values have been consumed).  The
+  // releasing form makes every thread wait for all its outstanding global stores first (ERRBAR in SASS).
+  VMK_HD void cluster_sync_relaxed() const {
+#ifdef __CUDA_ARCH__
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
+    vmk_host_cluster_barrier_wait(hbar);
+#endif
+  }
   // address of the same shared-memory location in CTA `rank` of the cluster (distributed shared memory); the result
   // is a generic pointer, ordinary loads and stores through it travel over the SM-to-SM network
   template <class T>

@@ -15,7 +15,7 @@ for n in [int(a) for a in sys.argv[1:]] or [16384]:
     dt = 1e-4 * (8192. / n)**2
     p = Plan(lib, n, n)
     p.upload(w0)
-    for pf in (1, 0, 1):
+    for pf in (-1, 0, 7):
         p.set_option("cl_prefetch", pf)
         p.step(dx, dx, dt, 1000., 3)
         p.sync()
