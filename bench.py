@@ -91,17 +91,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def vm_initial_condition(n):
-    """vm_ic + main()'s ghost fill (Common.jl:208-219, vm.jl:107-128) -- synthetic input, no files."""
-    import cfd_julia_b200 as vm
+def vm_initial_condition(n, j0=0, nj=None):
+    """vm_ic + main()'s ghost fill (Common.jl:208-219, vm.jl:107-128) -- synthetic input, no files.
+    Only the ghosted columns j0 .. j0+nj+1 (a rank's slab and its halo columns) are evaluated; the rest of the
+    (lazily committed) array stays untouched, so that 8 ranks at 32768^2 do not each build an 8.6 GB field."""
     dx = 2 * np.pi / n
-    x = dx * np.arange(n + 1)
+    nj = n if nj is None else nj
     w = np.zeros((n + 2, n + 2), order="F")
-    vm.vm_ic(n, n, x, x, w)
-    w[0, :] = w[n, :]
-    w[:, 0] = w[:, n]
-    w[n + 1, :] = w[1, :]
-    w[:, n + 1] = w[:, 1]
+    xg = dx * ((np.arange(n + 2) - 1) % n)[:, None]          # ghosted index -> periodic node coordinate
+    # the slab's ghosted columns, plus the INTERIOR columns its halos wrap to (vmk_upload imposes periodicity from
+    # the interior of the caller's array, not from its ghost cells)
+    cols = np.unique(np.concatenate([np.arange(j0, j0 + nj + 2), [(j0 - 1) % n + 1, (j0 + nj) % n + 1]]))
+    for jb in range(0, len(cols), 512):                       # column blocks bound the temporaries
+        cb = cols[jb:jb + 512]
+        y = dx * ((cb - 1) % n)[None, :]
+        w[:, cb] = (np.exp(-np.pi * ((xg - 3 * np.pi / 4)**2 + (y - np.pi)**2)) +
+                    np.exp(-np.pi * ((xg - 5 * np.pi / 4)**2 + (y - np.pi)**2)))
     return dx, w
 
 
@@ -149,7 +154,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=8192, help="grid size (default: the BASELINE workload)")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=8192,
+                    help="grid size (default: the BASELINE workload); use --size under torchrun, whose own parser "
+                         "takes a bare --n for an abbreviation of its options")
     ap.add_argument("--cpu-n", type=int, default=4096, help="grid size of the --impl reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -173,7 +180,9 @@ def main():
     torch.cuda.set_device(local_rank)
     lib = vm.default_library()
     n, K, W = args.n, args.steps, args.warmup
-    dx, w0 = vm_initial_condition(n)
+    world_ = int(os.environ.get("WORLD_SIZE", "1"))
+    rank_ = int(os.environ.get("RANK", "0"))
+    dx, w0 = vm_initial_condition(n, rank_ * (n // world_), n // world_)
     global DT
     if n > 8192:
         DT = DT * (8192. / n)**2  # diffusive RK3 limit ~ dx^2 (1.155e-5 at 32768^2)

@@ -30,7 +30,7 @@ import numpy as np
 
 from ._lib import SNAPSHOT_FN, VmkError, VmkLibrary, default_library
 
-__all__ = ["Common", "fps", "vm_rhs", "numerical", "numerical_tgv", "ps_fft", "vm_ic", "exact_tgv",
+__all__ = ["Common", "fps", "vm_rhs", "numerical", "numerical_tgv", "numerical_hybrid", "ps_fft", "vm_ic", "exact_tgv",
            "compute_l2norm_bnds", "write_field", "Plan", "VmkError"]
 
 
@@ -170,6 +170,31 @@ class Common:
     def numerical_tgv(self, nx, ny, nt, dx, dy, dt, re, wn):
         return self._numerical(nx, ny, nt, dx, dy, dt, re, wn, 0, None, None, None, None)
 
+    # ---- 20_NS2D_Hybrid_Solver/hybrid.jl:14-90 ---------------------------------------------------
+    def numerical_hybrid(self, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
+        """The hybrid RK3 / Crank-Nicolson solver's `numerical`: same arguments as vm.jl's, wn is only read, returns
+        ut = real(ifft(wf)) as an (nx+1) x (ny+1) array.  snapshot(k, ut) / the text files vm{m}.txt every nt // ns
+        steps (hybrid.jl:71-86; this script does increment its record index)."""
+        if ns <= 0 or nt // ns == 0:
+            raise ZeroDivisionError("mod(k, nt ÷ ns) with nt ÷ ns == 0")  # Julia: DivideError at hybrid.jl:71
+        freq = nt // ns
+        p = self.plan(nx, ny)
+        ut = np.zeros((nx + 1, ny + 1), order="F")
+        rec = [0]
+
+        def _snap(k, _ptr, _user):
+            rec[0] += 1
+            if snapshot is not None:
+                snapshot(int(k), ut)
+            if outdir is not None:
+                write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut)
+
+        want = snapshot is not None or outdir is not None
+        cb = SNAPSHOT_FN(_snap) if want else SNAPSHOT_FN()
+        self.lib.check(self.lib.hybrid_numerical(p.handle, int(nt), dx, dy, dt, re, _ptr(wn, (nx + 2, ny + 2), "wn"),
+                                                 ut.ctypes.data, freq if want else 0, cb, None))
+        return ut
+
     def _numerical(self, nx, ny, nt, dx, dy, dt, re, wn, freq, x, y, snapshot, outdir):
         p = self.plan(nx, ny)
         g = (nx + 2, ny + 2)
@@ -246,6 +271,10 @@ def numerical(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=No
 
 def numerical_tgv(nx, ny, nt, dx, dy, dt, re, wn):
     return _common.numerical_tgv(nx, ny, nt, dx, dy, dt, re, wn)
+
+
+def numerical_hybrid(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
+    return _common.numerical_hybrid(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot, outdir)
 
 
 def plan(nx, ny) -> Plan:

@@ -21,6 +21,7 @@
 #define vmk_ps_fft vmke_ps_fft
 #define vmk_rhs vmke_rhs
 #define vmk_numerical vmke_numerical
+#define vmk_hybrid_numerical vmke_hybrid_numerical
 #define vmk_upload vmke_upload
 #define vmk_step vmke_step
 #define vmk_download vmke_download
@@ -47,6 +48,7 @@
 
 #include "vmk_backend.cuh"
 #include "vmk_cluster.cuh"
+#include "vmk_hybrid.cuh"
 #include "vmk_kernels.cuh"
 
 using namespace vmk;
@@ -77,6 +79,10 @@ struct SizeOps {
   int (*k1)(int grid, const K1Args&, Stream&);
   int (*k2)(int grid, const K2Args&, Stream&);
   int (*k3)(int grid, const K3Args&, Stream&);
+  // hybrid RK3/CN solver (vmk_hybrid.cuh); null for the cluster sizes
+  int (*kh_configure)(int* res);
+  int (*kh)(int grid, const KHArgs&, Stream&);
+  void (*fill_ksqperm)(const double* ksq, double* out);
 };
 
 template <class C>
@@ -90,6 +96,10 @@ struct K2Body {
 template <class C, bool PIECES = false>
 struct K3Body {
   VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, PIECES>(c, a); }
+};
+template <class C>
+struct KHBody {
+  VMK_HD static void run(const Ctx& c, const KHArgs& a) { kh_body<C>(c, a); }
 };
 template <int MODE>
 struct K4Body {
@@ -203,6 +213,9 @@ SizeOps make_cluster_ops() {
     return a.pieces ? be_launch_cluster<K3CBody<C, Q, true>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s)
                     : be_launch_cluster<K3CBody<C, Q>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
   };
+  o.kh_configure = nullptr;
+  o.kh = nullptr;
+  o.fill_ksqperm = nullptr;
   return o;
 }
 
@@ -236,6 +249,16 @@ SizeOps make_ops() {
     return a.pieces ? be_launch<K3Body<C, true>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s)
                     : be_launch<K3Body<C>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
   };
+  if constexpr (C::SPLIT) {  // (measurement / test configurations with the split exchange buffer)
+    o.kh_configure = nullptr;
+    o.kh = nullptr;
+  } else {
+    o.kh_configure = [](int* r) -> int { return be_configure<KHBody<C>, KHArgs, C::CT, C::MINB>(C::SMEM_BYTES, r); };
+    o.kh = [](int grid, const KHArgs& a, Stream& s) -> int {
+      return be_launch<KHBody<C>, KHArgs, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    };
+  }
+  o.fill_ksqperm = &fill_ccperm<C>;  // the same register-order permutation as the divisor table
   return o;
 }
 
@@ -294,6 +317,14 @@ struct vmk_plan {
   double* cccos = nullptr;
   double* ccperm = nullptr;
   double* staging = nullptr;  // (NJ+2) x (N+2), allocated on first host-array call
+  // hybrid solver (vmk_hybrid_numerical), allocated on first use
+  double2* hW = nullptr;      // vorticity spectrum [N/2][N], register order
+  double2* hJ = nullptr;      // previous stage's Jacobian spectrum
+  double2* hVs = nullptr;     // inverse-j of wf/k2 (V holds the one of wf)
+  double* hksq = nullptr;     // kx^2 table and its register-order permutation
+  double* hksqperm = nullptr;
+  double hyb_dx = 0;
+  int res_kh = 0;
   int64_t dev_bytes = 0;
   // peers (slab decomposition): pointers to every rank's buffers, own entries included
   double* peer_w[3][kMaxPeers];
@@ -607,6 +638,26 @@ int launch_k2(vmk_plan* p, double sign) {
   return 0;
 }
 
+// hybrid solver: inverse transform along i of a row-major half spectrum `V` into the slab `out` (single GPU)
+int launch_k3_rows(vmk_plan* p, const double2* V, double* out) {
+  K3Args a;
+  a.T = V;
+  a.pieces = 0;
+  a.prefetch = 0;
+  a.tw = p->tw;
+  a.psi = out;
+  a.lo_dst = out + (size_t)(p->NJ + 1) * p->N;
+  a.hi_dst = out;
+  a.NJ = p->NJ;
+  a.npairs = p->NJ / 2;
+  const int work = rowpair_units(p, a.npairs, 1);
+  Timed t(p, KI_K3);
+  VMK_TRY(p->ops.k3(work < p->res_k3 ? work : p->res_k3, a, p->st));
+  t.done();
+  p->launches++;
+  return 0;
+}
+
 int launch_k3(vmk_plan* p) {
   K3Args a;
   a.T = p->V;
@@ -706,6 +757,81 @@ int enqueue_step(vmk_plan* p, const StepParams& sp) {
   VMK_TRY(enqueue_poisson(p, p->w[2], -1.0));
   VMK_TRY(cross_rank_barrier(p));
   VMK_TRY(launch_k4(p, 3, 2, 0, 0, sp));
+  return 0;
+}
+
+// ---- hybrid RK3 / Crank-Nicolson solver (20_NS2D_Hybrid_Solver/hybrid.jl) -------------------------------------------
+int ensure_hybrid(vmk_plan* p, double dx) {
+  if (p->nranks != 1) return fail(VMK_EARG, "the hybrid solver runs on single-GPU plans");
+  if (!p->ops.kh) return fail(VMK_ESIZE, "the hybrid solver supports grids up to 8192^2");
+  const size_t spec = sizeof(double2) * (size_t)(p->N / 2) * p->N;
+  if (!p->hW) {
+    VMK_TRY(p->ops.kh_configure(&p->res_kh));
+    VMK_TRY(dev_alloc(p, (void**)&p->hW, spec));
+    VMK_TRY(dev_alloc(p, (void**)&p->hJ, spec));
+    VMK_TRY(dev_alloc(p, (void**)&p->hVs, spec));
+    VMK_TRY(dev_alloc(p, (void**)&p->hksq, sizeof(double) * p->N));
+    VMK_TRY(dev_alloc(p, (void**)&p->hksqperm, sizeof(double) * p->N));
+    p->hyb_dx = 0;
+  }
+  if (p->hyb_dx != dx) {
+    // wavespace, Common.jl:184-204: hx = 2 pi/(nx dx), kx[i] = hx (i-1), kx[i+nx/2] = hx (i-nx/2-1), kx[1] = eps, ky = kx
+    const int n = p->N;
+    std::vector<double> k(n), kp(n);
+    const double hx = 2.0 * M_PI / ((double)n * dx);
+    for (int i = 1; i <= n / 2; i++) {
+      k[i - 1] = hx * ((double)i - 1.0);
+      k[i + n / 2 - 1] = hx * (double)(i - n / 2 - 1);
+    }
+    k[0] = 1.e-6;
+    for (int i = 0; i < n; i++) k[i] = k[i] * k[i];
+    p->ops.fill_ksqperm(k.data(), kp.data());
+    VMK_TRY(be_sync(p->st));
+    VMK_TRY(be_h2d(p->hksq, k.data(), sizeof(double) * n, p->st));
+    VMK_TRY(be_h2d(p->hksqperm, kp.data(), sizeof(double) * n, p->st));
+    VMK_TRY(be_sync(p->st));
+    p->hyb_dx = dx;
+  }
+  return 0;
+}
+
+// stage 0: wf = fft(w0); 1..3: the RK3/CN stages (alpha, gamma, rho of hybrid.jl:29-31)
+int launch_kh(vmk_plan* p, int stage, double dt, double re) {
+  static const double alpha[4] = {0.0, 8. / 15., 2. / 15., 1. / 3.};
+  static const double gamma[4] = {0.0, 8. / 15., 5. / 12., 3. / 4.};
+  static const double rho[4] = {0.0, 0.0, -17. / 60., -5. / 12.};
+  KHArgs a;
+  a.T = p->T;
+  a.W = p->hW;
+  a.J = p->hJ;
+  a.Vw = p->V;
+  a.Vs = p->hVs;
+  a.tw = p->tw;
+  a.ksq = p->hksq;
+  a.ksqperm = p->hksqperm;
+  a.zfac = .5 * dt / re;
+  a.alpha = alpha[stage];
+  a.gdt = stage ? gamma[stage] * dt : 1.0;
+  a.rdt = rho[stage] * dt;
+  a.scale = 1.0 / (2.0 * (double)p->N * (double)p->N);
+  a.stage = stage;
+  a.nrows = p->N / 2;
+  const int work = (a.nrows + p->ops.fpc - 1) / p->ops.fpc;
+  Timed t(p, KI_K2);
+  VMK_TRY(p->ops.kh(work < p->res_kh ? work : p->res_kh, a, p->st));
+  t.done();
+  p->launches++;
+  return 0;
+}
+
+// ut = real(ifft(wf)) with the periodic duplicates (hybrid.jl:73-78): (N+1) x (N+1) on the host
+int hybrid_field(vmk_plan* p, double* ut) {
+  const size_t N = (size_t)p->N, n1 = N + 1;
+  VMK_TRY(launch_k3_rows(p, p->V, p->w[1]));
+  VMK_TRY(be_d2h_2d(ut, sizeof(double) * n1, p->w[1] + N, sizeof(double) * N, sizeof(double) * N, N, p->st));
+  VMK_TRY(be_sync(p->st));
+  for (size_t j = 0; j < N; j++) ut[N + j * n1] = ut[j * n1];
+  memcpy(ut + N * n1, ut, sizeof(double) * n1);
   return 0;
 }
 
@@ -882,6 +1008,11 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_free(p->cccos);
   be_free(p->ccperm);
   be_free(p->staging);
+  be_free(p->hW);
+  be_free(p->hJ);
+  be_free(p->hVs);
+  be_free(p->hksq);
+  be_free(p->hksqperm);
   be_event_destroy(p->ev0);
   be_event_destroy(p->ev1);
   be_event_destroy(p->ev_join);
@@ -1093,6 +1224,39 @@ int vmk_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, doub
     const size_t ld = (size_t)p->N + 2, n1 = (size_t)p->N + 1;
     for (size_t j = 0; j < n1; j++) memcpy(out + j * n1, wn + (j + 1) * ld + 1, sizeof(double) * n1);
   }
+  return VMK_OK;
+}
+
+int vmk_hybrid_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
+                         double* ut, int64_t freq, vmk_snapshot_fn snap, void* user) {
+  VMK_TRY(check_plan(p));
+  if (!wn || !ut) return fail(VMK_EARG, "wn or ut is NULL");
+  if (nt < 0) return fail(VMK_EARG, "nt < 0");
+  if (dx != dy) return fail(VMK_EARG, "the hybrid solver needs dx == dy (wavespace aliases ky = kx, Common.jl:197)");
+  VMK_TRY(ensure_hybrid(p, dx));
+  VMK_TRY(upload_ghosted(p, wn, p->w[0]));
+  VMK_TRY(be_event_record(p->ev0, p->st));
+  VMK_TRY(launch_k1(p, p->w[0]));
+  VMK_TRY(launch_kh(p, 0, dt, re));  // wf = fft(w0), wf[1,1] = 0 (hybrid.jl:26-27) and the first half of jacobian(wf)
+  const StepParams sp{dx, dy, 0.0, INFINITY};  // 1/re = 0: K4 in mode 0 returns -J/3 exactly (hybrid.jl:130-149)
+  for (int64_t k = 1; k <= nt; k++) {
+    for (int stage = 1; stage <= 3; stage++) {
+      VMK_TRY(launch_k3_rows(p, p->V, p->w[1]));   // w   = real(ifft(wf))        hybrid.jl:109
+      VMK_TRY(launch_k3_rows(p, p->hVs, p->psi));  // psi = real(ifft(wf / k2))   hybrid.jl:124-126
+      VMK_TRY(launch_k4(p, 0, 1, 1, 2, sp));       // -J(w, psi)/3                hybrid.jl:130-149
+      VMK_TRY(launch_k1(p, p->w[2]));              // fft along i                 hybrid.jl:151
+      VMK_TRY(launch_kh(p, stage, dt, re));        // fft along j, update, ifft along j of wf' and wf'/k2
+    }
+    if (snap && freq > 0 && k % freq == 0 && k != nt) {  // hybrid.jl:71-86 (the final field is produced below)
+      VMK_TRY(hybrid_field(p, ut));
+      snap(k, ut, user);
+    }
+  }
+  VMK_TRY(be_event_record(p->ev1, p->st));
+  p->ev_valid = true;
+  VMK_TRY(hybrid_field(p, ut));
+  if (snap && freq > 0 && nt > 0 && nt % freq == 0) snap(nt, ut, user);
+  p->uploaded = false;  // w[0..2] were used as scratch
   return VMK_OK;
 }
 

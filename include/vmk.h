@@ -91,6 +91,15 @@ typedef void (*vmk_snapshot_fn)(int64_t k, const double* wn_ghosted, void* user)
 int vmk_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, double re, double* wn, double* out,
                   int64_t freq, vmk_snapshot_fn snap, void* user);
 
+/* numerical(nx,ny,nt,dx,dy,dt,re,x,y,wn,ns)  20_NS2D_Hybrid_Solver/hybrid.jl:14-90 -- the hybrid solver: the vorticity
+ * lives in Fourier space, the Arakawa Jacobian is evaluated in real space (jacobian(), hybrid.jl:96-152) and advanced
+ * with RK3, the diffusion with Crank-Nicolson per mode (k2 from wavespace, Common.jl:184-204, kx[1] = eps).
+ * wn: ghosted initial vorticity (read only, as in the reference).  ut: (nx+1) x (ny+1), receives real(ifft(wf)) with
+ * the periodic duplicates (what the reference returns).  snap(k, ut, user) after every step k with k % freq == 0
+ * (here the array passed is ut, (nx+1) x (ny+1)).  Single-GPU plans, nx == ny <= 8192, dx == dy. */
+int vmk_hybrid_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
+                         double* ut, int64_t freq, vmk_snapshot_fn snap, void* user);
+
 /* ---- device-resident path (what numerical() is built from) ------------------------------------------- */
 int vmk_upload(vmk_plan* plan, const double* wn_ghosted);
 int vmk_step(vmk_plan* plan, double dx, double dy, double dt, double re, int64_t nsteps); /* asynchronous */

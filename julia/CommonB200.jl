@@ -110,6 +110,33 @@ numerical(nx, ny, nt, Δx, Δy, Δt, re, wn::Matrix{Float64}) = begin
   return out
 end
 
+# hybrid.jl flavour (20_NS2D_Hybrid_Solver/hybrid.jl:14-90): RK3 / Crank-Nicolson in Fourier space.  Same arguments as
+# vm.jl's numerical; wn is only read; returns ut = real(ifft(wf)) with the periodic duplicates, (nx+1) x (ny+1), and
+# writes "vm<m>.txt" every nt ÷ ns steps (hybrid.jl:71-86).
+numerical_hybrid(nx, ny, nt, Δx, Δy, Δt, re, x, y, wn::Matrix{Float64}, ns) = begin
+  ghosted(wn, nx, ny, "wn")
+  freq = nt ÷ ns
+  ut = Array{Float64}(undef, nx + 1, ny + 1)
+  m = Ref(1)
+  cb = Ref{Function}(k -> begin
+    @show k
+    open("vm$(m[]).txt", "w") do io
+      for j ∈ 1:ny + 1 for i ∈ 1:nx + 1
+        write(io, "$(x[i]) $(y[j]) $(ut[i, j])\n")
+      end end
+    end
+    m[] += 1
+  end)
+  GC.@preserve cb begin
+    check(ccall((:vmk_hybrid_numerical, libvmk), Cint,
+                (Ptr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cvoid},
+                 Ptr{Cvoid}),
+                vmk_plan(nx, ny).handle, nt, Δx, Δy, Δt, re, wn, ut, freq,
+                @cfunction(snap_trampoline, Cvoid, (Int64, Ptr{Cdouble}, Ptr{Cvoid})), pointer_from_objref(cb)))
+  end
+  return ut
+end
+
 # ---- several GPUs driven by this one Julia process (slab decomposition along j) ---------------------------------------
 # plans = vmk_plans_multi(nx, ny, ngpu); numerical_multi(plans, nt, Δx, Δy, Δt, re, wn) steps all ranks concurrently
 # (vmk_step is asynchronous) and gathers every rank's rows back into wn.

@@ -177,3 +177,78 @@ def grid(nx, ny, lx=2 * np.pi, ly=2 * np.pi):
     dx = lx / nx
     dy = ly / ny
     return dx, dy, dx * np.arange(nx + 1), dy * np.arange(ny + 1)
+
+
+# ---- 20_NS2D_Hybrid_Solver/hybrid.jl ------------------------------------------------------------
+def wavespace(nx, ny, dx, dy, eps=1.e-6):
+    """Common.jl:184-204: k2[i,j] = kx[i]^2 + ky[j]^2, hx = 2 pi/(nx dx), kx[1] = eps, ky = kx."""
+    hx = 2 * np.pi / (nx * dx)
+    kx = np.empty(nx)
+    i = np.arange(1, nx // 2 + 1)
+    kx[i - 1] = hx * (i - 1.)
+    kx[i + nx // 2 - 1] = hx * (i - nx // 2 - 1)
+    kx[0] = eps
+    ky = kx
+    return kx[:, None]**2 + ky[None, :]**2
+
+
+def hybrid_jacobian(nx, ny, dx, dy, wf, k2):
+    """hybrid.jl:96-152: jf = fft(-J(w, psi)), w = real(ifft(wf)), psi = real(ifft(wf / k2)), Arakawa J."""
+    gg = 1. / (4. * dx * dy)
+    hh = 1. / 3.
+
+    def ghosted(a):
+        g = np.empty((nx + 2, ny + 2))
+        g[1:nx + 1, 1:ny + 1] = a
+        g[nx + 1, :] = g[1, :]
+        g[:, ny + 1] = g[:, 1]
+        g[0, :] = g[nx, :]
+        g[:, 0] = g[:, ny]
+        return g
+
+    w = ghosted(np.real(np.fft.ifft2(wf)))
+    s = ghosted(np.real(np.fft.ifft2(wf / k2)))
+    c = slice(1, nx + 1)
+    p = slice(2, nx + 2)
+    m = slice(0, nx)
+    j1 = gg * ((w[p, c] - w[m, c]) * (s[c, p] - s[c, m]) - (w[c, p] - w[c, m]) * (s[p, c] - s[m, c]))
+    j2 = gg * (w[p, c] * (s[p, p] - s[p, m]) - w[m, c] * (s[m, p] - s[m, m]) -
+               w[c, p] * (s[p, p] - s[m, p]) + w[c, m] * (s[p, m] - s[m, m]))
+    j3 = gg * (w[p, p] * (s[c, p] - s[p, c]) - w[m, m] * (s[m, c] - s[c, m]) -
+               w[m, p] * (s[c, p] - s[m, c]) + w[p, m] * (s[p, c] - s[c, m]))
+    return np.fft.fft2(-(j1 + j2 + j3) * hh)
+
+
+def hybrid_numerical(nx, ny, nt, dx, dy, dt, re, wn, freq=0, snapshot=None):
+    """hybrid.jl:14-90: RK3 (explicit Jacobian) / Crank-Nicolson (implicit diffusion) in Fourier space.  Returns
+    ut = real(ifft(wnf)) with the periodic duplicate row/column, (nx+1) x (ny+1); wn (ghosted) is only read.
+    snapshot(k, ut) every `freq` steps (hybrid.jl:71-86; the text dump stays with the caller)."""
+    assert nx == ny
+    k2 = wavespace(nx, ny, dx, dy)
+    wnf = np.fft.fft2(wn[1:nx + 1, 1:ny + 1].astype(np.complex128))
+    wnf[0, 0] = 0.
+    a1, a2, a3 = 8. / 15., 2. / 15., 1. / 3.
+    g1, g2, g3 = 8. / 15., 5. / 12., 3. / 4.
+    r2, r3 = -17. / 60., -5. / 12.
+    z = .5 * dt * k2 / re
+    d1, d2, d3 = a1 * z, a2 * z, a3 * z
+
+    def field(wf):
+        ut = np.empty((nx + 1, ny + 1), order="F")
+        ut[:nx, :ny] = np.real(np.fft.ifft2(wf))
+        ut[nx, :] = ut[0, :]
+        ut[:, ny] = ut[:, 0]
+        return ut
+
+    for k in range(1, nt + 1):
+        jnf = hybrid_jacobian(nx, ny, dx, dy, wnf, k2)
+        w1f = ((1. - d1) / (1. + d1)) * wnf + (g1 * dt * jnf) / (1. + d1)
+        w1f[0, 0] = 0.
+        j1f = hybrid_jacobian(nx, ny, dx, dy, w1f, k2)
+        w2f = ((1. - d2) / (1. + d2)) * w1f + (r2 * dt * jnf + g2 * dt * j1f) / (1. + d2)
+        w2f[0, 0] = 0.
+        j2f = hybrid_jacobian(nx, ny, dx, dy, w2f, k2)
+        wnf = ((1. - d3) / (1. + d3)) * w2f + (r3 * dt * j1f + g3 * dt * j2f) / (1. + d3)
+        if snapshot is not None and freq > 0 and k % freq == 0:
+            snapshot(k, field(wnf))
+    return field(wnf)

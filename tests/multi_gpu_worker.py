@@ -29,7 +29,17 @@ def main():
         return out
 
     worst = 0.0
-    for n, nt in ((256, 6), (1024, 3), (4096, 1)):
+    # VMK_MG_CASES="n:nt,..." ; "n@n0:nt" = a field of period n0 on the n-grid (same dx), checked against the oracle's
+    # n0-grid run -- how the cluster sizes 16384 / 32768 are checked (tests/test_gpu_cluster.py explains the property)
+    cases = []
+    for item in os.environ.get("VMK_MG_CASES", "256:6,1024:3,4096:1").split(","):
+        size, nt = item.split(":")
+        n, n0 = (int(q) for q in size.split("@")) if "@" in size else (int(size), None)
+        cases.append((n, n0, int(nt)))
+    for n, n0, nt in cases:
+        if n0 is not None:
+            worst = max(worst, tiled_case(lib, Plan, oc, dist, gather, rank, world, n, n0, nt))
+            continue
         dx, dy, _, _ = grid(n)
         dt = stable_dt(n, 1000.)
         w0 = vm_field(n) + 0.05 * noise_field(n, 7)
@@ -54,6 +64,37 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.destroy_process_group()
     return 0 if float(t.item()) < 1e-10 else 1
+
+
+def tiled_case(lib, Plan, oc, dist, gather, rank, world, n, n0, nt):
+    """Each rank fills only its own columns (and halo columns) of the lazily committed n x n host array."""
+    from helpers import noise_field, rel_l2, stable_dt, vm_field
+    rep, nj, j0 = n // n0, n // world, rank * (n // world)
+    dx = 2 * np.pi / n0
+    dt = stable_dt(n0, 1000.)
+    small = vm_field(n0) + 0.2 * noise_field(n0, 7)
+    ref = small.copy(order="F")
+    _, sref = oc.numerical(n0, n0, nt, dx, dx, dt, 1000., ref)
+    ii = 1 + (np.arange(n + 2) - 1) % n0                  # ghosted index on the n-grid -> ghosted index on the tile
+    jj = 1 + (np.arange(j0, j0 + nj + 2) - 1) % n0
+    wn = np.zeros((n + 2, n + 2), order="F")
+    wn[:, j0:j0 + nj + 2] = small[np.ix_(ii, jj)]
+    for jw in ((j0 - 1) % n + 1, (j0 + nj) % n + 1):      # interior columns the halos wrap to (vmk_upload reads those)
+        wn[:, jw] = small[ii, 1 + (jw - 1) % n0]
+    psi = np.zeros((n + 2, n + 2), order="F")
+    p = Plan(lib, n, n, rank, world)
+    p.attach_peers(gather)
+    dist.barrier()
+    p.upload(wn)
+    p.step(dx, dx, dt, 1000., nt)
+    p.download(wn, psi)
+    e1 = rel_l2(wn[:, j0:j0 + nj + 2], ref[np.ix_(ii, jj)])
+    e2 = rel_l2(psi[:, j0:j0 + nj + 2], sref[np.ix_(ii, jj)])
+    print(f"rank {rank}/{world} n={n} (period {n0}) steps={nt}: rel-L2 w {e1:.2e} psi {e2:.2e} "
+          f"step {p.step_elapsed_ms() / nt:.3f} ms", flush=True)
+    dist.barrier()
+    p.close()
+    return max(e1, e2)
 
 
 if __name__ == "__main__":

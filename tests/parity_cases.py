@@ -144,3 +144,22 @@ def check_errors(cm):
         p.step(.1, .1, .01, 100., 1)  # step before upload
     assert e.value.code == 4
     p.close()
+
+
+def check_hybrid(cm, onp, n, nt, dt=None, re=1000., ns=1, tol=TOL_RUN):
+    """20_NS2D_Hybrid_Solver/hybrid.jl `numerical` against the numpy restatement (oracle_np.hybrid_numerical)."""
+    dx, dy, x, y = grid(n)
+    w = vm_field(n) + 0.05 * noise_field(n, 3)
+    dt = stable_dt(n, re) if dt is None else dt
+    wb = w.copy(order="F")
+    snaps_ref, snaps = [], []
+    ref = onp.hybrid_numerical(n, n, nt, dx, dy, dt, re, w, nt // ns, lambda k, ut: snaps_ref.append((k, ut.copy())))
+    ut = cm.numerical_hybrid(n, n, nt, dx, dy, dt, re, x, y, w, ns, snapshot=lambda k, u: snaps.append((k, u.copy())))
+    assert ut.shape == (n + 1, n + 1) and np.array_equal(w, wb)  # wn is only read (hybrid.jl:24)
+    assert rel_l2(ut, ref) < tol
+    assert np.array_equal(ut[n, :], ut[0, :]) and np.array_equal(ut[:, n], ut[:, 0])  # hybrid.jl:75-78
+    assert abs(ut[:n, :n].mean()) < 1e-12  # the mean mode is dropped (hybrid.jl:27)
+    assert [k for k, _ in snaps] == [k for k, _ in snaps_ref]
+    for (_, a), (_, b) in zip(snaps, snaps_ref):
+        assert rel_l2(a, b) < tol
+    return ut

@@ -83,6 +83,29 @@ def test_numerical_noise(emul, oracle_c):
     pc.check_numerical(emul, oracle_c, noise_field(64, 3), 5, 1e-3, 100.)
 
 
+@pytest.mark.parametrize("n,nt,ns", [(32, 6, 3), (64, 4, 2), (128, 3, 1), (256, 2, 1), (512, 2, 2), (1024, 1, 1)])
+def test_hybrid_solver(emul, oracle_np, n, nt, ns):
+    """hybrid.jl's RK3/CN spectral-space solver (kernel KH + the finite-difference path's K1/K3/K4)"""
+    pc.check_hybrid(emul, oracle_np, n, nt, ns=ns)
+
+
+def test_hybrid_solver_errors(emul):
+    from cfd_julia_b200.common import Plan, VmkError
+    n = 64
+    dx, dy, x, y = grid(n)
+    w = vm_field(n)
+    with pytest.raises(ZeroDivisionError):
+        emul.numerical_hybrid(n, n, 3, dx, dy, .01, 1000., x, y, w, 5)
+    with pytest.raises(VmkError):  # wavespace aliases ky = kx: dx != dy is not representable
+        emul.numerical_hybrid(n, n, 2, dx, 2 * dy, .01, 1000., x, y, w, 1)
+    p = Plan(emul.lib, n, n, 0, 2)
+    ut = np.zeros((n + 1, n + 1), order="F")
+    from cfd_julia_b200._lib import SNAPSHOT_FN
+    assert emul.lib.hybrid_numerical(p.handle, 1, dx, dy, .01, 1000., w.ctypes.data, ut.ctypes.data, 0, SNAPSHOT_FN(),
+                                     None) != 0
+    p.close()
+
+
 def test_golden(emul):
     pc.check_golden(emul)
 

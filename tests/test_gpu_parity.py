@@ -96,6 +96,35 @@ def test_tgv_1024_full_config(gpu):
     assert abs(np.max(np.abs(out)) - 8. * np.exp(-32. / re)) < 1e-3  # amplitude 2 nq exp(-2 nq^2 t / re)
 
 
+@pytest.mark.parametrize("n,nt,ns", [(32, 20, 4), (64, 20, 2), (128, 50, 5), (512, 10, 1), (1024, 10, 2), (2048, 3, 1),
+                                      (4096, 2, 1)])
+def test_hybrid_solver(gpu, oracle_np, n, nt, ns):
+    """20_NS2D_Hybrid_Solver/hybrid.jl (RK3 / Crank-Nicolson in Fourier space) against the numpy oracle"""
+    pc.check_hybrid(gpu, oracle_np, n, nt, ns=ns)
+    if n >= 2048:
+        gpu.clear_plans()
+
+
+def test_hybrid_defaults_500_steps(gpu, oracle_np):
+    """hybrid.jl's own configuration (128^2, dt = .01, Re = 1000), first 500 of its 2000 steps"""
+    pc.check_hybrid(gpu, oracle_np, 128, 500, dt=.01, ns=10)
+
+
+def test_hybrid_8192_properties(gpu):
+    """full size, no oracle run (minutes of numpy FFTs): finite, mean-free, periodic duplicates, enstrophy decays"""
+    n = 8192
+    dx, dy, x, y = grid(n)
+    w = vm_field(n)
+    ut = gpu.numerical_hybrid(n, n, 2, dx, dy, 1e-4, 1000., x, y, w, 1)
+    assert np.isfinite(ut).all() and abs(ut[:n, :n].mean()) < 1e-12
+    assert np.array_equal(ut[n, :], ut[0, :]) and np.array_equal(ut[:, n], ut[:, 0])
+    w0 = w[1:n + 1, 1:n + 1] - w[1:n + 1, 1:n + 1].mean()
+    e0, e1 = float((w0**2).sum()), float((ut[:n, :n]**2).sum())
+    assert e1 < e0 and (e0 - e1) / e0 < 1e-3
+    assert rel_l2(ut[:n, :n], w0) < 1e-3  # two steps of dt = 1e-4 barely move the field
+    gpu.clear_plans()
+
+
 def test_golden(gpu):
     pc.check_golden(gpu)
 

@@ -24,6 +24,19 @@ def test_slab_parity(world):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("world,cases", [(2, "16384@2048:1"), (8, "32768@1024:1")])
+def test_slab_parity_cluster_sizes(world, cases):
+    """rows of 16384 / 32768 points (thread-block-cluster kernels) across GPUs; (8, 32768) is BASELINE config 5"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
+           os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, VMK_MG_CASES=cases))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_single_process_two_devices():
     """The Julia host model: ONE process and one host thread drive two devices through
     vmk_peer_attach_local; vmk_step is asynchronous, so stepping rank 0 and then rank 1 runs them concurrently."""
