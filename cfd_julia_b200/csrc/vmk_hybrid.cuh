@@ -83,7 +83,9 @@ VMK_HD void kh_body(const Ctx& c, const KHArgs& a) {
       auto mirror_addr = [&](int u, int p) {
         return F::addr(F::pos_of_k((N - F::k_of_pos(((t + T * u) << bl) | p)) & (N - 1)));
       };
-      double2 ym[E];
+      // (all barriers of this branch sit outside the per-transform `kx == 0` test: at small N several transforms share
+      // a warp, and a barrier inside a divergent branch would hang)
+      double2 ym[E], w[E], wm[E];
       F::template store_smem<P - 1>(y, sm, t);
       c.sync();
       static_for<0, E>([&](auto e_) {
@@ -91,28 +93,30 @@ VMK_HD void kh_body(const Ctx& c, const KHArgs& a) {
         ym[e] = sm[mirror_addr(e / rl, e % rl)];
       });
       c.sync();
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        w[e] = (a.stage >= 1 && active) ? a.W[roff + e * T + t] : mk2(0.0, 0.0);
+      });
+      F::template store_smem<P - 1>(w, sm, t);
+      c.sync();
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        wm[e] = sm[mirror_addr(e / rl, e % rl)];
+      });
+      c.sync();
       if (kx == 0) {
-        // W (stage 0: there is no old W, wf' = the transform itself, i.e. Y with gamma dt = 1 handled by the caller)
-        double2 w[E];
-        static_for<0, E>([&](auto e_) {
-          constexpr int e = decltype(e_)::value;
-          w[e] = (a.stage >= 1) ? a.W[roff + e * T + t] : mk2(0.0, 0.0);
-        });
-        F::template store_smem<P - 1>(w, sm, t);
-        c.sync();
         const double ka = ld_ro(a.ksq + 0), kb = ld_ro(a.ksq + N / 2);
         static_for<0, E>([&](auto e_) {
           constexpr int e = decltype(e_)::value, u = e / rl, p = e % rl;
           const int ky = F::k_of_pos(((t + T * u) << bl) | p);
-          const double2 wm = sm[mirror_addr(u, p)];
           const double kyy = ld_ro(a.ksq + ky);
           const double k2a = ka + kyy, k2b = kb + kyy;                  // Common.jl:199-201
           const double da = a.alpha * (a.zfac * k2a), db = a.alpha * (a.zfac * k2b);
           const double ga = rcp_rn(1.0 + da), gb = rcp_rn(1.0 + db);
           const double ca = (1.0 - da) * ga, cb = (1.0 - db) * gb;
           // parts: A = (X + conj Xm)/2, B = -i (X - conj Xm)/2
-          const double2 wa = mk2(.5 * (w[e].x + wm.x), .5 * (w[e].y - wm.y));
-          const double2 wb = mk2(.5 * (w[e].y + wm.y), .5 * (wm.x - w[e].x));
+          const double2 wa = mk2(.5 * (w[e].x + wm[e].x), .5 * (w[e].y - wm[e].y));
+          const double2 wb = mk2(.5 * (w[e].y + wm[e].y), .5 * (wm[e].x - w[e].x));
           const double2 ya = mk2(.5 * (y[e].x + ym[e].x), .5 * (y[e].y - ym[e].y));
           const double2 yb = mk2(.5 * (y[e].y + ym[e].y), .5 * (ym[e].x - y[e].x));
           double2 pa, pb;
@@ -128,7 +132,6 @@ VMK_HD void kh_body(const Ctx& c, const KHArgs& a) {
           const double ra = a.scale * rcp_rn(k2a), rb2 = a.scale * rcp_rn(k2b);
           y[e] = mk2(pa.x * ra - pb.y * rb2, pa.y * ra + pb.x * rb2);  // (A'/k2a + i B'/k2b) / (2 N^2)
         });
-        c.sync();
       } else {
         // an ordinary row that shares the CTA with row 0 (several transforms per CTA at small N)
         const double kxx = ld_ro(a.ksq + kx);
@@ -139,17 +142,13 @@ VMK_HD void kh_body(const Ctx& c, const KHArgs& a) {
           const double d = a.alpha * (a.zfac * k2);
           const double gg = rcp_rn(1.0 + d), cc = (1.0 - d) * gg;
           if (a.stage >= 1) {
-            const double2 w = active ? a.W[roff + e * T + t] : mk2(0.0, 0.0);
-            v[e] = mk2(fma_(cc, w.x, gg * y[e].x), fma_(cc, w.y, gg * y[e].y));
+            v[e] = mk2(fma_(cc, w[e].x, gg * y[e].x), fma_(cc, w[e].y, gg * y[e].y));
           } else {
             v[e] = y[e];
           }
           const double r = a.scale * rcp_rn(k2);
           y[e] = cscale(v[e], r);
         });
-        // (two more barriers, to stay in step with the transform that owns row 0)
-        c.sync();
-        c.sync();
       }
       if (active) {
         static_for<0, E>([&](auto e_) {
