@@ -56,6 +56,7 @@ struct Worker {
   int bid = 0, nblk = 0;        // first CTA of the cluster, CTAs in the grid
   int block = 0, cluster = 1;
   int yield_kind = 0;           // what the fiber that just yielded waits for: 0 CTA barrier, 1 cluster barrier
+  void* yield_site = nullptr;   // return address of that barrier call = the call site in the (inlined) kernel body
 };
 
 void fiber_entry(unsigned lo, unsigned hi) {
@@ -97,8 +98,10 @@ void run_cluster(Worker* w, int block, int cluster) {
       bool blocked = false;
       while (alive[cr] > 0 && !blocked) {
         int kinds[2] = {0, 0};
+        void* warp_site = nullptr;
         for (int t = 0; t < block; t++) {
           Fiber& f = w->fibers[cr * block + t];
+          if (t % 32 == 0) warp_site = nullptr;
           if (f.done) continue;
           w->current = cr * block + t;
           swapcontext(&w->sched, &f.ctx);
@@ -107,6 +110,14 @@ void run_cluster(Worker* w, int block, int cluster) {
             total--;
           } else {
             kinds[w->yield_kind]++;
+            // On the device the 32 threads of a warp must reach the SAME barrier instruction together: a barrier inside
+            // a branch that diverges within a warp hangs (or is undefined).  Fibers cannot hang that way, so check it.
+            if (!warp_site) warp_site = w->yield_site;
+            if (warp_site != w->yield_site) {
+              fprintf(stderr, "emul: threads of one warp (CTA %d, warp %d) wait at different barrier call sites: "
+                              "a barrier sits inside a branch that diverges within the warp\n", w->bid + cr, t / 32);
+              abort();
+            }
           }
         }
         if (kinds[0] && kinds[1]) {
@@ -125,11 +136,13 @@ void run_cluster(Worker* w, int block, int cluster) {
 extern "C" void vmk_host_barrier_wait(void* bar) {
   Worker* w = static_cast<Worker*>(bar);
   w->yield_kind = 0;
+  w->yield_site = __builtin_return_address(0);
   swapcontext(&w->fibers[w->current].ctx, &w->sched);
 }
 extern "C" void vmk_host_cluster_barrier_wait(void* bar) {
   Worker* w = static_cast<Worker*>(bar);
   w->yield_kind = 1;
+  w->yield_site = __builtin_return_address(0);
   swapcontext(&w->fibers[w->current].ctx, &w->sched);
 }
 
