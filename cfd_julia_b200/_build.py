@@ -47,17 +47,28 @@ def stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
+def _compile(out: str, extra) -> None:
+    """nvcc into a private temporary file, then an atomic rename: several ranks of one torchrun job that all find the
+    library stale each produce a complete file, and no process ever maps a half-written one."""
+    tmp = f"{out}.tmp.{os.getpid()}"
+    try:
+        subprocess.check_call([_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", tmp, SRC], cwd=ROOT)
+        os.replace(tmp, out)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or stale():
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
-        subprocess.check_call(cmd, cwd=ROOT)
+        _compile(SO, ["-Xptxas", "-v"] if verbose else [])
     return SO
 
 
 def build_cluster_test(force: bool = False) -> str:
     if force or not os.path.exists(SO_CLUSTER_TEST) or any(
             os.path.getmtime(x) > os.path.getmtime(SO_CLUSTER_TEST) for x in sources()):
-        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-DVMK_CLUSTER_TEST", "-o", SO_CLUSTER_TEST, SRC], cwd=ROOT)
+        _compile(SO_CLUSTER_TEST, ["-DVMK_CLUSTER_TEST"])
     return SO_CLUSTER_TEST
 
 

@@ -18,7 +18,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = int(sys.argv[1])
-    dx, w0 = vm_initial_condition(n)
+    dx, w0 = vm_initial_condition(n, rank * (n // world), n // world)
+    if n > 8192:
+        DT = DT * (8192. / n)**2
     p = Plan(vm.default_library(), n, n, rank, world)
 
     def gather(b):
