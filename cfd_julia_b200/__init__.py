@@ -6,7 +6,7 @@ for Julia callers.  Importing the package does not need a GPU; calling into it d
 """
 from . import _build  # noqa: F401
 from .common import (Common, Plan, VmkError, compute_l2norm_bnds, exact_tgv, fps, numerical,  # noqa: F401
-                     numerical_hybrid, numerical_tgv, plan, ps_fft, vm_ic, vm_rhs, write_field)
+                     numerical_hybrid, numerical_ldc, numerical_tgv, plan, ps_fft, vm_ic, vm_rhs, write_field)
 from ._lib import SYMBOLS, VmkLibrary, default_library  # noqa: F401
 
 __version__ = "0.1.0"

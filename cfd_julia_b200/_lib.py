@@ -36,6 +36,7 @@ _PROTOS = {
     "rhs": (C.c_int, [_P, _D, _D, _D, _P, _P, _P, _P]),
     "numerical": (C.c_int, [_P, C.c_int64, _D, _D, _D, _D, _P, _P, C.c_int64, SNAPSHOT_FN, _P]),
     "hybrid_numerical": (C.c_int, [_P, C.c_int64, _D, _D, _D, _D, _P, _P, C.c_int64, SNAPSHOT_FN, _P]),
+    "ldc_numerical": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _D, _D, _D, _D, _P, _P, _P]),
     "upload": (C.c_int, [_P, _P]),
     "step": (C.c_int, [_P, _D, _D, _D, _D, C.c_int64]),
     "download": (C.c_int, [_P, _P, _P]),

@@ -30,7 +30,7 @@ import numpy as np
 
 from ._lib import SNAPSHOT_FN, VmkError, VmkLibrary, default_library
 
-__all__ = ["Common", "fps", "vm_rhs", "numerical", "numerical_tgv", "numerical_hybrid", "ps_fft", "vm_ic", "exact_tgv",
+__all__ = ["Common", "fps", "vm_rhs", "numerical", "numerical_tgv", "numerical_hybrid", "numerical_ldc", "ps_fft", "vm_ic", "exact_tgv",
            "compute_l2norm_bnds", "write_field", "Plan", "VmkError"]
 
 
@@ -195,6 +195,17 @@ class Common:
                                                  ut.ctypes.data, freq if want else 0, cb, None))
         return ut
 
+    # ---- 18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl:59-117 -----------------------------------
+    def numerical_ldc(self, nx, ny, nt, dx, dy, dt, re, wn, sn, rms):
+        """The lid-driven cavity script's `numerical`: same arguments, wn and sn ((nx+1) x (ny+1) node arrays) and
+        rms[0:nt] are mutated in place, nothing is returned."""
+        p = self.plan(2 * nx, 2 * ny)  # the sine transform runs as a periodic transform of the odd extension
+        if not isinstance(rms, np.ndarray) or rms.dtype != np.float64 or rms.size < nt or not rms.flags.c_contiguous:
+            raise IndexError("rms: expected a contiguous float64 array of at least nt elements")  # Julia: BoundsError
+        self.lib.check(self.lib.ldc_numerical(p.handle, nx, ny, int(nt), dx, dy, dt, re,
+                                              _ptr(wn, (nx + 1, ny + 1), "wn"), _ptr(sn, (nx + 1, ny + 1), "sn"),
+                                              rms.ctypes.data))
+
     def _numerical(self, nx, ny, nt, dx, dy, dt, re, wn, freq, x, y, snapshot, outdir):
         p = self.plan(nx, ny)
         g = (nx + 2, ny + 2)
@@ -275,6 +286,10 @@ def numerical_tgv(nx, ny, nt, dx, dy, dt, re, wn):
 
 def numerical_hybrid(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
     return _common.numerical_hybrid(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot, outdir)
+
+
+def numerical_ldc(nx, ny, nt, dx, dy, dt, re, wn, sn, rms):
+    return _common.numerical_ldc(nx, ny, nt, dx, dy, dt, re, wn, sn, rms)
 
 
 def plan(nx, ny) -> Plan:

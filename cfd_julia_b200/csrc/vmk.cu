@@ -22,6 +22,7 @@
 #define vmk_rhs vmke_rhs
 #define vmk_numerical vmke_numerical
 #define vmk_hybrid_numerical vmke_hybrid_numerical
+#define vmk_ldc_numerical vmke_ldc_numerical
 #define vmk_upload vmke_upload
 #define vmk_step vmke_step
 #define vmk_download vmke_download
@@ -47,6 +48,7 @@
 #include <vector>
 
 #include "vmk_backend.cuh"
+#include "vmk_cavity.cuh"
 #include "vmk_cluster.cuh"
 #include "vmk_hybrid.cuh"
 #include "vmk_kernels.cuh"
@@ -104,6 +106,25 @@ struct KHBody {
 template <int MODE>
 struct K4Body {
   VMK_HD static void run(const Ctx& c, const K4Args& a) { k4_body<MODE>(c, a); }
+};
+template <int MODE>
+struct KCStage {
+  VMK_HD static void run(const Ctx& c, const KCArgs& a) { kc_stage_body<MODE>(c, a); }
+};
+struct KCBc2 {
+  VMK_HD static void run(const Ctx& c, const KCArgs& a) { kc_bc2_body(c, a); }
+};
+struct KCExtend {
+  VMK_HD static void run(const Ctx& c, const KCArgs& a) { kc_extend_body(c, a); }
+};
+struct KCExtract {
+  VMK_HD static void run(const Ctx& c, const KCArgs& a) { kc_extract_body(c, a); }
+};
+struct KCRmsPartial {
+  VMK_HD static void run(const Ctx& c, const KCArgs& a) { kc_rms_partial_body(c, a); }
+};
+struct KCRmsFinal {
+  VMK_HD static void run(const Ctx& c, const KCArgs& a) { kc_rms_final_body(c, a); }
 };
 struct K6Push {
   VMK_HD static void run(const Ctx& c, const K6Args& a) { k6_push_body(c, a); }
@@ -325,6 +346,12 @@ struct vmk_plan {
   double* hksqperm = nullptr;
   double hyb_dx = 0;
   int res_kh = 0;
+  // lid-driven cavity (vmk_ldc_numerical), allocated on first use: node arrays (n+1)^2 with n = N/2
+  double* cw[3] = {nullptr, nullptr, nullptr};  // wn, wtA, wtB
+  double* cs = nullptr;                         // sn
+  double* csp = nullptr;                        // sp (previous step's sn)
+  double* cpart = nullptr;                      // partial sums of the rms reduction
+  int div_kind = 0;                             // 0: fps divisor (Common.jl:101-121), 1: cavity (lid_driven_cavity.jl:66-71)
   int64_t dev_bytes = 0;
   // peers (slab decomposition): pointers to every rank's buffers, own entries included
   double* peer_w[3][kMaxPeers];
@@ -386,7 +413,8 @@ int ensure_staging(vmk_plan* p) {
 // bb*cos(kx[i]) and cc*cos(ky[j]) exactly as Common.jl:101-113,120 evaluates them (kx[1] = eps, ky = kx).
 // 2N cos() evaluations on the host per (dx,dy,eps); the 2 N^2 per call of the reference disappear.
 int ensure_divisor(vmk_plan* p, double dx, double dy, double eps) {
-  if (p->div_valid && p->div_dx == dx && p->div_dy == dy && p->div_eps == eps) return 0;
+  if (p->div_valid && p->div_kind == 0 && p->div_dx == dx && p->div_dy == dy && p->div_eps == eps) return 0;
+  p->div_kind = 0;
   const int n = p->N;
   std::vector<double> kx(n), b(n), c(n);
   const double hx = 2.0 * M_PI / (double)n;  // Common.jl:106
@@ -760,6 +788,61 @@ int enqueue_step(vmk_plan* p, const StepParams& sp) {
   return 0;
 }
 
+// ---- lid-driven cavity (18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl) ----------------------------------------------
+// Divisor of fps_sine on the odd extension (plan size N = 2 nx): mode k of the 2nx-periodic grid is the DST frequency
+// pi k / nx, so d(k, l) = (2/dx^2)(cos(pi k/nx) - 1) + (2/dy^2)(cos(pi l/ny) - 1) exactly as lid_driven_cavity.jl:66-71
+// writes it (the two bracketed terms are tabulated and added: no aa + bb cos cancellation for the low modes).
+int ensure_divisor_cavity(vmk_plan* p, double dx, double dy) {
+  if (p->div_valid && p->div_kind == 1 && p->div_dx == dx && p->div_dy == dy) return 0;
+  const int N = p->N, n = N / 2;
+  std::vector<double> b(N), c(N), cp(N);
+  for (int k = 0; k < N; k++) {
+    const int km = k <= n ? k : N - k;  // cos is even about k = n: evaluate the mirror index, bitwise symmetric tables
+    const double ck = cos(M_PI * (double)km / (double)n) - 1.;
+    b[k] = (2. / (dx * dx)) * ck;
+    c[k] = (2. / (dy * dy)) * ck;
+  }
+  p->ops.fill_ccperm(c.data(), cp.data());
+  VMK_TRY(be_sync(p->st));
+  VMK_TRY(be_h2d(p->bbcos, b.data(), sizeof(double) * N, p->st));
+  VMK_TRY(be_h2d(p->cccos, c.data(), sizeof(double) * N, p->st));
+  VMK_TRY(be_h2d(p->ccperm, cp.data(), sizeof(double) * N, p->st));
+  VMK_TRY(be_sync(p->st));
+  p->div_aa = 0.0;
+  p->div_dx = dx;
+  p->div_dy = dy;
+  p->div_eps = 0.0;
+  p->div_kind = 1;
+  p->div_valid = true;
+  drop_graphs(p);
+  return 0;
+}
+
+template <class Body>
+int launch_kc(vmk_plan* p, const KCArgs& a, size_t items, size_t smem = 0, int grid_override = 0) {
+  size_t want = (items + kKCThreads - 1) / kKCThreads;
+  const size_t cap = (size_t)p->sms * 16;
+  int grid = (int)(want < cap ? want : cap);
+  if (grid < 1) grid = 1;
+  if (grid_override) grid = grid_override;
+  VMK_TRY((be_launch<Body, KCArgs, kKCThreads, 4>(grid, smem, a, p->st)));
+  p->launches++;
+  return 0;
+}
+
+// sn[2:nx, 2:ny] = fps_sine(-w)  (lid_driven_cavity.jl:87,100,113): odd extension -> periodic solve -> interior
+int cavity_poisson(vmk_plan* p, KCArgs a, const double* w) {
+  const size_t N = (size_t)p->N, m = N / 2 - 1;
+  a.w = w;
+  a.slab = p->w[1];
+  VMK_TRY(launch_kc<KCExtend>(p, a, N * N));
+  VMK_TRY(enqueue_poisson(p, p->w[1], -1.0));
+  a.slab = p->psi;
+  a.out = p->cs;
+  VMK_TRY(launch_kc<KCExtract>(p, a, m * m));
+  return 0;
+}
+
 // ---- hybrid RK3 / Crank-Nicolson solver (20_NS2D_Hybrid_Solver/hybrid.jl) -------------------------------------------
 int ensure_hybrid(vmk_plan* p, double dx) {
   if (p->nranks != 1) return fail(VMK_EARG, "the hybrid solver runs on single-GPU plans");
@@ -1013,6 +1096,10 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_free(p->hVs);
   be_free(p->hksq);
   be_free(p->hksqperm);
+  for (int b = 0; b < 3; b++) be_free(p->cw[b]);
+  be_free(p->cs);
+  be_free(p->csp);
+  be_free(p->cpart);
   be_event_destroy(p->ev0);
   be_event_destroy(p->ev1);
   be_event_destroy(p->ev_join);
@@ -1258,6 +1345,83 @@ int vmk_hybrid_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double d
   if (snap && freq > 0 && nt > 0 && nt % freq == 0) snap(nt, ut, user);
   p->uploaded = false;  // w[0..2] were used as scratch
   return VMK_OK;
+}
+
+int vmk_ldc_numerical(vmk_plan* p, int64_t nx, int64_t ny, int64_t nt, double dx, double dy, double dt, double re,
+                      double* wn, double* sn, double* rms) {
+  VMK_TRY(check_plan(p));
+  if (!wn || !sn || (nt > 0 && !rms)) return fail(VMK_EARG, "wn, sn or rms is NULL");
+  if (nt < 0) return fail(VMK_EARG, "nt < 0");
+  if (p->nranks != 1) return fail(VMK_EARG, "the cavity solver runs on single-GPU plans");
+  if (nx != ny || 2 * nx != p->N || nx < 16)
+    return fail(VMK_ESIZE, "cavity of nx x ny cells needs nx == ny >= 16 and a plan of size 2nx x 2ny (odd extension)");
+  const size_t n = (size_t)nx, nodes = (n + 1) * (n + 1), nb = sizeof(double) * nodes;
+  const int nparts = p->sms * 4;
+  if (!p->cs) {
+    for (int b = 0; b < 3; b++) VMK_TRY(dev_alloc(p, (void**)&p->cw[b], nb));
+    VMK_TRY(dev_alloc(p, (void**)&p->cs, nb));
+    VMK_TRY(dev_alloc(p, (void**)&p->csp, nb));
+    VMK_TRY(dev_alloc(p, (void**)&p->cpart, sizeof(double) * (size_t)nparts));
+  }
+  double* rms_dev = nullptr;
+  if (nt > 0) VMK_TRY(be_malloc((void**)&rms_dev, sizeof(double) * (size_t)nt));
+  int rc = 0;
+  do {
+    if ((rc = ensure_divisor_cavity(p, dx, dy))) break;
+    if ((rc = be_h2d(p->cw[0], wn, nb, p->st)) || (rc = be_h2d(p->cs, sn, nb, p->st))) break;
+    // the wall values of the stage arrays are written by bc2 before they are read; start them from wn anyway
+    if ((rc = be_d2d(p->cw[1], p->cw[0], nb, p->st)) || (rc = be_d2d(p->cw[2], p->cw[0], nb, p->st))) break;
+    KCArgs a{};
+    a.n = (int)nx;
+    a.s = p->cs;
+    a.aa = 1.0 / (re * (dx * dx));  // lid_driven_cavity.jl:125-128
+    a.bb = 1.0 / (re * (dy * dy));
+    a.gg = 1.0 / (4.0 * dx * dy);
+    a.hh = 1.0 / 3.0;
+    a.dt = dt;
+    a.dx2 = dx * dx;
+    a.dy2 = dy * dy;
+    a.lid = 3.0 / dy;
+    a.count = (double)nodes;
+    a.part = p->cpart;
+    a.nparts = nparts;
+    const size_t m2 = (n - 1) * (n - 1);
+    VMK_TRY(be_event_record(p->ev0, p->st));
+    for (int64_t k = 0; k < nt && !rc; k++) {
+      if ((rc = be_d2d(p->csp, p->cs, nb, p->st))) break;  // sp = sn, :77
+      // stage 1: wtA = wn + dt r(wn, sn); bc2; sn = fps_sine(-wtA)          :80-87
+      a.w = p->cw[0], a.wn = p->cw[0], a.out = p->cw[1];
+      if ((rc = launch_kc<KCStage<1>>(p, a, m2))) break;
+      if ((rc = launch_kc<KCBc2>(p, a, 4 * (n + 1)))) break;
+      if ((rc = cavity_poisson(p, a, p->cw[1]))) break;
+      // stage 2: wtB = .75 wn + .25 wtA + .25 dt r(wtA, sn)                   :90-100
+      a.w = p->cw[1], a.wn = p->cw[0], a.out = p->cw[2];
+      if ((rc = launch_kc<KCStage<2>>(p, a, m2))) break;
+      if ((rc = launch_kc<KCBc2>(p, a, 4 * (n + 1)))) break;
+      if ((rc = cavity_poisson(p, a, p->cw[2]))) break;
+      // stage 3: wn = (1/3) wn + (2/3) wtB + (2/3) dt r(wtB, sn)              :103-113
+      a.w = p->cw[2], a.wn = p->cw[0], a.out = p->cw[0];
+      if ((rc = launch_kc<KCStage<3>>(p, a, m2))) break;
+      if ((rc = launch_kc<KCBc2>(p, a, 4 * (n + 1)))) break;
+      if ((rc = cavity_poisson(p, a, p->cw[0]))) break;
+      // rms[k] = sqrt(sum((sn - sp)^2) / ((nx+1)(ny+1)))                      :111-113
+      a.w = p->csp, a.rms = rms_dev + k;
+      if ((rc = launch_kc<KCRmsPartial>(p, a, nodes, sizeof(double) * kKCThreads, nparts))) break;
+      if ((rc = launch_kc<KCRmsFinal>(p, a, 1, 0, 1))) break;
+    }
+    if (rc) break;
+    if ((rc = be_event_record(p->ev1, p->st))) break;
+    p->ev_valid = true;
+    if ((rc = be_d2h(wn, p->cw[0], nb, p->st)) || (rc = be_d2h(sn, p->cs, nb, p->st))) break;
+    if (nt > 0 && (rc = be_d2h(rms, rms_dev, sizeof(double) * (size_t)nt, p->st))) break;
+    rc = be_sync(p->st);
+  } while (0);
+  if (rms_dev) {
+    be_sync(p->st);
+    be_free(rms_dev);
+  }
+  p->uploaded = false;  // w[1], psi were used as scratch
+  return rc;
 }
 
 // ---- measurement -----------------------------------------------------------------------------------

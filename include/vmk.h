@@ -100,6 +100,15 @@ int vmk_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, d
 int vmk_hybrid_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
                          double* ut, int64_t freq, vmk_snapshot_fn snap, void* user);
 
+/* numerical(nx,ny,nt,dx,dy,dt,re,wn,sn,rms)  18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl:59-117 -- lid-driven cavity:
+ * RK3, the Arakawa/Laplacian rhs without periodic wrap (:123-158), Jensen wall vorticity bc2 (:38-52) and the sine-
+ * transform Poisson solve fps_sine (:11-21, FFTW RODFT00).  wn, sn: (nx+1) x (ny+1) node arrays, both mutated in place
+ * (sn's wall nodes are never written, as in the reference); rms[0..nt-1] receives the per-step change of sn (:111-113).
+ * `plan` must have size 2nx x 2ny: the DST is evaluated as the periodic transform of the odd extension with the
+ * kernels of the vortex-merger path.  nx == ny, a power of two in [16, 16384]; single-GPU plans. */
+int vmk_ldc_numerical(vmk_plan* plan, int64_t nx, int64_t ny, int64_t nt, double dx, double dy, double dt, double re,
+                      double* wn, double* sn, double* rms);
+
 /* ---- device-resident path (what numerical() is built from) ------------------------------------------- */
 int vmk_upload(vmk_plan* plan, const double* wn_ghosted);
 int vmk_step(vmk_plan* plan, double dx, double dy, double dt, double re, int64_t nsteps); /* asynchronous */

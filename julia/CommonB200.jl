@@ -137,6 +137,19 @@ numerical_hybrid(nx, ny, nt, Δx, Δy, Δt, re, x, y, wn::Matrix{Float64}, ns) =
   return ut
 end
 
+# lid_driven_cavity.jl flavour (18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl:59-117): same arguments, wn, sn
+# ((nx+1) x (ny+1) node arrays) and rms are mutated in place.  The plan has size 2nx x 2ny (sine transform = periodic
+# transform of the odd extension).
+numerical_ldc(nx, ny, nt, Δx, Δy, Δt, re, wn::Matrix{Float64}, sn::Matrix{Float64}, rms::Vector{Float64}) = begin
+  size(wn) == (nx + 1, ny + 1) || throw(BoundsError(wn, (nx + 1, ny + 1)))
+  size(sn) == (nx + 1, ny + 1) || throw(BoundsError(sn, (nx + 1, ny + 1)))
+  length(rms) >= nt || throw(BoundsError(rms, nt))
+  check(ccall((:vmk_ldc_numerical, libvmk), Cint,
+              (Ptr{Cvoid}, Int64, Int64, Int64, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+              vmk_plan(2nx, 2ny).handle, nx, ny, nt, Δx, Δy, Δt, re, wn, sn, rms))
+  return
+end
+
 # ---- several GPUs driven by this one Julia process (slab decomposition along j) ---------------------------------------
 # plans = vmk_plans_multi(nx, ny, ngpu); numerical_multi(plans, nt, Δx, Δy, Δt, re, wn) steps all ranks concurrently
 # (vmk_step is asynchronous) and gathers every rank's rows back into wn.

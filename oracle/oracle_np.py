@@ -252,3 +252,69 @@ def hybrid_numerical(nx, ny, nt, dx, dy, dt, re, wn, freq=0, snapshot=None):
         if snapshot is not None and freq > 0 and k % freq == 0:
             snapshot(k, field(wnf))
     return field(wnf)
+
+
+# ---- 18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl ----------------------------------------------
+# Arrays are (nx+1) x (ny+1) node arrays, no ghost cells; index [i, j] here = Julia [i+1, j+1].
+def ldc_rhs(nx, ny, dx, dy, re, w, s, r):
+    """lid_driven_cavity.jl:123-158: r[2:nx, 2:ny] = -J(w, s) (Arakawa) + (1/re) lap(w)."""
+    aa = 1 / (re * dx**2)
+    bb = 1 / (re * dy**2)
+    gg = 1 / (4 * dx * dy)
+    hh = 1 / 3
+    c = slice(1, nx)
+    p = slice(2, nx + 1)
+    m = slice(0, nx - 1)
+    j1 = gg * ((w[p, c] - w[m, c]) * (s[c, p] - s[c, m]) - (w[c, p] - w[c, m]) * (s[p, c] - s[m, c]))
+    j2 = gg * (w[p, c] * (s[p, p] - s[p, m]) - w[m, c] * (s[m, p] - s[m, m]) -
+               w[c, p] * (s[p, p] - s[m, p]) + w[c, m] * (s[p, m] - s[m, m]))
+    j3 = gg * (w[p, p] * (s[c, p] - s[p, c]) - w[m, m] * (s[m, c] - s[c, m]) -
+               w[m, p] * (s[c, p] - s[m, c]) + w[p, m] * (s[p, c] - s[c, m]))
+    jac = (j1 + j2 + j3) * hh
+    r[c, c] = -jac + (aa * (w[p, c] - 2 * w[c, c] + w[m, c]) + bb * (w[c, p] - 2 * w[c, c] + w[c, m]))
+
+
+def ldc_bc2(nx, ny, dx, dy, w, s):
+    """lid_driven_cavity.jl:38-52 (Jensen): left/right walls for every j, then bottom/top (lid: -3/dy) for every i."""
+    w[0, :] = (-4 * s[1, :] + .5 * s[2, :]) / dx**2
+    w[nx, :] = (-4 * s[nx - 1, :] + .5 * s[nx - 2, :]) / dx**2
+    w[:, 0] = (-4 * s[:, 1] + .5 * s[:, 2]) / dy**2
+    w[:, ny] = (-4 * s[:, ny - 1] + .5 * s[:, ny - 2]) / dy**2 - 3. / dy
+
+
+def ldc_iden(nx, ny, dx, dy):
+    """lid_driven_cavity.jl:66-71: iden[i,j] = 1/((2/dx^2)(cos(pi i/nx) - 1) + (2/dy^2)(cos(pi j/ny) - 1)), i, j from 1."""
+    i = np.arange(1, nx + 2)
+    j = np.arange(1, ny + 2)
+    return 1. / ((2 / dx**2) * (np.cos(np.pi * i / nx) - 1.)[:, None] + (2 / dy**2) * (np.cos(np.pi * j / ny) - 1.)[None, :])
+
+
+def ldc_fps_sine(nx, ny, f, iden, sn):
+    """lid_driven_cavity.jl:11-21: sn[2:nx, 2:ny] = RODFT00(RODFT00(f[2:nx, 2:ny]) * iden) / ((2nx)(2ny)).
+    FFTW's RODFT00 is scipy's unnormalised DST-I."""
+    from scipy.fft import dstn
+    e = dstn(f[1:nx, 1:ny], type=1)
+    sn[1:nx, 1:ny] = dstn(e * iden[:nx - 1, :ny - 1], type=1) / ((2 * nx) * (2 * ny))
+
+
+def ldc_numerical(nx, ny, nt, dx, dy, dt, re, wn, sn, rms):
+    """lid_driven_cavity.jl:59-117: RK3 steps; mutates wn, sn (node arrays) and rms[0:nt]."""
+    wt = np.zeros_like(wn)
+    r = np.zeros_like(wn)
+    iden = ldc_iden(nx, ny, dx, dy)
+    c = slice(1, nx)
+    for k in range(nt):
+        sp = sn.copy()
+        ldc_rhs(nx, ny, dx, dy, re, wn, sn, r)
+        wt[c, c] = wn[c, c] + dt * r[c, c]
+        ldc_bc2(nx, ny, dx, dy, wt, sn)
+        ldc_fps_sine(nx, ny, -wt, iden, sn)
+        ldc_rhs(nx, ny, dx, dy, re, wt, sn, r)
+        wt[c, c] = .75 * wn[c, c] + .25 * wt[c, c] + .25 * dt * r[c, c]
+        ldc_bc2(nx, ny, dx, dy, wt, sn)
+        ldc_fps_sine(nx, ny, -wt, iden, sn)
+        ldc_rhs(nx, ny, dx, dy, re, wt, sn, r)
+        wn[c, c] = (1 / 3) * wn[c, c] + (2 / 3) * wt[c, c] + (2 / 3) * dt * r[c, c]
+        ldc_bc2(nx, ny, dx, dy, wn, sn)
+        ldc_fps_sine(nx, ny, -wn, iden, sn)
+        rms[k] = np.sqrt(np.sum((sn - sp)**2) / ((nx + 1) * (ny + 1)))

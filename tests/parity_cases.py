@@ -163,3 +163,25 @@ def check_hybrid(cm, onp, n, nt, dt=None, re=1000., ns=1, tol=TOL_RUN):
     for (_, a), (_, b) in zip(snaps, snaps_ref):
         assert rel_l2(a, b) < tol
     return ut
+
+
+def check_ldc(cm, onp, n, nt, dt=None, re=100., from_rest=False, tol=TOL_RUN):
+    """18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl `numerical` against the numpy/scipy restatement
+    (oracle_np.ldc_numerical).  from_rest: the script's own initial condition (wn = sn = 0, the lid drives the flow);
+    otherwise a noisy start that exercises every sine mode and all wall formulas."""
+    dx = 1. / n
+    dt = min(.001, 0.2 * dx * dx * re) if dt is None else dt
+    wn = np.zeros((n + 1, n + 1), order="F")
+    sn = np.zeros((n + 1, n + 1), order="F")
+    if not from_rest:
+        rng = np.random.default_rng(n)
+        wn[...] = rng.uniform(-1, 1, (n + 1, n + 1))
+        sn[1:n, 1:n] = 1e-2 * rng.uniform(-1, 1, (n - 1, n - 1))
+    w2, s2 = wn.copy(order="F"), sn.copy(order="F")
+    rms, rms2 = np.zeros(nt), np.zeros(nt)
+    onp.ldc_numerical(n, n, nt, dx, dx, dt, re, w2, s2, rms2)
+    assert cm.numerical_ldc(n, n, nt, dx, dx, dt, re, wn, sn, rms) is None  # mutates wn, sn, rms like the reference
+    assert rel_l2(wn, w2) < tol and rel_l2(sn, s2) < tol
+    assert np.all(sn[0, :] == 0) and np.all(sn[n, :] == 0) and np.all(sn[:, 0] == 0) and np.all(sn[:, n] == 0)
+    assert np.max(np.abs(rms / rms2 - 1.)) < 1e-8
+    return wn, sn, rms

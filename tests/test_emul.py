@@ -106,6 +106,33 @@ def test_hybrid_solver_errors(emul):
     p.close()
 
 
+@pytest.mark.parametrize("n,nt", [(16, 4), (32, 3), (64, 3), (128, 2), (256, 1)])
+def test_lid_driven_cavity(emul, oracle_np, n, nt):
+    """lid_driven_cavity.jl (sine-transform Poisson solve as the periodic solve of the odd extension)"""
+    pc.check_ldc(emul, oracle_np, n, nt)
+    emul.clear_plans()
+
+
+def test_lid_driven_cavity_from_rest(emul, oracle_np):
+    wn, sn, rms = pc.check_ldc(emul, oracle_np, 32, 20, dt=.001, from_rest=True)
+    assert sn.min() < 0 and rms[0] > rms[-1] > 0  # the primary vortex spins up, the change per step decays
+
+
+def test_lid_driven_cavity_errors(emul):
+    from cfd_julia_b200.common import Plan, VmkError
+    import ctypes as C
+    n = 32
+    w = np.zeros((n + 1, n + 1), order="F")
+    rms = np.zeros(2)
+    p = emul.plan(n, n)  # wrong plan size: the cavity needs 2n x 2n
+    assert emul.lib.ldc_numerical(p.handle, n, n, 1, 1. / n, 1. / n, 1e-3, 100., w.ctypes.data, w.ctypes.data,
+                                  rms.ctypes.data) == 1
+    with pytest.raises(IndexError):
+        emul.numerical_ldc(n, n, 5, 1. / n, 1. / n, 1e-3, 100., w, w.copy(order="F"), rms)
+    with pytest.raises(IndexError):
+        emul.numerical_ldc(n, n, 1, 1. / n, 1. / n, 1e-3, 100., np.zeros((n, n), order="F"), w, rms)
+
+
 def test_golden(emul):
     pc.check_golden(emul)
 

@@ -49,6 +49,12 @@ def test_cluster_slab_decomposition(emul_cl, oracle_c, n, nranks):
     _slab_run(emul_cl, oracle_c, n, nranks)
 
 
+def test_cluster_lid_driven_cavity(emul_cl, oracle_np):
+    """the cavity solver on top of the cluster kernels (production: nx = 8192 -> 16384-point transforms)"""
+    pc.check_ldc(emul_cl, oracle_np, 64, 2)
+    emul_cl.clear_plans()
+
+
 def test_cluster_v_layouts_agree(emul_cl):
     n = 256
     dx, dy, _, _ = grid(n)

@@ -125,6 +125,20 @@ def test_hybrid_8192_properties(gpu):
     gpu.clear_plans()
 
 
+@pytest.mark.parametrize("n,nt", [(16, 20), (64, 20), (256, 10), (1024, 5), (4096, 2)])
+def test_lid_driven_cavity(gpu, oracle_np, n, nt):
+    """18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl against the numpy/scipy oracle"""
+    pc.check_ldc(gpu, oracle_np, n, nt)
+    if n >= 1024:
+        gpu.clear_plans()
+
+
+def test_lid_driven_cavity_script_config(gpu, oracle_np):
+    """the script's own configuration (64^2, dt = .001, Re = 100, from rest), first 300 of its 10 000 steps"""
+    wn, sn, rms = pc.check_ldc(gpu, oracle_np, 64, 300, dt=.001, from_rest=True)
+    assert sn.min() < -0.04 and rms[0] > rms[-1] > 0
+
+
 def test_golden(gpu):
     pc.check_golden(gpu)
 
