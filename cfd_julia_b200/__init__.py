@@ -5,8 +5,9 @@ The product is cfd_julia_b200/libvmk.so (hand-written CUDA kernels behind the C 
 for Julia callers.  Importing the package does not need a GPU; calling into it does.
 """
 from . import _build  # noqa: F401
-from .common import (Common, Plan, VmkError, compute_l2norm_bnds, exact_tgv, fps, numerical,  # noqa: F401
-                     numerical_hybrid, numerical_ldc, numerical_tgv, plan, ps_fft, vm_ic, vm_rhs, write_field)
+from .common import (Common, Plan, VmkError, compute_l2norm_bnds, exact_tgv, fps, julia_float_str,  # noqa: F401
+                     numerical, numerical_hybrid, numerical_ldc, numerical_ps23, numerical_tgv, plan, ps_fft,
+                     read_field, vm_ic, vm_rhs, write_field)
 from ._lib import SYMBOLS, VmkLibrary, default_library  # noqa: F401
 
 __version__ = "0.1.0"

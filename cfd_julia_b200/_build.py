@@ -37,7 +37,7 @@ def _nvcc() -> str:
 
 
 def sources():
-    return [SRC] + sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [os.path.join(ROOT, "include", "vmk.h")]
+    return [SRC] + sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "csrc", "*.hpp"))) + [os.path.join(ROOT, "include", "vmk.h")]
 
 
 def stale() -> bool:

@@ -24,14 +24,15 @@ m is never incremented (hybrid.jl:81 does increment it); numerical() here number
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 
 import numpy as np
 
 from ._lib import SNAPSHOT_FN, VmkError, VmkLibrary, default_library
 
-__all__ = ["Common", "fps", "vm_rhs", "numerical", "numerical_tgv", "numerical_hybrid", "numerical_ldc", "ps_fft", "vm_ic", "exact_tgv",
-           "compute_l2norm_bnds", "write_field", "Plan", "VmkError"]
+__all__ = ["Common", "fps", "vm_rhs", "numerical", "numerical_tgv", "numerical_hybrid", "numerical_ps23", "numerical_ldc", "ps_fft", "vm_ic", "exact_tgv",
+           "compute_l2norm_bnds", "write_field", "read_field", "julia_float_str", "Plan", "VmkError"]
 
 
 def _ptr(a: np.ndarray, shape, what: str):
@@ -175,6 +176,18 @@ class Common:
         """The hybrid RK3 / Crank-Nicolson solver's `numerical`: same arguments as vm.jl's, wn is only read, returns
         ut = real(ifft(wf)) as an (nx+1) x (ny+1) array.  snapshot(k, ut) / the text files vm{m}.txt every nt // ns
         steps (hybrid.jl:71-86; this script does increment its record index)."""
+        return self._numerical_spectral(self.lib.hybrid_numerical, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot,
+                                        outdir)
+
+    # ---- 22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl:13-89 ---------------------------
+    def numerical_ps23(self, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
+        """The pseudo-spectral solver's `numerical` (2/3 truncation rule): same arguments as vm.jl's, wn is only read,
+        returns ut = real(ifft(wf)) as an (nx+1) x (ny+1) array; snapshot(k, ut) / vm{m}.txt every nt // ns steps
+        (pseudospectral_23_rule.jl:69-86)."""
+        return self._numerical_spectral(self.lib.ps23_numerical, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot,
+                                        outdir)
+
+    def _numerical_spectral(self, entry, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot, outdir):
         if ns <= 0 or nt // ns == 0:
             raise ZeroDivisionError("mod(k, nt ÷ ns) with nt ÷ ns == 0")  # Julia: DivideError at hybrid.jl:71
         freq = nt // ns
@@ -187,12 +200,12 @@ class Common:
             if snapshot is not None:
                 snapshot(int(k), ut)
             if outdir is not None:
-                write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut)
+                write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut, lib=self.lib)
 
         want = snapshot is not None or outdir is not None
         cb = SNAPSHOT_FN(_snap) if want else SNAPSHOT_FN()
-        self.lib.check(self.lib.hybrid_numerical(p.handle, int(nt), dx, dy, dt, re, _ptr(wn, (nx + 2, ny + 2), "wn"),
-                                                 ut.ctypes.data, freq if want else 0, cb, None))
+        self.lib.check(entry(p.handle, int(nt), dx, dy, dt, re, _ptr(wn, (nx + 2, ny + 2), "wn"), ut.ctypes.data,
+                             freq if want else 0, cb, None))
         return ut
 
     # ---- 18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl:59-117 -----------------------------------
@@ -218,7 +231,7 @@ class Common:
             if snapshot is not None:
                 snapshot(int(k), ut)
             if outdir is not None:
-                write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut)
+                write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut, lib=self.lib)
 
         want = freq > 0 and (snapshot is not None or outdir is not None)
         cb = SNAPSHOT_FN(_snap) if want else SNAPSHOT_FN()
@@ -227,13 +240,42 @@ class Common:
         return out
 
 
-def write_field(path, x, y, ut):
-    """The reference's text dump "x y w" with j outer, i inner (vm.jl:81-85, 132-136, 142-146)."""
+def write_field(path, x, y, ut, lib=None):
+    """The reference's text dump "x y w" with j outer, i inner (vm.jl:81-85, 132-136, 142-146), written by the
+    library's native writer (csrc/vmk_io.hpp) with Julia's own Float64 formatting, so the files are byte-identical to
+    what the scripts write for the same values."""
+    lib = lib or default_library()
+    ut = np.asarray(ut)
     nx1, ny1 = ut.shape
-    with open(path, "w") as io:
-        for j in range(ny1):
-            for i in range(nx1):
-                io.write(f"{float(x[i])!r} {float(y[j])!r} {float(ut[i, j])!r}\n")
+    xa = np.ascontiguousarray(np.asarray(x, dtype=np.float64)[:nx1])
+    ya = np.ascontiguousarray(np.asarray(y, dtype=np.float64)[:ny1])
+    ua = np.asfortranarray(ut, dtype=np.float64)
+    if xa.size != nx1 or ya.size != ny1:
+        raise IndexError("write_field: x / y shorter than the field")  # Julia: BoundsError
+    lib.check(lib.write_field(os.fsencode(path), xa.ctypes.data, ya.ctypes.data, ua.ctypes.data, nx1, ny1))
+
+
+def read_field(path, nx, ny, lib=None):
+    """plotting.jl:14-28: readdlm + reshape.  Returns (x[0:nx+1], y[0:ny+1], w (nx+1) x (ny+1))."""
+    lib = lib or default_library()
+    n = (nx + 1) * (ny + 1)
+    cols = [np.zeros(n) for _ in range(3)]
+    rows = C.c_int64(0)
+    lib.check(lib.read_field(os.fsencode(path), cols[0].ctypes.data, cols[1].ctypes.data, cols[2].ctypes.data, n,
+                             C.byref(rows)))
+    if rows.value != n:
+        raise ValueError(f"{path}: {rows.value} rows, expected {(nx + 1)}*{(ny + 1)}")  # Julia: DimensionMismatch in reshape
+    xx = cols[0][:nx + 1].copy()
+    yy = cols[1].reshape((nx + 1, ny + 1), order="F")[0, :].copy()
+    return xx, yy, cols[2].reshape((nx + 1, ny + 1), order="F")
+
+
+def julia_float_str(v, lib=None) -> str:
+    """Julia's print(::Float64) (what "$(x)" interpolates), from the library's formatter."""
+    lib = lib or default_library()
+    buf = C.create_string_buffer(40)
+    n = lib.print_float64(float(v), buf)
+    return buf.raw[:n].decode()
 
 
 # ---- setup helpers of the callers (host-side, not on the hot path) ----------------------------------
@@ -286,6 +328,10 @@ def numerical_tgv(nx, ny, nt, dx, dy, dt, re, wn):
 
 def numerical_hybrid(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
     return _common.numerical_hybrid(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot, outdir)
+
+
+def numerical_ps23(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
+    return _common.numerical_ps23(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot, outdir)
 
 
 def numerical_ldc(nx, ny, nt, dx, dy, dt, re, wn, sn, rms):

@@ -22,6 +22,10 @@
 #define vmk_rhs vmke_rhs
 #define vmk_numerical vmke_numerical
 #define vmk_hybrid_numerical vmke_hybrid_numerical
+#define vmk_ps23_numerical vmke_ps23_numerical
+#define vmk_print_float64 vmke_print_float64
+#define vmk_write_field vmke_write_field
+#define vmk_read_field vmke_read_field
 #define vmk_ldc_numerical vmke_ldc_numerical
 #define vmk_upload vmke_upload
 #define vmk_step vmke_step
@@ -51,7 +55,9 @@
 #include "vmk_cavity.cuh"
 #include "vmk_cluster.cuh"
 #include "vmk_hybrid.cuh"
+#include "vmk_io.hpp"
 #include "vmk_kernels.cuh"
+#include "vmk_pseudo.cuh"
 
 using namespace vmk;
 
@@ -85,6 +91,9 @@ struct SizeOps {
   int (*kh_configure)(int* res);
   int (*kh)(int grid, const KHArgs&, Stream&);
   void (*fill_ksqperm)(const double* ksq, double* out);
+  // pseudo-spectral solver, 2/3 rule (vmk_pseudo.cuh); null where kh is
+  int (*kp_configure)(int* res);
+  int (*kp)(int grid, const KPArgs&, Stream&);
 };
 
 template <class C>
@@ -102,6 +111,13 @@ struct K3Body {
 template <class C>
 struct KHBody {
   VMK_HD static void run(const Ctx& c, const KHArgs& a) { kh_body<C>(c, a); }
+};
+template <class C>
+struct KPBody {
+  VMK_HD static void run(const Ctx& c, const KPArgs& a) { kp_body<C>(c, a); }
+};
+struct KPProduct {
+  VMK_HD static void run(const Ctx& c, const KPProdArgs& a) { kp_product_body(c, a); }
 };
 template <int MODE>
 struct K4Body {
@@ -237,6 +253,8 @@ SizeOps make_cluster_ops() {
   o.kh_configure = nullptr;
   o.kh = nullptr;
   o.fill_ksqperm = nullptr;
+  o.kp_configure = nullptr;
+  o.kp = nullptr;
   return o;
 }
 
@@ -273,10 +291,16 @@ SizeOps make_ops() {
   if constexpr (C::SPLIT) {  // (measurement / test configurations with the split exchange buffer)
     o.kh_configure = nullptr;
     o.kh = nullptr;
+    o.kp_configure = nullptr;
+    o.kp = nullptr;
   } else {
     o.kh_configure = [](int* r) -> int { return be_configure<KHBody<C>, KHArgs, C::CT, C::MINB>(C::SMEM_BYTES, r); };
     o.kh = [](int grid, const KHArgs& a, Stream& s) -> int {
       return be_launch<KHBody<C>, KHArgs, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    };
+    o.kp_configure = [](int* r) -> int { return be_configure<KPBody<C>, KPArgs, C::CT, C::MINB>(C::SMEM_BYTES, r); };
+    o.kp = [](int grid, const KPArgs& a, Stream& s) -> int {
+      return be_launch<KPBody<C>, KPArgs, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
     };
   }
   o.fill_ksqperm = &fill_ccperm<C>;  // the same register-order permutation as the divisor table
@@ -346,6 +370,12 @@ struct vmk_plan {
   double* hksqperm = nullptr;
   double hyb_dx = 0;
   int res_kh = 0;
+  // pseudo-spectral solver (vmk_ps23_numerical), allocated on first use; shares hW, hJ, hksq, hksqperm, V, hVs
+  double2* pV[2] = {nullptr, nullptr};  // inverse-j of j3f, j4f (V and hVs hold j1f, j2f)
+  double2* pA0 = nullptr;               // kx = 0 part of the packed spectrum row, [N]
+  double* ptab = nullptr;               // 8 x [N]: mp, mm, cc, dd (natural order), then the same in register order
+  double ps_dx = 0;
+  int res_kp = 0;
   // lid-driven cavity (vmk_ldc_numerical), allocated on first use: node arrays (n+1)^2 with n = N/2
   double* cw[3] = {nullptr, nullptr, nullptr};  // wn, wtA, wtB
   double* cs = nullptr;                         // sn
@@ -918,6 +948,121 @@ int hybrid_field(vmk_plan* p, double* ut) {
   return 0;
 }
 
+// ---- pseudo-spectral solver, 2/3 rule (22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl) -------------------
+int ensure_ps23(vmk_plan* p, double dx) {
+  VMK_TRY(ensure_hybrid(p, dx));  // wf, jf, k2 tables: the same state as the hybrid solver's
+  if (!p->ops.kp) return fail(VMK_ESIZE, "the pseudo-spectral solver supports grids up to 8192^2");
+  const int n = p->N;
+  const size_t spec = sizeof(double2) * (size_t)(n / 2) * n;
+  if (!p->ptab) {
+    VMK_TRY(p->ops.kp_configure(&p->res_kp));
+    VMK_TRY(dev_alloc(p, (void**)&p->pV[0], spec));
+    VMK_TRY(dev_alloc(p, (void**)&p->pV[1], spec));
+    VMK_TRY(dev_alloc(p, (void**)&p->pA0, sizeof(double2) * n));
+    VMK_TRY(dev_alloc(p, (void**)&p->ptab, sizeof(double) * 8 * n));
+    p->ps_dx = 0;
+  }
+  if (p->ps_dx != dx) {
+    // jacobian(), pseudospectral_23_rule.jl:96-108: hx = 2 pi/(nx dx), kx[1] = eps, ky = kx; :124-133: the zeroed band
+    std::vector<double> k(n), m(n), tab(8 * (size_t)n);
+    const double hx = 2.0 * M_PI / ((double)n * dx);
+    for (int i = 1; i <= n / 2; i++) {
+      k[i - 1] = hx * ((double)i - 1.0);
+      k[i + n / 2 - 1] = hx * (double)(i - n / 2 - 1);
+    }
+    k[0] = 1.e-6;
+    const int nxe = (int)floor(2.0 * (double)n / 3.0), half = nxe / 2;
+    for (int i = 0; i < n; i++) m[i] = (i >= half && i < n - half) ? 0.0 : 1.0;  // 1-based half+1 .. n-half zeroed
+    if (m[n / 2] != 0.0) return fail(VMK_ESIZE, "2/3 rule: the Nyquist mode is expected inside the truncated band");
+    double *mp = tab.data(), *mm = mp + n, *cc = mm + n, *dd = cc + n;
+    for (int i = 0; i < n; i++) {
+      const int mi = (n - i) % n;
+      mp[i] = m[i];
+      mm[i] = m[mi];
+      cc[i] = k[i] * m[i] * .5;
+      dd[i] = -k[mi] * m[mi] * .5;
+    }
+    for (int q = 0; q < 4; q++) p->ops.fill_ksqperm(tab.data() + (size_t)q * n, tab.data() + (size_t)(4 + q) * n);
+    VMK_TRY(be_sync(p->st));
+    VMK_TRY(be_h2d(p->ptab, tab.data(), sizeof(double) * 8 * n, p->st));
+    VMK_TRY(be_sync(p->st));
+    p->ps_dx = dx;
+  }
+  return 0;
+}
+
+// stage 0: wf = fft(w0); 1..3: the RK3/CN stages (alpha, gamma, rho of pseudospectral_23_rule.jl:30-32); 4: V = ifft_j(wf)
+int launch_kp(vmk_plan* p, int stage, double dt, double re) {
+  static const double alpha[5] = {0.0, 8. / 15., 2. / 15., 1. / 3., 0.0};
+  static const double gamma[5] = {0.0, 8. / 15., 5. / 12., 3. / 4., 0.0};
+  static const double rho[5] = {0.0, 0.0, -17. / 60., -5. / 12., 0.0};
+  const size_t n = (size_t)p->N;
+  KPArgs a;
+  a.T = p->T;
+  a.W = p->hW;
+  a.J = p->hJ;
+  a.A0 = p->pA0;
+  a.V[0] = stage == 4 ? p->T : p->V;
+  a.V[1] = p->hVs;
+  a.V[2] = p->pV[0];
+  a.V[3] = p->pV[1];
+  a.tw = p->tw;
+  a.ksq = p->hksq;
+  a.ksqperm = p->hksqperm;
+  a.mp = p->ptab;
+  a.mm = p->ptab + n;
+  a.cc = p->ptab + 2 * n;
+  a.dd = p->ptab + 3 * n;
+  a.mpperm = p->ptab + 4 * n;
+  a.mmperm = p->ptab + 5 * n;
+  a.ccperm = p->ptab + 6 * n;
+  a.ddperm = p->ptab + 7 * n;
+  a.zfac = .5 * dt / re;
+  a.alpha = alpha[stage];
+  a.gdt = (stage >= 1 && stage <= 3) ? gamma[stage] * dt : 1.0;
+  a.rdt = rho[stage] * dt;
+  a.scale = 1.0 / (2.0 * (double)p->N * (double)p->N);
+  a.stage = stage;
+  a.nrows = p->N / 2;
+  const int work = (a.nrows + p->ops.fpc - 1) / p->ops.fpc;
+  Timed t(p, KI_K2);
+  VMK_TRY(p->ops.kp(work < p->res_kp ? work : p->res_kp, a, p->st));
+  t.done();
+  p->launches++;
+  return 0;
+}
+
+// jacp = j1 j2 - j3 j4 over the interior rows of four slabs, in place over the first (pseudospectral_23_rule.jl:138-141)
+int launch_kp_product(vmk_plan* p, double* q1, const double* q2, const double* q3, const double* q4) {
+  KPProdArgs a;
+  const size_t N = (size_t)p->N;
+  a.q1 = q1 + N;
+  a.q2 = q2 + N;
+  a.q3 = q3 + N;
+  a.q4 = q4 + N;
+  a.n = N * (size_t)p->NJ;
+  size_t want = (a.n / 2 + kK5Threads - 1) / kK5Threads;
+  const size_t cap = (size_t)p->sms * 16;
+  const int grid = (int)(want < cap ? want : cap);
+  VMK_TRY((be_launch<KPProduct, KPProdArgs, kK5Threads, 4>(grid < 1 ? 1 : grid, 0, a, p->st)));
+  p->launches++;
+  return 0;
+}
+
+// ut = real(ifft(wf)) with the periodic duplicates (pseudospectral_23_rule.jl:71-77): (N+1) x (N+1) on the host.
+// Scratch: T (free once the last stage's KP has consumed it) and w[1]; the four derivative spectra V[0..3] that the next
+// step's first jacobian reads stay untouched.
+int ps23_field(vmk_plan* p, double* ut, double dt, double re) {
+  const size_t N = (size_t)p->N, n1 = N + 1;
+  VMK_TRY(launch_kp(p, 4, dt, re));
+  VMK_TRY(launch_k3_rows(p, p->T, p->w[1]));
+  VMK_TRY(be_d2h_2d(ut, sizeof(double) * n1, p->w[1] + N, sizeof(double) * N, sizeof(double) * N, N, p->st));
+  VMK_TRY(be_sync(p->st));
+  for (size_t j = 0; j < N; j++) ut[N + j * n1] = ut[j * n1];
+  memcpy(ut + N * n1, ut, sizeof(double) * n1);
+  return 0;
+}
+
 int check_plan(vmk_plan* p) {
   if (!p) return fail(VMK_EARG, "plan is NULL");
   VMK_TRY(be_set_device(p->device));  // a host thread may drive several plans on different devices
@@ -1096,6 +1241,10 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_free(p->hVs);
   be_free(p->hksq);
   be_free(p->hksqperm);
+  be_free(p->pV[0]);
+  be_free(p->pV[1]);
+  be_free(p->pA0);
+  be_free(p->ptab);
   for (int b = 0; b < 3; b++) be_free(p->cw[b]);
   be_free(p->cs);
   be_free(p->csp);
@@ -1344,6 +1493,58 @@ int vmk_hybrid_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double d
   VMK_TRY(hybrid_field(p, ut));
   if (snap && freq > 0 && nt > 0 && nt % freq == 0) snap(nt, ut, user);
   p->uploaded = false;  // w[0..2] were used as scratch
+  return VMK_OK;
+}
+
+int vmk_ps23_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
+                       double* ut, int64_t freq, vmk_snapshot_fn snap, void* user) {
+  VMK_TRY(check_plan(p));
+  if (!wn || !ut) return fail(VMK_EARG, "wn or ut is NULL");
+  if (nt < 0) return fail(VMK_EARG, "nt < 0");
+  if (dx != dy) return fail(VMK_EARG, "the pseudo-spectral solver needs dx == dy (wavespace aliases ky = kx, Common.jl:197)");
+  VMK_TRY(ensure_ps23(p, dx));
+  VMK_TRY(upload_ghosted(p, wn, p->w[0]));
+  VMK_TRY(be_event_record(p->ev0, p->st));
+  VMK_TRY(launch_k1(p, p->w[0]));
+  VMK_TRY(launch_kp(p, 0, dt, re));  // wf = fft(w0), wf[1,1] = 0 (:24-27) and the spectral half of jacobian(wf)
+  for (int64_t k = 1; k <= nt; k++) {
+    for (int stage = 1; stage <= 3; stage++) {
+      VMK_TRY(launch_k3_rows(p, p->V, p->w[0]));      // j1 = real(ifft(i kx wf / k2))    pseudospectral_23_rule.jl:135
+      VMK_TRY(launch_k3_rows(p, p->hVs, p->w[1]));    // j2 = real(ifft(i ky wf))
+      VMK_TRY(launch_k3_rows(p, p->pV[0], p->w[2]));  // j3 = real(ifft(i ky wf / k2))
+      VMK_TRY(launch_k3_rows(p, p->pV[1], p->psi));   // j4 = real(ifft(i kx wf))
+      VMK_TRY(launch_kp_product(p, p->w[0], p->w[1], p->w[2], p->psi));  // j1 j2 - j3 j4       :138-141
+      VMK_TRY(launch_k1(p, p->w[0]));                 // fft along i                      :143
+      VMK_TRY(launch_kp(p, stage, dt, re));           // fft along j, update, the four ifft along j for the next stage
+    }
+    if (snap && freq > 0 && k % freq == 0 && k != nt) {  // :69-86 (the final field is produced below)
+      VMK_TRY(ps23_field(p, ut, dt, re));
+      snap(k, ut, user);
+    }
+  }
+  VMK_TRY(be_event_record(p->ev1, p->st));
+  p->ev_valid = true;
+  VMK_TRY(ps23_field(p, ut, dt, re));
+  if (snap && freq > 0 && nt > 0 && nt % freq == 0) snap(nt, ut, user);
+  p->uploaded = false;  // w[0..2], psi were used as scratch
+  return VMK_OK;
+}
+
+// ---- the callers' snapshot files (vmk_io.hpp; host code, no device involved) ------------------------------------------
+int vmk_print_float64(double v, char* buf) { return buf ? julia_print_f64(v, buf) : 0; }
+
+int vmk_write_field(const char* path, const double* x, const double* y, const double* ut, int64_t nx1, int64_t ny1) {
+  if (!path || !x || !y || !ut) return fail(VMK_EARG, "path, x, y or ut is NULL");
+  if (nx1 < 0 || ny1 < 0) return fail(VMK_EARG, "negative extent");
+  std::string err;
+  if (write_field_text(path, x, y, ut, nx1, ny1, &err)) return fail(VMK_EIO, err);
+  return VMK_OK;
+}
+
+int vmk_read_field(const char* path, double* x, double* y, double* w, int64_t cap, int64_t* nrows) {
+  if (!path) return fail(VMK_EARG, "path is NULL");
+  std::string err;
+  if (read_field_text(path, x, y, w, cap < 0 ? 0 : cap, nrows, &err)) return fail(VMK_EIO, err);
   return VMK_OK;
 }
 

@@ -33,6 +33,7 @@ extern "C" {
 #define VMK_ECUDA 2  /* CUDA runtime error (including "no device") */
 #define VMK_EARG 3   /* bad argument (NULL pointer, bad rank, ...) */
 #define VMK_ESTATE 4 /* call sequence error (e.g. step before upload) */
+#define VMK_EIO 5    /* snapshot file could not be opened, written or parsed */
 
 typedef struct vmk_plan vmk_plan;
 
@@ -100,6 +101,18 @@ int vmk_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, d
 int vmk_hybrid_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
                          double* ut, int64_t freq, vmk_snapshot_fn snap, void* user);
 
+/* numerical(nx,ny,nt,dx,dy,dt,re,x,y,wn,ns)  22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl:13-89 -- the pseudo-
+ * spectral solver with the 2/3 truncation rule: the vorticity lives in Fourier space, jacobian() (:95-144) multiplies
+ * it by i kx [/ k2], i ky [/ k2] (kx[1] = eps, :107), zeroes the band floor(nxe/2)+1 .. nx-floor(nxe/2), takes
+ * real(ifft) of the four spectra, forms j1 j2 - j3 j4 in real space and transforms it back; RK3 for the Jacobian and
+ * Crank-Nicolson per mode for the diffusion exactly as in hybrid.jl.  Arguments as vmk_hybrid_numerical: wn ghosted, read
+ * only; ut (nx+1) x (ny+1) receives real(ifft(wf)) with the periodic duplicates; snap(k, ut, user) after every step k
+ * with k % freq == 0.  (The reference returns the field of its LAST snapshot; that is the final field whenever nt is a
+ * multiple of freq, as in its own configuration -- ut here is always the final field.)
+ * Single-GPU plans, nx == ny <= 8192, dx == dy. */
+int vmk_ps23_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
+                       double* ut, int64_t freq, vmk_snapshot_fn snap, void* user);
+
 /* numerical(nx,ny,nt,dx,dy,dt,re,wn,sn,rms)  18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl:59-117 -- lid-driven cavity:
  * RK3, the Arakawa/Laplacian rhs without periodic wrap (:123-158), Jensen wall vorticity bc2 (:38-52) and the sine-
  * transform Poisson solve fps_sine (:11-21, FFTW RODFT00).  wn, sn: (nx+1) x (ny+1) node arrays, both mutated in place
@@ -108,6 +121,18 @@ int vmk_hybrid_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, doubl
  * kernels of the vortex-merger path.  nx == ny, a power of two in [16, 16384]; single-GPU plans. */
 int vmk_ldc_numerical(vmk_plan* plan, int64_t nx, int64_t ny, int64_t nt, double dx, double dy, double dt, double re,
                       double* wn, double* sn, double* rms);
+
+/* ---- the callers' snapshot files (host code) ------------------------------------------- */
+/* Julia's print(::Float64) -- "$(x)" in the scripts' write calls (vm.jl:83): shortest round-trip digits, positional
+ * for 1e-4 <= |v| < 1e6, otherwise d.ddde[-]X without exponent padding ("1.0e-5", not C's "1e-05").  buf: at least 32
+ * bytes, no terminator is written; returns the number of characters. */
+int vmk_print_float64(double v, char* buf);
+/* for j in 1:ny1, i in 1:nx1: "x[i] y[j] ut[i,j]\n" (vm.jl:81-85,132-136,142-146; hybrid.jl:79-83); ut column-major
+ * nx1 x ny1.  Byte-identical to what the Julia scripts write for the same values. */
+int vmk_write_field(const char* path, const double* x, const double* y, const double* ut, int64_t nx1, int64_t ny1);
+/* plotting.jl:14-28 (readdlm): three whitespace-separated columns per line into x, y, w (each may be NULL; at most cap
+ * rows are stored), *nrows = rows in the file. */
+int vmk_read_field(const char* path, double* x, double* y, double* w, int64_t cap, int64_t* nrows);
 
 /* ---- device-resident path (what numerical() is built from) ------------------------------------------- */
 int vmk_upload(vmk_plan* plan, const double* wn_ghosted);

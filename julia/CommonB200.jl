@@ -16,7 +16,8 @@
 # the same ABI is exercised in CI through ctypes (cfd_julia_b200/common.py), which this file mirrors line by line.
 module CommonB200
 
-export fps, vm_rhs, numerical, ps_fft, vmk_plan, vmk_upload, vmk_step, vmk_download, vmk_plans_multi, numerical_multi
+export fps, vm_rhs, numerical, numerical_hybrid, numerical_ps23, numerical_ldc, write_field, read_field, ps_fft
+export vmk_plan, vmk_upload, vmk_step, vmk_download, vmk_plans_multi, numerical_multi
 
 const libvmk = get(ENV, "VMK_LIB", joinpath(@__DIR__, "..", "cfd_julia_b200", "libvmk.so"))
 
@@ -110,31 +111,50 @@ numerical(nx, ny, nt, Δx, Δy, Δt, re, wn::Matrix{Float64}) = begin
   return out
 end
 
-# hybrid.jl flavour (20_NS2D_Hybrid_Solver/hybrid.jl:14-90): RK3 / Crank-Nicolson in Fourier space.  Same arguments as
-# vm.jl's numerical; wn is only read; returns ut = real(ifft(wf)) with the periodic duplicates, (nx+1) x (ny+1), and
-# writes "vm<m>.txt" every nt ÷ ns steps (hybrid.jl:71-86).
-numerical_hybrid(nx, ny, nt, Δx, Δy, Δt, re, x, y, wn::Matrix{Float64}, ns) = begin
-  ghosted(wn, nx, ny, "wn")
-  freq = nt ÷ ns
-  ut = Array{Float64}(undef, nx + 1, ny + 1)
-  m = Ref(1)
-  cb = Ref{Function}(k -> begin
-    @show k
-    open("vm$(m[]).txt", "w") do io
-      for j ∈ 1:ny + 1 for i ∈ 1:nx + 1
-        write(io, "$(x[i]) $(y[j]) $(ut[i, j])\n")
-      end end
+# hybrid.jl flavour (20_NS2D_Hybrid_Solver/hybrid.jl:14-90): RK3 / Crank-Nicolson in Fourier space, and the pseudo-spectral
+# solver with the 2/3 rule (22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl:13-89): same time loop, spectral
+# Jacobian.  Same arguments as vm.jl's numerical; wn is only read; returns ut = real(ifft(wf)) with the periodic
+# duplicates, (nx+1) x (ny+1), and writes "vm<m>.txt" every nt ÷ ns steps (hybrid.jl:71-86) through the library's writer
+# (byte-identical to the scripts' `write(io, "$(x[i]) $(y[j]) $(ut[i, j])\n")` loop, minutes faster at 8192^2).
+for (jlname, csym) in ((:numerical_hybrid, :vmk_hybrid_numerical), (:numerical_ps23, :vmk_ps23_numerical))
+  @eval $jlname(nx, ny, nt, Δx, Δy, Δt, re, x, y, wn::Matrix{Float64}, ns) = begin
+    ghosted(wn, nx, ny, "wn")
+    freq = nt ÷ ns
+    ut = Array{Float64}(undef, nx + 1, ny + 1)
+    m = Ref(1)
+    cb = Ref{Function}(k -> begin
+      @show k
+      write_field("vm$(m[]).txt", x, y, ut)
+      m[] += 1
+    end)
+    GC.@preserve cb begin
+      check(ccall(($(QuoteNode(csym)), libvmk), Cint,
+                  (Ptr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cvoid},
+                   Ptr{Cvoid}),
+                  vmk_plan(nx, ny).handle, nt, Δx, Δy, Δt, re, wn, ut, freq,
+                  @cfunction(snap_trampoline, Cvoid, (Int64, Ptr{Cdouble}, Ptr{Cvoid})), pointer_from_objref(cb)))
     end
-    m[] += 1
-  end)
-  GC.@preserve cb begin
-    check(ccall((:vmk_hybrid_numerical, libvmk), Cint,
-                (Ptr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cvoid},
-                 Ptr{Cvoid}),
-                vmk_plan(nx, ny).handle, nt, Δx, Δy, Δt, re, wn, ut, freq,
-                @cfunction(snap_trampoline, Cvoid, (Int64, Ptr{Cdouble}, Ptr{Cvoid})), pointer_from_objref(cb)))
+    return ut
   end
-  return ut
+end
+
+# the scripts' text dump (vm.jl:81-85,132-136,142-146) and plotting.jl:14-28's reader, native code in the library
+write_field(path::AbstractString, x::Vector{Float64}, y::Vector{Float64}, ut::Matrix{Float64}) = begin
+  nx1, ny1 = size(ut)
+  (length(x) >= nx1 && length(y) >= ny1) || throw(BoundsError(x, nx1))
+  check(ccall((:vmk_write_field, libvmk), Cint, (Cstring, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Int64),
+              path, x, y, ut, nx1, ny1))
+  return
+end
+
+read_field(path::AbstractString, nx::Integer, ny::Integer) = begin
+  n = (nx + 1) * (ny + 1)
+  x, y, w = zeros(n), zeros(n), zeros(n)
+  rows = Ref{Int64}(0)
+  check(ccall((:vmk_read_field, libvmk), Cint, (Cstring, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Int64}),
+              path, x, y, w, n, rows))
+  rows[] == n || throw(DimensionMismatch("$path: $(rows[]) rows, expected $n"))
+  return x[1:nx+1], reshape(y, (nx + 1, ny + 1))[1, :], reshape(w, (nx + 1, ny + 1))
 end
 
 # lid_driven_cavity.jl flavour (18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl:59-117): same arguments, wn, sn

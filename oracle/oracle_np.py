@@ -318,3 +318,102 @@ def ldc_numerical(nx, ny, nt, dx, dy, dt, re, wn, sn, rms):
         ldc_bc2(nx, ny, dx, dy, wn, sn)
         ldc_fps_sine(nx, ny, -wn, iden, sn)
         rms[k] = np.sqrt(np.sum((sn - sp)**2) / ((nx + 1) * (ny + 1)))
+
+
+# ---- 21_NS2D_PseudoSpectral_32_Rule, 22_NS2D_PseudoSpectral_23_Rule -------------------------------
+def ps_wavenumbers(nx, dx, eps=1.e-6):
+    """pseudospectral_23_rule.jl:96-107 (= pseudospectral_32_rule.jl:96-107): hx = 2 pi/(nx dx), kx[1] = eps."""
+    hx = 2 * np.pi / (nx * dx)
+    kx = np.empty(nx)
+    i = np.arange(1, nx // 2 + 1)
+    kx[i - 1] = hx * (i - 1.)
+    kx[i + nx // 2 - 1] = hx * (i - nx // 2 - 1)
+    kx[0] = eps
+    return kx
+
+
+def ps23_jacobian(nx, ny, dx, dy, wf, k2):
+    """pseudospectral_23_rule.jl:95-144: the four derivative spectra, truncated with the 2/3 rule (modes i in
+    floor(nxe/2)+1 .. nx-floor(nxe/2), 1-based, are zeroed in both directions: the retained band is -K .. K-1 with
+    K = floor(floor(2nx/3)/2), NOT symmetric), real(ifft) of each, the product in real space and its fft."""
+    kx = ps_wavenumbers(nx, dx)
+    ky = kx
+    j1f = 1j * wf * kx[:, None] / k2
+    j4f = 1j * wf * kx[:, None]
+    j2f = 1j * wf * ky[None, :]
+    j3f = 1j * wf * ky[None, :] / k2
+    nxe = int(np.floor(2 * nx / 3))
+    nye = int(np.floor(2 * ny / 3))
+    for a in (j1f, j2f, j3f, j4f):
+        a[nxe // 2:nx - nxe // 2, :] = 0.   # 1-based floor(nxe/2)+1 : nx-floor(nxe/2)
+        a[:, nye // 2:ny - nye // 2] = 0.
+    j1, j2, j3, j4 = (np.real(np.fft.ifft2(a)) for a in (j1f, j2f, j3f, j4f))
+    return np.fft.fft2(j1 * j2 - j3 * j4)
+
+
+def ps32_jacobian(nx, ny, dx, dy, wf, k2):
+    """pseudospectral_32_rule.jl:95-177: the four derivative spectra zero-padded to 1.5nx x 1.5ny (the nx/2 upper
+    indices go to the top of the padded array: retained modes -nx/2 .. nx/2-1), real(ifft) on the padded grid (scaled
+    by nxe nye/(nx ny)), product, fft, extraction of the same nx x ny modes, scaled back."""
+    kx = ps_wavenumbers(nx, dx)
+    ky = kx
+    j1f = 1j * wf * kx[:, None] / k2
+    j4f = 1j * wf * kx[:, None]
+    j2f = 1j * wf * ky[None, :]
+    j3f = 1j * wf * ky[None, :] / k2
+    nxe, nye = int(1.5 * nx), int(1.5 * ny)
+    hx, hy = nx // 2, ny // 2
+
+    def pad(a):
+        p = np.zeros((nxe, nye), dtype=np.complex128)
+        p[:hx, :hy] = a[:hx, :hy]
+        p[nxe - hx:, :hy] = a[hx:, :hy]
+        p[:hx, nye - hy:] = a[:hx, hy:]
+        p[nxe - hx:, nye - hy:] = a[hx:, hy:]
+        return p
+
+    j1, j2, j3, j4 = (np.real(np.fft.ifft2(pad(a) * (nxe * nye) / (nx * ny))) for a in (j1f, j2f, j3f, j4f))
+    jacpf = np.fft.fft2(j1 * j2 - j3 * j4)
+    jf = np.zeros((nx, ny), dtype=np.complex128)
+    jf[:hx, :hy] = jacpf[:hx, :hy]
+    jf[hx:, :hy] = jacpf[nxe - hx:, :hy]
+    jf[:hx, hy:] = jacpf[:hx, nye - hy:]
+    jf[hx:, hy:] = jacpf[nxe - hx:, nye - hy:]
+    return jf * (nx * ny) / (nxe * nye)
+
+
+def ps_numerical(rule, nx, ny, nt, dx, dy, dt, re, wn, freq=0, snapshot=None):
+    """pseudospectral_23_rule.jl:13-89 / pseudospectral_32_rule.jl:13-89 (identical time loops): RK3 for the
+    pseudo-spectral Jacobian, Crank-Nicolson per mode for the diffusion.  rule = 23 or 32.  Returns real(ifft(wnf)) with
+    the periodic duplicates, (nx+1) x (ny+1) (the reference returns the field of its last snapshot, which is the final
+    one whenever nt is a multiple of nt ÷ ns, as in its own configuration); wn (ghosted) is only read."""
+    assert nx == ny and rule in (23, 32)
+    jacobian = ps23_jacobian if rule == 23 else ps32_jacobian
+    k2 = wavespace(nx, ny, dx, dy)
+    wnf = np.fft.fft2(wn[1:nx + 1, 1:ny + 1].astype(np.complex128))
+    wnf[0, 0] = 0.
+    a1, a2, a3 = 8. / 15., 2. / 15., 1. / 3.
+    g1, g2, g3 = 8. / 15., 5. / 12., 3. / 4.
+    r2, r3 = -17. / 60., -5. / 12.
+    z = .5 * dt * k2 / re
+    d1, d2, d3 = a1 * z, a2 * z, a3 * z
+
+    def field(wf):
+        ut = np.empty((nx + 1, ny + 1), order="F")
+        ut[:nx, :ny] = np.real(np.fft.ifft2(wf))
+        ut[nx, :] = ut[0, :]
+        ut[:, ny] = ut[:, 0]
+        return ut
+
+    for k in range(1, nt + 1):
+        jnf = jacobian(nx, ny, dx, dy, wnf, k2)
+        w1f = ((1. - d1) / (1. + d1)) * wnf + (g1 * dt * jnf) / (1. + d1)
+        w1f[0, 0] = 0.
+        j1f = jacobian(nx, ny, dx, dy, w1f, k2)
+        w2f = ((1. - d2) / (1. + d2)) * w1f + (r2 * dt * jnf + g2 * dt * j1f) / (1. + d2)
+        w2f[0, 0] = 0.
+        j2f = jacobian(nx, ny, dx, dy, w2f, k2)
+        wnf = ((1. - d3) / (1. + d3)) * w2f + (r3 * dt * j1f + g3 * dt * j2f) / (1. + d3)
+        if snapshot is not None and freq > 0 and k % freq == 0:
+            snapshot(k, field(wnf))
+    return field(wnf)

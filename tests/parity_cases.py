@@ -165,6 +165,27 @@ def check_hybrid(cm, onp, n, nt, dt=None, re=1000., ns=1, tol=TOL_RUN):
     return ut
 
 
+def check_ps23(cm, onp, n, nt, dt=None, re=1000., ns=1, tol=TOL_RUN, noise=0.05):
+    """22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl `numerical` against the literal numpy restatement
+    (oracle_np.ps_numerical, full complex spectra, numpy's C2C transforms).  The noisy start puts energy into every
+    mode, including the half-weighted mode -K at the edge of the (asymmetric) retained band and the Nyquist lines."""
+    dx, dy, x, y = grid(n)
+    w = vm_field(n) + noise * noise_field(n, 5)
+    dt = stable_dt(n, re) if dt is None else dt
+    wb = w.copy(order="F")
+    snaps_ref, snaps = [], []
+    ref = onp.ps_numerical(23, n, n, nt, dx, dy, dt, re, w, nt // ns, lambda k, ut: snaps_ref.append((k, ut.copy())))
+    ut = cm.numerical_ps23(n, n, nt, dx, dy, dt, re, x, y, w, ns, snapshot=lambda k, u: snaps.append((k, u.copy())))
+    assert ut.shape == (n + 1, n + 1) and np.array_equal(w, wb)  # wn is only read (:22)
+    assert rel_l2(ut, ref) < tol
+    assert np.array_equal(ut[n, :], ut[0, :]) and np.array_equal(ut[:, n], ut[:, 0])  # :73-76
+    assert abs(ut[:n, :n].mean()) < 1e-12  # the mean mode is dropped (:27) and only re-enters at rounding level
+    assert [k for k, _ in snaps] == [k for k, _ in snaps_ref]
+    for (_, a), (_, b) in zip(snaps, snaps_ref):
+        assert rel_l2(a, b) < tol
+    return ut
+
+
 def check_ldc(cm, onp, n, nt, dt=None, re=100., from_rest=False, tol=TOL_RUN):
     """18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl `numerical` against the numpy/scipy restatement
     (oracle_np.ldc_numerical).  from_rest: the script's own initial condition (wn = sn = 0, the lid drives the flow);

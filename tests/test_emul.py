@@ -106,6 +106,45 @@ def test_hybrid_solver_errors(emul):
     p.close()
 
 
+@pytest.mark.parametrize("n,nt,ns,noise", [(32, 6, 3, 1.), (64, 4, 2, 1.), (128, 3, 1, .05), (256, 2, 2, .5), (512, 2, 1, .05),
+                                            (1024, 1, 1, .05)])
+def test_pseudospectral_23_rule(emul, oracle_np, n, nt, ns, noise):
+    """pseudospectral_23_rule.jl (kernel KP + kp_product + the finite-difference path's K1/K3) against
+    the literal full-spectrum numpy restatement; noise = 1 is a white-noise start (every mode, incl. the half-weighted
+    edge of the asymmetric retained band)"""
+    pc.check_ps23(emul, oracle_np, n, nt, dt=1e-3 if noise >= .5 else None, ns=ns, noise=noise)
+
+
+def test_pseudospectral_23_rule_defaults_60_steps(emul, oracle_np):
+    """the script's own configuration (128^2, dt = .01, Re = 1000, vm_ic), its first 60 steps, snapshots every 20"""
+    pc.check_ps23(emul, oracle_np, 128, 60, dt=.01, ns=3, noise=0.)
+
+
+def test_pseudospectral_errors(emul):
+    from cfd_julia_b200.common import Plan, VmkError
+    n = 64
+    dx, dy, x, y = grid(n)
+    w = vm_field(n)
+    with pytest.raises(ZeroDivisionError):
+        emul.numerical_ps23(n, n, 3, dx, dy, .01, 1000., x, y, w, 5)
+    with pytest.raises(VmkError):  # ky = kx (pseudospectral_23_rule.jl:108): dx != dy is not representable
+        emul.numerical_ps23(n, n, 2, dx, 2 * dy, .01, 1000., x, y, w, 1)
+    p = Plan(emul.lib, n, n, 0, 2)  # slab plans: not supported by the spectral-space solvers
+    ut = np.zeros((n + 1, n + 1), order="F")
+    from cfd_julia_b200._lib import SNAPSHOT_FN
+    assert emul.lib.ps23_numerical(p.handle, 1, dx, dy, .01, 1000., w.ctypes.data, ut.ctypes.data, 0, SNAPSHOT_FN(),
+                                   None) != 0
+    p.close()
+
+
+def test_pseudospectral_then_finite_difference(emul, oracle_c, oracle_np):
+    """the solvers share buffers and tables inside one plan: interleaving them must not disturb either"""
+    pc.check_ps23(emul, oracle_np, 64, 2)
+    pc.check_numerical(emul, oracle_c, vm_field(64), 3, .01, 1000.)
+    pc.check_hybrid(emul, oracle_np, 64, 2)
+    pc.check_ps23(emul, oracle_np, 64, 2)
+
+
 @pytest.mark.parametrize("n,nt", [(16, 4), (32, 3), (64, 3), (128, 2), (256, 1)])
 def test_lid_driven_cavity(emul, oracle_np, n, nt):
     """lid_driven_cavity.jl (sine-transform Poisson solve as the periodic solve of the odd extension)"""

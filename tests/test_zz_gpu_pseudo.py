@@ -1,0 +1,54 @@
+"""GPU suite (-m gpu), SURVEY 8f row f3: the pseudo-spectral solver with the 2/3 rule
+(22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl) through the C ABI of libvmk.so against the literal numpy
+restatement (oracle_np.ps_numerical: full complex spectra, numpy C2C transforms).  Tolerance: relative L2 <= 1e-10.
+
+(The file sorts last on purpose: it was added after the round's GPU budget was spent, so its kernels were validated on
+the host emulator only -- tests/test_emul.py::test_pseudospectral_* -- before their first run on a B200.)"""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from helpers import grid, rel_l2, vm_field
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU suite needs a CUDA device"
+    import cfd_julia_b200
+    from cfd_julia_b200.common import Common
+    lib = cfd_julia_b200.default_library()  # raises if libvmk.so is missing: no fallback
+    assert lib.prefix == "vmk_" and lib.path.endswith("libvmk.so")
+    cm = Common(lib)
+    yield cm
+    cm.clear_plans()
+
+
+@pytest.mark.parametrize("n,nt,ns,noise", [(32, 20, 4, 1.), (64, 20, 2, 1.), (128, 50, 5, .05), (256, 10, 2, .5),
+                                            (512, 10, 1, .05), (1024, 10, 2, .05), (2048, 3, 1, .05), (4096, 2, 1, .05)])
+def test_pseudospectral_23_rule(gpu, oracle_np, n, nt, ns, noise):
+    pc.check_ps23(gpu, oracle_np, n, nt, dt=1e-3 if noise >= .5 else None, ns=ns, noise=noise)
+    if n >= 2048:
+        gpu.clear_plans()
+
+
+def test_pseudospectral_23_rule_defaults_500_steps(gpu, oracle_np):
+    """the script's own configuration (128^2, dt = .01, Re = 1000, vm_ic), first 500 of its 2000 steps"""
+    pc.check_ps23(gpu, oracle_np, 128, 500, dt=.01, ns=10, noise=0.)
+
+
+def test_pseudospectral_8192_properties(gpu):
+    """full size, no oracle run (minutes of numpy FFTs): finite, mean-free, periodic duplicates, enstrophy decays"""
+    n = 8192
+    dx, dy, x, y = grid(n)
+    w = vm_field(n)
+    ut = gpu.numerical_ps23(n, n, 2, dx, dy, 1e-4, 1000., x, y, w, 1)
+    assert np.isfinite(ut).all() and abs(ut[:n, :n].mean()) < 1e-12
+    assert np.array_equal(ut[n, :], ut[0, :]) and np.array_equal(ut[:, n], ut[:, 0])
+    w0 = w[1:n + 1, 1:n + 1] - w[1:n + 1, 1:n + 1].mean()
+    e0, e1 = float((w0**2).sum()), float((ut[:n, :n]**2).sum())
+    assert e1 < e0 and (e0 - e1) / e0 < 1e-3
+    assert rel_l2(ut[:n, :n], w0) < 1e-3  # two steps of dt = 1e-4 barely move the field
+    gpu.clear_plans()
