@@ -6,7 +6,7 @@ for Julia callers.  Importing the package does not need a GPU; calling into it d
 """
 from . import _build  # noqa: F401
 from .common import (Common, Plan, VmkError, compute_l2norm_bnds, exact_tgv, fps, julia_float_str,  # noqa: F401
-                     numerical, numerical_hybrid, numerical_ldc, numerical_ps23, numerical_tgv, plan, ps_fft,
+                     numerical, numerical_hybrid, numerical_ldc, numerical_ps23, numerical_ps32, numerical_tgv, plan, ps_fft,
                      read_field, vm_ic, vm_rhs, write_field)
 from ._lib import SYMBOLS, VmkLibrary, default_library  # noqa: F401
 

@@ -37,6 +37,7 @@ _PROTOS = {
     "numerical": (C.c_int, [_P, C.c_int64, _D, _D, _D, _D, _P, _P, C.c_int64, SNAPSHOT_FN, _P]),
     "hybrid_numerical": (C.c_int, [_P, C.c_int64, _D, _D, _D, _D, _P, _P, C.c_int64, SNAPSHOT_FN, _P]),
     "ps23_numerical": (C.c_int, [_P, C.c_int64, _D, _D, _D, _D, _P, _P, C.c_int64, SNAPSHOT_FN, _P]),
+    "ps32_numerical": (C.c_int, [_P, C.c_int64, _D, _D, _D, _D, _P, _P, C.c_int64, SNAPSHOT_FN, _P]),
     "print_float64": (C.c_int, [_D, C.c_char_p]),
     "write_field": (C.c_int, [C.c_char_p, _P, _P, _P, C.c_int64, C.c_int64]),
     "read_field": (C.c_int, [C.c_char_p, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),

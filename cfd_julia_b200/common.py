@@ -31,7 +31,7 @@ import numpy as np
 
 from ._lib import SNAPSHOT_FN, VmkError, VmkLibrary, default_library
 
-__all__ = ["Common", "fps", "vm_rhs", "numerical", "numerical_tgv", "numerical_hybrid", "numerical_ps23", "numerical_ldc", "ps_fft", "vm_ic", "exact_tgv",
+__all__ = ["Common", "fps", "vm_rhs", "numerical", "numerical_tgv", "numerical_hybrid", "numerical_ps23", "numerical_ps32", "numerical_ldc", "ps_fft", "vm_ic", "exact_tgv",
            "compute_l2norm_bnds", "write_field", "read_field", "julia_float_str", "Plan", "VmkError"]
 
 
@@ -187,6 +187,13 @@ class Common:
         return self._numerical_spectral(self.lib.ps23_numerical, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot,
                                         outdir)
 
+    # ---- 21_NS2D_PseudoSpectral_32_Rule/pseudospectral_32_rule.jl:13-89 ---------------------------
+    def numerical_ps32(self, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
+        """The pseudo-spectral solver's `numerical` (3/2 padding rule): same arguments and return value as
+        numerical_ps23."""
+        return self._numerical_spectral(self.lib.ps32_numerical, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot,
+                                        outdir)
+
     def _numerical_spectral(self, entry, nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot, outdir):
         if ns <= 0 or nt // ns == 0:
             raise ZeroDivisionError("mod(k, nt ÷ ns) with nt ÷ ns == 0")  # Julia: DivideError at hybrid.jl:71
@@ -332,6 +339,10 @@ def numerical_hybrid(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, ou
 
 def numerical_ps23(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
     return _common.numerical_ps23(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot, outdir)
+
+
+def numerical_ps32(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot=None, outdir=None):
+    return _common.numerical_ps32(nx, ny, nt, dx, dy, dt, re, x, y, wn, ns, snapshot, outdir)
 
 
 def numerical_ldc(nx, ny, nt, dx, dy, dt, re, wn, sn, rms):

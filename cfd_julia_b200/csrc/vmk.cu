@@ -23,6 +23,7 @@
 #define vmk_numerical vmke_numerical
 #define vmk_hybrid_numerical vmke_hybrid_numerical
 #define vmk_ps23_numerical vmke_ps23_numerical
+#define vmk_ps32_numerical vmke_ps32_numerical
 #define vmk_print_float64 vmke_print_float64
 #define vmk_write_field vmke_write_field
 #define vmk_read_field vmke_read_field
@@ -58,6 +59,7 @@
 #include "vmk_io.hpp"
 #include "vmk_kernels.cuh"
 #include "vmk_pseudo.cuh"
+#include "vmk_pseudo32.cuh"
 
 using namespace vmk;
 
@@ -94,6 +96,9 @@ struct SizeOps {
   // pseudo-spectral solver, 2/3 rule (vmk_pseudo.cuh); null where kh is
   int (*kp_configure)(int* res);
   int (*kp)(int grid, const KPArgs&, Stream&);
+  // batched row FFT of the 3/2-rule solver (vmk_pseudo32.cuh); null where kh is
+  int (*kx_configure)(int* res);
+  int (*kx)(int grid, const KXArgs&, Stream&);
 };
 
 template <class C>
@@ -115,6 +120,28 @@ struct KHBody {
 template <class C>
 struct KPBody {
   VMK_HD static void run(const Ctx& c, const KPArgs& a) { kp_body<C>(c, a); }
+};
+template <class C>
+struct KXBody {
+  VMK_HD static void run(const Ctx& c, const KXArgs& a) { kx_body<C>(c, a); }
+};
+struct P32Init {
+  VMK_HD static void run(const Ctx& c, const P32Args& a) { p32_init_body(c, a); }
+};
+struct P32Spectra {
+  VMK_HD static void run(const Ctx& c, const P32Args& a) { p32_spectra_body(c, a); }
+};
+struct P32Fold {
+  VMK_HD static void run(const Ctx& c, const P32Args& a) { p32_fold_body(c, a); }
+};
+struct P32Unfold {
+  VMK_HD static void run(const Ctx& c, const P32Args& a) { p32_unfold_body(c, a); }
+};
+struct P32Update {
+  VMK_HD static void run(const Ctx& c, const P32Args& a) { p32_update_body(c, a); }
+};
+struct P32Final {
+  VMK_HD static void run(const Ctx& c, const P32Args& a) { p32_final_body(c, a); }
 };
 struct KPProduct {
   VMK_HD static void run(const Ctx& c, const KPProdArgs& a) { kp_product_body(c, a); }
@@ -255,6 +282,8 @@ SizeOps make_cluster_ops() {
   o.fill_ksqperm = nullptr;
   o.kp_configure = nullptr;
   o.kp = nullptr;
+  o.kx_configure = nullptr;
+  o.kx = nullptr;
   return o;
 }
 
@@ -293,6 +322,8 @@ SizeOps make_ops() {
     o.kh = nullptr;
     o.kp_configure = nullptr;
     o.kp = nullptr;
+    o.kx_configure = nullptr;
+    o.kx = nullptr;
   } else {
     o.kh_configure = [](int* r) -> int { return be_configure<KHBody<C>, KHArgs, C::CT, C::MINB>(C::SMEM_BYTES, r); };
     o.kh = [](int grid, const KHArgs& a, Stream& s) -> int {
@@ -301,6 +332,10 @@ SizeOps make_ops() {
     o.kp_configure = [](int* r) -> int { return be_configure<KPBody<C>, KPArgs, C::CT, C::MINB>(C::SMEM_BYTES, r); };
     o.kp = [](int grid, const KPArgs& a, Stream& s) -> int {
       return be_launch<KPBody<C>, KPArgs, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    };
+    o.kx_configure = [](int* r) -> int { return be_configure<KXBody<C>, KXArgs, C::CT, C::MINB>(C::SMEM_BYTES, r); };
+    o.kx = [](int grid, const KXArgs& a, Stream& s) -> int {
+      return be_launch<KXBody<C>, KXArgs, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
     };
   }
   o.fill_ksqperm = &fill_ccperm<C>;  // the same register-order permutation as the divisor table
@@ -376,6 +411,20 @@ struct vmk_plan {
   double* ptab = nullptr;               // 8 x [N]: mp, mm, cc, dd (natural order), then the same in register order
   double ps_dx = 0;
   int res_kp = 0;
+  // pseudo-spectral solver, 3/2 rule (vmk_ps32_numerical), allocated on first use: an (N/2)^2 plan for the 9 sub-grids of
+  // the padded grid (its K1 / K3 / product kernels and its stream) and the natural-order spectra of vmk_pseudo32.cuh
+  vmk_plan* child = nullptr;
+  double2* qS = nullptr;    // state [L+1][2L+1]
+  double2* qJ = nullptr;
+  double2* qY = nullptr;    // [4][L+1][3][L]
+  double2* qVF = nullptr;   // [4][9][L/2][L]
+  double2* qT9 = nullptr;   // [9][L/2][L]
+  double2* qPi = nullptr;   // [L+1][3][L]
+  double* qF = nullptr;     // [4][9] slabs of the child plan, (L+2) x L each
+  double2* qtw = nullptr;   // [3L]
+  double* qtab = nullptr;   // 5 x [2L+1]
+  double q_dx = 0;
+  int res_kx = 0;
   // lid-driven cavity (vmk_ldc_numerical), allocated on first use: node arrays (n+1)^2 with n = N/2
   double* cw[3] = {nullptr, nullptr, nullptr};  // wn, wtA, wtB
   double* cs = nullptr;                         // sn
@@ -1063,6 +1112,162 @@ int ps23_field(vmk_plan* p, double* ut, double dt, double re) {
   return 0;
 }
 
+// ---- pseudo-spectral solver, 3/2 rule (21_NS2D_PseudoSpectral_32_Rule/pseudospectral_32_rule.jl; vmk_pseudo32.cuh) ----
+int ensure_kx(vmk_plan* p) {
+  if (!p->ops.kx) return fail(VMK_ESIZE, "the 3/2-rule solver supports grids of 64^2 .. 8192^2");
+  if (!p->res_kx) VMK_TRY(p->ops.kx_configure(&p->res_kx));
+  return 0;
+}
+
+int ensure_ps32(vmk_plan* p, double dx) {
+  if (p->nranks != 1) return fail(VMK_EARG, "the pseudo-spectral solver runs on single-GPU plans");
+  if (p->N < 64) return fail(VMK_ESIZE, "the 3/2-rule solver supports grids of 64^2 .. 8192^2");
+  VMK_TRY(ensure_kx(p));
+  const size_t L = (size_t)p->N / 2, W = 2 * L + 1, c2 = sizeof(double2);
+  if (!p->child) {
+    VMK_TRY(vmk_plan_create((int64_t)L, (int64_t)L, &p->child));
+    VMK_TRY(ensure_kx(p->child));
+    VMK_TRY(dev_alloc(p, (void**)&p->qS, c2 * (L + 1) * W));
+    VMK_TRY(dev_alloc(p, (void**)&p->qJ, c2 * (L + 1) * W));
+    VMK_TRY(dev_alloc(p, (void**)&p->qY, c2 * 4 * (L + 1) * 3 * L));
+    VMK_TRY(dev_alloc(p, (void**)&p->qVF, c2 * 36 * (L / 2) * L));
+    VMK_TRY(dev_alloc(p, (void**)&p->qT9, c2 * 9 * (L / 2) * L));
+    VMK_TRY(dev_alloc(p, (void**)&p->qPi, c2 * (L + 1) * 3 * L));
+    VMK_TRY(dev_alloc(p, (void**)&p->qF, sizeof(double) * 36 * (L + 2) * L));
+    VMK_TRY(dev_alloc(p, (void**)&p->qtw, c2 * 3 * L));
+    VMK_TRY(dev_alloc(p, (void**)&p->qtab, sizeof(double) * 5 * W));
+    p->q_dx = 0;
+  }
+  if (p->q_dx != dx) {
+    // jacobian(), pseudospectral_32_rule.jl:96-108: hx = 2 pi/(nx dx), kx[1] = eps, ky = kx; :137-155: the retained modes
+    const int l = (int)L, n = p->N, w = (int)W, m3 = 3 * l;
+    std::vector<double> kap(W), tab(5 * W);
+    const double hx = 2.0 * M_PI / ((double)n * dx);
+    for (int c = 0; c < w; c++) kap[c] = hx * (double)(c - l);
+    kap[l] = 1.e-6;
+    double *ksq = tab.data(), *mp = ksq + W, *mm = mp + W, *cc = mm + W, *dd = cc + W;
+    for (int c = 0; c < w; c++) mp[c] = c < 2 * l ? 1.0 : 0.0;
+    for (int c = 0; c < w; c++) {
+      ksq[c] = kap[c] * kap[c];
+      mm[c] = mp[2 * l - c];
+      cc[c] = kap[c] * mp[c] * .5;
+      dd[c] = -kap[2 * l - c] * mm[c] * .5;
+    }
+    std::vector<double2> tw(m3);
+    const long double tau = 6.283185307179586476925286766559005768L;
+    for (int e = 0; e < m3; e++) {
+      const long double ang = tau * (long double)e / (long double)m3;
+      tw[e].x = (double)cosl(ang);
+      tw[e].y = (double)(-sinl(ang));
+    }
+    VMK_TRY(be_sync(p->st));
+    VMK_TRY(be_sync(p->child->st));
+    VMK_TRY(be_h2d(p->qtab, tab.data(), sizeof(double) * 5 * W, p->st));
+    VMK_TRY(be_h2d(p->qtw, tw.data(), c2 * m3, p->st));
+    VMK_TRY(be_sync(p->st));
+    p->q_dx = dx;
+  }
+  return 0;
+}
+
+// batched row FFT on plan q's stream (natural order, in place allowed)
+int launch_kx(vmk_plan* q, const double2* in, double2* out, int nrows, int inverse) {
+  KXArgs a;
+  a.in = in;
+  a.out = out;
+  a.tw = q->tw;
+  a.nrows = nrows;
+  a.inverse = inverse;
+  const int work = (nrows + q->ops.fpc - 1) / q->ops.fpc;
+  VMK_TRY(q->ops.kx(work < q->res_kx ? work : q->res_kx, a, q->st));
+  q->launches++;
+  return 0;
+}
+
+template <class Body>
+int launch_p32(vmk_plan* q, const P32Args& a, size_t items) {
+  size_t want = (items + kK5Threads - 1) / kK5Threads;
+  const size_t cap = (size_t)q->sms * 16;
+  const int grid = (int)(want < cap ? want : cap);
+  VMK_TRY((be_launch<Body, P32Args, kK5Threads, 4>(grid < 1 ? 1 : grid, 0, a, q->st)));
+  q->launches++;
+  return 0;
+}
+
+P32Args p32_args(vmk_plan* p, int stage, double dt, double re) {
+  static const double alpha[4] = {0.0, 8. / 15., 2. / 15., 1. / 3.};
+  static const double gamma[4] = {0.0, 8. / 15., 5. / 12., 3. / 4.};
+  static const double rho[4] = {0.0, 0.0, -17. / 60., -5. / 12.};
+  const size_t W = (size_t)p->N + 1;
+  P32Args a;
+  a.L = p->N / 2;
+  a.twM = p->qtw;
+  a.ksq = p->qtab;
+  a.mp = p->qtab + W;
+  a.mm = p->qtab + 2 * W;
+  a.cc = p->qtab + 3 * W;
+  a.dd = p->qtab + 4 * W;
+  a.S = p->qS;
+  a.J = p->qJ;
+  a.Y = p->qY;
+  a.VF = p->qVF;
+  a.T9 = p->qT9;
+  a.Pi = p->qPi;
+  a.Xn = p->V;
+  a.Un = p->T;
+  a.zfac = .5 * dt / re;
+  a.alpha = alpha[stage];
+  a.gdt = gamma[stage] * dt;
+  a.rdt = rho[stage] * dt;
+  a.scale = 1.0 / (2.0 * (double)p->N * (double)p->N);
+  a.stage = stage;
+  return a;
+}
+
+// one RK3 stage on the child plan's stream
+int ps32_stage(vmk_plan* p, int stage, double dt, double re) {
+  vmk_plan* ch = p->child;
+  const size_t L = (size_t)p->N / 2, slab = (L + 2) * L, blk = (L / 2) * L;
+  const P32Args a = p32_args(p, stage, dt, re);
+  VMK_TRY(launch_p32<P32Spectra>(ch, a, (L + 1) * L));                    // i k wf [/ k2], folded along j   :113-155
+  VMK_TRY(launch_kx(ch, p->qY, p->qY, (int)(12 * (L + 1)), 1));           // ifft along j (3 sub-rows each)  :157-160
+  VMK_TRY(launch_p32<P32Fold>(ch, a, 4 * 3 * (L / 2) * L));               // folded along i
+  for (int q = 0; q < 4; q++)
+    for (int sub = 0; sub < 9; sub++)                                      // ifft along i, 9 sub-grids per field
+      VMK_TRY(launch_k3_rows(ch, p->qVF + (size_t)(q * 9 + sub) * blk, p->qF + (size_t)(q * 9 + sub) * slab));
+  double2* child_T = ch->T;
+  int rc = 0;
+  for (int sub = 0; sub < 9 && !rc; sub++) {
+    double* f1 = p->qF + (size_t)sub * slab;
+    rc = launch_kp_product(ch, f1, p->qF + (size_t)(9 + sub) * slab, p->qF + (size_t)(18 + sub) * slab,
+                           p->qF + (size_t)(27 + sub) * slab);            // j1 j2 - j3 j4                   :163-166
+    if (rc) break;
+    ch->T = p->qT9 + (size_t)sub * blk;
+    rc = launch_k1(ch, f1);                                                // fft along i                     :168
+  }
+  ch->T = child_T;
+  VMK_TRY(rc);
+  VMK_TRY(launch_p32<P32Unfold>(ch, a, (L + 1) * 3 * L));                 // unfolded along i, x nx ny/(nxe nye)  :176
+  VMK_TRY(launch_kx(ch, p->qPi, p->qPi, (int)(3 * (L + 1)), 0));          // fft along j
+  VMK_TRY(launch_p32<P32Update>(ch, a, (L + 1) * (2 * L + 1)));           // unfolded along j + the RK3/CN update  :41-66
+  return 0;
+}
+
+// ut = real(ifft(wnf)) on the nx x ny grid with the periodic duplicates (:71-76), on the parent plan's stream
+int ps32_field(vmk_plan* p, double* ut, double dt, double re) {
+  const size_t N = (size_t)p->N, n1 = N + 1;
+  VMK_TRY(be_sync(p->child->st));
+  const P32Args a = p32_args(p, 0, dt, re);
+  VMK_TRY(launch_p32<P32Final>(p, a, (N / 2) * N));
+  VMK_TRY(launch_kx(p, p->T, p->V, (int)(N / 2), 1));
+  VMK_TRY(launch_k3_rows(p, p->V, p->w[1]));
+  VMK_TRY(be_d2h_2d(ut, sizeof(double) * n1, p->w[1] + N, sizeof(double) * N, sizeof(double) * N, N, p->st));
+  VMK_TRY(be_sync(p->st));
+  for (size_t j = 0; j < N; j++) ut[N + j * n1] = ut[j * n1];
+  memcpy(ut + N * n1, ut, sizeof(double) * n1);
+  return 0;
+}
+
 int check_plan(vmk_plan* p) {
   if (!p) return fail(VMK_EARG, "plan is NULL");
   VMK_TRY(be_set_device(p->device));  // a host thread may drive several plans on different devices
@@ -1241,6 +1446,16 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_free(p->hVs);
   be_free(p->hksq);
   be_free(p->hksqperm);
+  if (p->child) vmk_plan_destroy(p->child);
+  be_free(p->qS);
+  be_free(p->qJ);
+  be_free(p->qY);
+  be_free(p->qVF);
+  be_free(p->qT9);
+  be_free(p->qPi);
+  be_free(p->qF);
+  be_free(p->qtw);
+  be_free(p->qtab);
   be_free(p->pV[0]);
   be_free(p->pV[1]);
   be_free(p->pA0);
@@ -1527,6 +1742,38 @@ int vmk_ps23_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt,
   VMK_TRY(ps23_field(p, ut, dt, re));
   if (snap && freq > 0 && nt > 0 && nt % freq == 0) snap(nt, ut, user);
   p->uploaded = false;  // w[0..2], psi were used as scratch
+  return VMK_OK;
+}
+
+int vmk_ps32_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
+                       double* ut, int64_t freq, vmk_snapshot_fn snap, void* user) {
+  VMK_TRY(check_plan(p));
+  if (!wn || !ut) return fail(VMK_EARG, "wn or ut is NULL");
+  if (nt < 0) return fail(VMK_EARG, "nt < 0");
+  if (dx != dy) return fail(VMK_EARG, "the pseudo-spectral solver needs dx == dy (wavespace aliases ky = kx, Common.jl:197)");
+  VMK_TRY(ensure_ps32(p, dx));
+  const size_t L = (size_t)p->N / 2;
+  const int64_t child_launches0 = p->child->launches;
+  VMK_TRY(upload_ghosted(p, wn, p->w[0]));
+  VMK_TRY(be_event_record(p->ev0, p->st));
+  VMK_TRY(launch_k1(p, p->w[0]));                               // wnf = fft(data), nx x ny   :24
+  VMK_TRY(launch_kx(p, p->T, p->V, (int)L, 0));
+  VMK_TRY(launch_p32<P32Init>(p, p32_args(p, 0, dt, re), (L + 1) * (2 * L + 1)));  // -> S, wnf[1,1] = 0  :27
+  VMK_TRY(be_sync(p->st));
+  for (int64_t k = 1; k <= nt; k++) {
+    for (int stage = 1; stage <= 3; stage++) VMK_TRY(ps32_stage(p, stage, dt, re));
+    if (snap && freq > 0 && k % freq == 0 && k != nt) {  // :69-86 (the final field is produced below)
+      VMK_TRY(ps32_field(p, ut, dt, re));
+      snap(k, ut, user);
+    }
+  }
+  VMK_TRY(be_sync(p->child->st));
+  VMK_TRY(be_event_record(p->ev1, p->st));
+  p->ev_valid = true;
+  VMK_TRY(ps32_field(p, ut, dt, re));
+  if (snap && freq > 0 && nt > 0 && nt % freq == 0) snap(nt, ut, user);
+  p->launches += p->child->launches - child_launches0;
+  p->uploaded = false;  // w[0..1], T, V were used as scratch
   return VMK_OK;
 }
 

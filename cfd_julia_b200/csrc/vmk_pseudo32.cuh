@@ -1,0 +1,297 @@
+// vmk_pseudo32.cuh -- the pseudo-spectral solver with the 3/2 padding rule
+// (21_NS2D_PseudoSpectral_32_Rule/pseudospectral_32_rule.jl:13-177).
+//
+// jacobian() (:95-177) zero-pads the four derivative spectra from nx x ny to M x M, M = 1.5 nx, takes real(ifft) on the
+// padded grid, multiplies in real space and transforms back, keeping the nx x ny modes.  M = 3 L with L = nx/2 a power
+// of two, so every M-point transform is split radix-3 into three L-point transforms -- and because real space is only
+// ever used for a pointwise product, the three (per direction) interleaved sub-grids  x = 2 pi (3 px + rx) / M,
+// rx = 0, 1, 2,  never have to be interleaved: real space is kept as 9 independent L x L sub-grids, transformed by the
+// finite-difference path's own K1 / K3 (an L x L plan inside the plan), and the radix-3 butterflies become elementwise
+// "fold" / "unfold" passes over the spectra with the twiddles w^m = exp(-2 pi i m / M):
+//   inverse, one direction:  u[3p + r] = sum_{k' < L} ( sum_{k = k' mod L} U[k] w^{-k r} ) exp(+2 pi i k' p / L)
+//   forward, one direction:  X[k]      = sum_r w^{k r} ( sum_p x[3p + r] exp(-2 pi i (k mod L) p / L) )
+// The retained modes are k in -L .. L-1 per direction (:137-155) -- not a symmetric set -- and real(ifft(.)) keeps the
+// Hermitian part, exactly as in the 2/3 rule (vmk_pseudo.cuh).  The state is therefore held on the symmetric set
+//   S[kx][ky],  kx = 0 .. L,  ky = -L .. L  (column c = ky + L),   S = 2 x wf[kx,ky] if (kx,ky) is a retained mode,
+//                                                                  else 2 x conj(wf[-kx,-ky])  ((L,-L): neither, 0),
+// which the per-mode RK3 / Crank-Nicolson update (:41-66; real, even coefficients) maps onto itself, with the weights
+// Dx, Dy of vmk_pseudo.cuh built from the indicator of the retained set.  Unlike the 2/3 rule the Nyquist lines carry
+// an O(1) non-Hermitian part here (jf[-L, ky] is taken from the padded spectrum's mode -L alone, :171-174); the final
+// field real(ifft(wnf)) on the nx x ny grid (:71) folds +L and -L back together (p32_final_body).
+//
+// One stage = E1 spectra -> KX (12 (L+1) inverse L-point rows, in place) -> E2 fold along i -> 36 x K3_L -> 9 products
+// -> 9 x K1_L -> E3 unfold along i -> KX (3 (L+1) forward rows, in place) -> E4 unfold along j + mode update.
+// Every pass works in natural index order on global memory: a deliberately plain first version (many passes over the
+// spectra, scattered stores in KX) whose arithmetic was fixed first as a numpy model (tools/ps32_model.py, 3e-16
+// against the literal restatement of the script with white-noise input); fusing E1/E4 into the row transforms the way
+// KP does for the 2/3 rule is the obvious next step.
+#pragma once
+#include "vmk_kernels.cuh"
+
+namespace vmk {
+
+// ---- batched complex FFT along contiguous rows, natural order in and out (in place allowed) ----------------------
+struct KXArgs {
+  const double2* in;   // [nrows][N]
+  double2* out;        // [nrows][N]
+  const double2* tw;
+  int nrows;
+  int inverse;         // 0: sum x exp(-2 pi i k n / N), 1: sum X exp(+2 pi i k n / N) (both unnormalised)
+};
+
+template <class C>
+VMK_HD void kx_body(const Ctx& c, const KXArgs& a) {
+  using F = Fft<C>;
+  constexpr int N = C::N, E = C::E, T = C::T, P = C::P;
+  constexpr int bl = C::bits(P - 1), rl = 1 << bl;
+  static_assert(!C::SPLIT, "kx_body uses the plain exchange buffer");
+  double2* tw = F::tables(c.smem);
+  F::load_tables(c, tw, a.tw);
+  c.sync();
+  const int g = c.tid / T, t = c.tid % T;
+  double2* sm = F::xbuf(c.smem, g);
+  const int nblocks = (a.nrows + C::FPC - 1) / C::FPC;
+  for (int rb = c.bid; rb < nblocks; rb += c.nblk) {
+    const int row = rb * C::FPC + g;
+    const bool active = row < a.nrows;
+    // a transform slot past the last row redoes the last row and discards the result: its loads and barriers are then
+    // unconditional (no thread-varying branch around the barriers for a compiler to specialise), only the store is not
+    const size_t roff = (size_t)(active ? row : a.nrows - 1) * N;
+    double2 v[E];
+    if (a.inverse) {
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value, u = e / rl, p = e % rl;
+        const int k = F::k_of_pos(((t + T * u) << bl) | p);
+        v[e] = a.in[roff + k];
+      });
+      c.sync();  // the previous row's last exchange has been read everywhere
+      F::inverse(c, v, sm, tw, t);
+      if (active) {
+        static_for<0, E>([&](auto e_) {
+          constexpr int e = decltype(e_)::value;
+          a.out[roff + F::template own_pos<e>(t)] = v[e];
+        });
+      }
+    } else {
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        v[e] = a.in[roff + F::template own_pos<e>(t)];
+      });
+      c.sync();
+      F::forward(c, v, sm, tw, t);
+      if (active) {
+        static_for<0, E>([&](auto e_) {
+          constexpr int e = decltype(e_)::value, u = e / rl, p = e % rl;
+          a.out[roff + F::k_of_pos(((t + T * u) << bl) | p)] = v[e];
+        });
+      }
+    }
+  }
+}
+
+// ---- elementwise passes -------------------------------------------------------------------------------------------
+struct P32Args {
+  int L;                 // nx / 2; M = 3 L, N = 2 L
+  const double2* twM;    // [3L] w^m = exp(-2 pi i m / M)
+  const double* ksq;     // [2L+1] by column c = k + L: k[k]^2 (k[0] = eps, :107; +-L: (L hx)^2)
+  const double* mp;      //        1 if k is retained (-L .. L-1)
+  const double* mm;      //        mp(-k)
+  const double* cc;      //        k[k] mp(k) / 2
+  const double* dd;      //        -k[-k] mp(-k) / 2
+  double2* S;            // [L+1][2L+1] state
+  double2* J;            // [L+1][2L+1] previous stage's jf
+  double2* Y;            // [4][L+1][3][L]: E1 output, transformed in place by KX, E2 input
+  double2* VF;           // [4][3 rx][3 ry][L/2][L]: K3_L inputs
+  const double2* T9;     // [3 rx][3 ry][L/2][L]: K1_L outputs
+  double2* Pi;           // [L+1][3][L]: E3 output, transformed in place by KX, E4 input
+  const double2* Xn;     // init:  [L][N] forward-j of K1_N(w0) (row 0 packed), natural order
+  double2* Un;           // final: [L][N] N-grid half spectrum (row 0 packed), natural order
+  double zfac;           // .5 dt / re
+  double alpha, gdt, rdt;
+  double scale;          // 1 / (2 N^2)
+  int stage;
+};
+
+VMK_HD size_t p32_begin(const Ctx& c) { return (size_t)c.bid * kK5Threads + c.tid; }
+VMK_HD size_t p32_stride(const Ctx& c) { return (size_t)c.nblk * kK5Threads; }
+
+// E0: S <- the nx x ny spectrum of the initial field (pseudospectral_32_rule.jl:24-27), J <- 0
+VMK_HD void p32_init_body(const Ctx& c, const P32Args& a) {
+  const int L = a.L, N = 2 * L, W = 2 * L + 1;
+  const size_t total = (size_t)(L + 1) * W;
+  for (size_t q = p32_begin(c); q < total; q += p32_stride(c)) {
+    const int kx = (int)(q / W), col = (int)(q % W), ky = col - L;
+    const int n = (ky + N) % N, nm = (N - ky) % N;
+    double2 s;
+    if (kx >= 1 && kx < L) {
+      s = a.Xn[(size_t)kx * N + n];
+    } else {
+      // packed row X = A + i B (A: kx = 0, B: kx = -L): A[ky] = (X[ky] + conj X[-ky]) / 2, B[ky] = (X[ky] - conj X[-ky]) / 2i
+      const double2 x = a.Xn[n], xm = a.Xn[nm];
+      if (kx == 0) {
+        s = mk2(.5 * (x.x + xm.x), .5 * (x.y - xm.y));
+        if (col == 2 * L) s = cconj(s);
+      } else {
+        // S[L][ky] = conj(B[-ky]),  B[-ky] = (X[-ky] - conj X[ky]) / 2i
+        const double2 bm = mk2(.5 * (xm.y + x.y), .5 * (x.x - xm.x));
+        s = cconj(bm);
+        if (col == 0) s = mk2(0.0, 0.0);
+      }
+    }
+    if (kx == 0 && col == L) s = mk2(0.0, 0.0);  // wf[1,1] = 0 (:27)
+    a.S[q] = s;
+    a.J[q] = mk2(0.0, 0.0);
+  }
+}
+
+// the four derivative spectra of one mode (:113-122 with the Hermitian-part weights), scaled by 1 / (2 N^2)
+VMK_HD void p32_mode(const P32Args& a, int kxc, int col, double2 s, double2* g) {
+  const double k2 = ld_ro(a.ksq + kxc) + ld_ro(a.ksq + col);
+  const double dx = ld_ro(a.cc + kxc) * ld_ro(a.mp + col) + ld_ro(a.dd + kxc) * ld_ro(a.mm + col);
+  const double dy = ld_ro(a.mp + kxc) * ld_ro(a.cc + col) + ld_ro(a.mm + kxc) * ld_ro(a.dd + col);
+  const double fx = dx * a.scale, fy = dy * a.scale, r = 1.0 / k2;
+  const double2 is = mk2(-s.y, s.x);  // i S
+  g[0] = cscale(is, fx * r);          // j1f = i kx wf / k2
+  g[1] = cscale(is, fy);              // j2f = i ky wf
+  g[2] = cscale(is, fy * r);          // j3f = i ky wf / k2
+  g[3] = cscale(is, fx);              // j4f = i kx wf
+}
+
+// E1: Y[q][kx][ry][ky'] = sum over ky = ky' mod L of G_q[kx][ky] w^{-ky ry}
+VMK_HD void p32_spectra_body(const Ctx& c, const P32Args& a) {
+  const int L = a.L, M = 3 * L, W = 2 * L + 1;
+  const size_t total = (size_t)(L + 1) * L;
+  for (size_t id = p32_begin(c); id < total; id += p32_stride(c)) {
+    const int kx = (int)(id / L), kp = (int)(id % L), kxc = kx + L;
+    const double2* srow = a.S + (size_t)kx * W;
+    double2 ga[4], gb[4], ge[4];
+    p32_mode(a, kxc, kp + L, srow[kp + L], ga);  // ky = ky'
+    p32_mode(a, kxc, kp, srow[kp], gb);          // ky = ky' - L
+    if (kp == 0) p32_mode(a, kxc, 2 * L, srow[2 * L], ge);  // ky = +L
+    for (int ry = 0; ry < 3; ry++) {
+      const double2 wa = ld_ro2(a.twM + (M - kp * ry) % M);      // w^{-ky' ry}
+      const double2 wb = ld_ro2(a.twM + (L - kp) * ry);          // w^{-(ky'-L) ry}
+      const double2 we = ld_ro2(a.twM + (M - L * ry) % M);       // w^{-L ry}
+      for (int q = 0; q < 4; q++) {
+        double2 y = cadd(cmul(ga[q], wa), cmul(gb[q], wb));
+        if (kp == 0) y = cadd(y, cmul(ge[q], we));
+        a.Y[(((size_t)q * (L + 1) + kx) * 3 + ry) * L + kp] = y;
+      }
+    }
+  }
+}
+
+// E2: fold along i.  VF[q][rx][ry][kx'][py] = sum over kx = kx' mod L (Hermitian completion in kx) of V w^{-kx rx};
+// row kx' = 0 packs the (real) kx' = 0 and kx' = L/2 lines as K3 expects
+VMK_HD void p32_fold_body(const Ctx& c, const P32Args& a) {
+  const int L = a.L, M = 3 * L, h = L / 2;
+  const size_t total = (size_t)4 * 3 * h * L;
+  for (size_t id = p32_begin(c); id < total; id += p32_stride(c)) {
+    const int py = (int)(id % L);
+    size_t r = id / L;
+    const int kp = (int)(r % h);
+    r /= h;
+    const int ry = (int)(r % 3), q = (int)(r / 3);
+    auto V = [&](int kx) { return a.Y[(((size_t)q * (L + 1) + kx) * 3 + ry) * L + py]; };
+    for (int rx = 0; rx < 3; rx++) {
+      double2 y;
+      if (kp == 0) {
+        const double2 v0 = V(0), vl = V(L), vh = V(h);
+        const double2 tl = cmul(vl, ld_ro2(a.twM + (M - L * rx) % M));  // V[L] w^{-L rx}; its conjugate is the -L term
+        const double2 th = cmul(vh, ld_ro2(a.twM + (M - h * rx) % M));  // V[L/2] w^{-(L/2) rx}; conjugate: kx = -L/2
+        y = mk2(v0.x + (tl.x + tl.x), th.x + th.x);
+      } else {
+        const double2 v1 = V(kp), v2 = cconj(V(L - kp));
+        y = cadd(cmul(v1, ld_ro2(a.twM + (M - kp * rx) % M)), cmul(v2, ld_ro2(a.twM + (L - kp) * rx)));
+      }
+      a.VF[((((size_t)q * 3 + rx) * 3 + ry) * h + kp) * L + py] = y;
+    }
+  }
+}
+
+// E3: unfold along i.  Pi[kx][ry][py] = (4/9) sum_rx w^{kx rx} T_rx[kx mod L][ry][py]   (N^2 / M^2 = 4/9, :176)
+VMK_HD void p32_unfold_body(const Ctx& c, const P32Args& a) {
+  const int L = a.L, h = L / 2;
+  const size_t total = (size_t)(L + 1) * 3 * L;
+  for (size_t id = p32_begin(c); id < total; id += p32_stride(c)) {
+    const int py = (int)(id % L);
+    const size_t r = id / L;
+    const int ry = (int)(r % 3), kx = (int)(r / 3), kk = kx % L;
+    double2 acc = mk2(0.0, 0.0);
+    for (int rx = 0; rx < 3; rx++) {
+      const double2* blk = a.T9 + (size_t)(rx * 3 + ry) * h * L;
+      double2 tv;
+      if (kk == 0) {
+        tv = mk2(blk[py].x, 0.0);
+      } else if (kk == h) {
+        tv = mk2(blk[py].y, 0.0);
+      } else if (kk < h) {
+        tv = blk[(size_t)kk * L + py];
+      } else {
+        tv = cconj(blk[(size_t)(L - kk) * L + py]);
+      }
+      acc = cadd(acc, cmul(tv, ld_ro2(a.twM + kx * rx)));
+    }
+    a.Pi[id] = cscale(acc, 4.0 / 9.0);
+  }
+}
+
+// E4: unfold along j, jf[kx][ky] = sum_ry w^{ky ry} Q[kx][ry][ky mod L], and the RK3 / Crank-Nicolson update (:41-66)
+VMK_HD void p32_update_body(const Ctx& c, const P32Args& a) {
+  const int L = a.L, M = 3 * L, W = 2 * L + 1;
+  const size_t total = (size_t)(L + 1) * W;
+  for (size_t id = p32_begin(c); id < total; id += p32_stride(c)) {
+    const int kx = (int)(id / W), col = (int)(id % W), ky = col - L;
+    const int km = (ky + 2 * L) % L;
+    double2 pf = mk2(0.0, 0.0);
+    for (int ry = 0; ry < 3; ry++) {
+      const int e = ((ky * ry) % M + M) % M;
+      pf = cadd(pf, cmul(a.Pi[((size_t)kx * 3 + ry) * L + km], ld_ro2(a.twM + e)));
+    }
+    const double k2 = ld_ro(a.ksq + kx + L) + ld_ro(a.ksq + col);
+    const double d = a.alpha * (a.zfac * k2);
+    const double g = 1.0 / (1.0 + d), cf = (1.0 - d) * g;
+    double2 y = cscale(pf, a.gdt);
+    if (a.stage >= 2) {
+      const double2 jp = a.J[id];
+      y = mk2(fma_(a.rdt, jp.x, y.x), fma_(a.rdt, jp.y, y.y));
+    }
+    if (a.stage == 1 || a.stage == 2) a.J[id] = pf;
+    const double2 s = a.S[id];
+    double2 sn = mk2(fma_(cf, s.x, g * y.x), fma_(cf, s.y, g * y.y));
+    if (kx == L && col == 0) sn = mk2(0.0, 0.0);                  // (L, -L): neither it nor its mirror is retained
+    if (kx == 0 && col == L && a.stage != 3) sn = mk2(0.0, 0.0);  // w1f[1,1] = w2f[1,1] = 0 (:47,58)
+    a.S[id] = sn;
+  }
+}
+
+// E5: the nx x ny half spectrum of real(ifft(wnf)) (:71): the Hermitian part on the N grid, where +L and -L coincide
+VMK_HD void p32_final_body(const Ctx& c, const P32Args& a) {
+  const int L = a.L, N = 2 * L, W = 2 * L + 1;
+  const size_t total = (size_t)L * N;
+  const double inv = 1.0 / ((double)N * (double)N);
+  for (size_t id = p32_begin(c); id < total; id += p32_stride(c)) {
+    const int kx = (int)(id / N), n = (int)(id % N), ky = n < L ? n : n - N;  // ky in -L .. L-1
+    const int col = ky + L, colm = L - ky;
+    double2 u;
+    if (kx >= 1) {
+      const double2* s = a.S + (size_t)kx * W;
+      u = ky != -L ? cscale(s[col], .5) : cscale(cadd(s[0], s[2 * L]), .25);
+    } else {
+      const double2* s0 = a.S;
+      const double2* sl = a.S + (size_t)L * W;
+      double2 u0, ul;
+      if (ky != -L) {
+        u0 = cscale(cadd(s0[col], cconj(s0[colm])), .25);
+        ul = cscale(cadd(cconj(sl[colm]), sl[col]), .25);
+      } else {
+        u0 = mk2(.5 * s0[0].x, 0.0);
+        ul = mk2(.5 * sl[2 * L].x, 0.0);
+      }
+      u = mk2(u0.x - ul.y, u0.y + ul.x);  // U[0] + i U[Nyquist]
+    }
+    a.Un[id] = cscale(u, inv);
+  }
+}
+
+}  // namespace vmk

@@ -113,6 +113,14 @@ int vmk_hybrid_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, doubl
 int vmk_ps23_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
                        double* ut, int64_t freq, vmk_snapshot_fn snap, void* user);
 
+/* numerical(nx,ny,nt,dx,dy,dt,re,x,y,wn,ns)  21_NS2D_PseudoSpectral_32_Rule/pseudospectral_32_rule.jl:13-89 -- the pseudo-
+ * spectral solver with the 3/2 padding rule: as vmk_ps23_numerical, but jacobian() (:95-177) zero-pads the four spectra
+ * to 1.5nx x 1.5ny, multiplies on that grid and keeps the nx x ny modes of the product's transform.  The 1.5nx-point
+ * transforms run as radix-3 splits into nx/2-point transforms (csrc/vmk_pseudo32.cuh).  Same arguments and contract as
+ * vmk_ps23_numerical.  Single-GPU plans, nx == ny in [64, 8192], dx == dy. */
+int vmk_ps32_numerical(vmk_plan* plan, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
+                       double* ut, int64_t freq, vmk_snapshot_fn snap, void* user);
+
 /* numerical(nx,ny,nt,dx,dy,dt,re,wn,sn,rms)  18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl:59-117 -- lid-driven cavity:
  * RK3, the Arakawa/Laplacian rhs without periodic wrap (:123-158), Jensen wall vorticity bc2 (:38-52) and the sine-
  * transform Poisson solve fps_sine (:11-21, FFTW RODFT00).  wn, sn: (nx+1) x (ny+1) node arrays, both mutated in place

@@ -16,7 +16,7 @@
 # the same ABI is exercised in CI through ctypes (cfd_julia_b200/common.py), which this file mirrors line by line.
 module CommonB200
 
-export fps, vm_rhs, numerical, numerical_hybrid, numerical_ps23, numerical_ldc, write_field, read_field, ps_fft
+export fps, vm_rhs, numerical, numerical_hybrid, numerical_ps23, numerical_ps32, numerical_ldc, write_field, read_field, ps_fft
 export vmk_plan, vmk_upload, vmk_step, vmk_download, vmk_plans_multi, numerical_multi
 
 const libvmk = get(ENV, "VMK_LIB", joinpath(@__DIR__, "..", "cfd_julia_b200", "libvmk.so"))
@@ -112,11 +112,12 @@ numerical(nx, ny, nt, Δx, Δy, Δt, re, wn::Matrix{Float64}) = begin
 end
 
 # hybrid.jl flavour (20_NS2D_Hybrid_Solver/hybrid.jl:14-90): RK3 / Crank-Nicolson in Fourier space, and the pseudo-spectral
-# solver with the 2/3 rule (22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl:13-89): same time loop, spectral
-# Jacobian.  Same arguments as vm.jl's numerical; wn is only read; returns ut = real(ifft(wf)) with the periodic
+# solvers with the 2/3 rule (22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl:13-89) and the 3/2 rule
+# (21_NS2D_PseudoSpectral_32_Rule/pseudospectral_32_rule.jl:13-89): same time loop, spectral Jacobian.  Same arguments as vm.jl's numerical; wn is only read; returns ut = real(ifft(wf)) with the periodic
 # duplicates, (nx+1) x (ny+1), and writes "vm<m>.txt" every nt ÷ ns steps (hybrid.jl:71-86) through the library's writer
 # (byte-identical to the scripts' `write(io, "$(x[i]) $(y[j]) $(ut[i, j])\n")` loop, minutes faster at 8192^2).
-for (jlname, csym) in ((:numerical_hybrid, :vmk_hybrid_numerical), (:numerical_ps23, :vmk_ps23_numerical))
+for (jlname, csym) in ((:numerical_hybrid, :vmk_hybrid_numerical), (:numerical_ps23, :vmk_ps23_numerical),
+                       (:numerical_ps32, :vmk_ps32_numerical))
   @eval $jlname(nx, ny, nt, Δx, Δy, Δt, re, x, y, wn::Matrix{Float64}, ns) = begin
     ghosted(wn, nx, ny, "wn")
     freq = nt ÷ ns

@@ -165,17 +165,19 @@ def check_hybrid(cm, onp, n, nt, dt=None, re=1000., ns=1, tol=TOL_RUN):
     return ut
 
 
-def check_ps23(cm, onp, n, nt, dt=None, re=1000., ns=1, tol=TOL_RUN, noise=0.05):
-    """22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl `numerical` against the literal numpy restatement
-    (oracle_np.ps_numerical, full complex spectra, numpy's C2C transforms).  The noisy start puts energy into every
-    mode, including the half-weighted mode -K at the edge of the (asymmetric) retained band and the Nyquist lines."""
+def check_ps23(cm, onp, n, nt, dt=None, re=1000., ns=1, tol=TOL_RUN, noise=0.05, rule=23):
+    """22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl (rule=23) or 21_NS2D_PseudoSpectral_32_Rule/
+    pseudospectral_32_rule.jl (rule=32) `numerical` against the literal numpy restatement (oracle_np.ps_numerical, full
+    complex spectra, numpy's C2C transforms, 1.5n-point transforms for the 3/2 rule).  The noisy start puts energy into
+    every mode, including the half-weighted mode at the edge of the (asymmetric) retained band and the Nyquist lines."""
     dx, dy, x, y = grid(n)
     w = vm_field(n) + noise * noise_field(n, 5)
     dt = stable_dt(n, re) if dt is None else dt
     wb = w.copy(order="F")
     snaps_ref, snaps = [], []
-    ref = onp.ps_numerical(23, n, n, nt, dx, dy, dt, re, w, nt // ns, lambda k, ut: snaps_ref.append((k, ut.copy())))
-    ut = cm.numerical_ps23(n, n, nt, dx, dy, dt, re, x, y, w, ns, snapshot=lambda k, u: snaps.append((k, u.copy())))
+    ref = onp.ps_numerical(rule, n, n, nt, dx, dy, dt, re, w, nt // ns, lambda k, ut: snaps_ref.append((k, ut.copy())))
+    numerical = cm.numerical_ps23 if rule == 23 else cm.numerical_ps32
+    ut = numerical(n, n, nt, dx, dy, dt, re, x, y, w, ns, snapshot=lambda k, u: snaps.append((k, u.copy())))
     assert ut.shape == (n + 1, n + 1) and np.array_equal(w, wb)  # wn is only read (:22)
     assert rel_l2(ut, ref) < tol
     assert np.array_equal(ut[n, :], ut[0, :]) and np.array_equal(ut[:, n], ut[:, 0])  # :73-76
@@ -184,6 +186,10 @@ def check_ps23(cm, onp, n, nt, dt=None, re=1000., ns=1, tol=TOL_RUN, noise=0.05)
     for (_, a), (_, b) in zip(snaps, snaps_ref):
         assert rel_l2(a, b) < tol
     return ut
+
+
+def check_ps32(cm, onp, n, nt, **kw):
+    return check_ps23(cm, onp, n, nt, rule=32, **kw)
 
 
 def check_ldc(cm, onp, n, nt, dt=None, re=100., from_rest=False, tol=TOL_RUN):

@@ -120,6 +120,30 @@ def test_pseudospectral_23_rule_defaults_60_steps(emul, oracle_np):
     pc.check_ps23(emul, oracle_np, 128, 60, dt=.01, ns=3, noise=0.)
 
 
+@pytest.mark.parametrize("n,nt,ns,noise", [(64, 6, 3, 1.), (128, 3, 1, 1.), (256, 2, 2, .5), (512, 2, 1, .05), (1024, 1, 1, .05)])
+def test_pseudospectral_32_rule(emul, oracle_np, n, nt, ns, noise):
+    """pseudospectral_32_rule.jl -- the 1.5n-point transforms as radix-3 splits into n/2-point ones on
+    9 sub-grids (vmk_pseudo32.cuh) against the literal numpy restatement (numpy does the 1.5n-point transforms directly)"""
+    pc.check_ps32(emul, oracle_np, n, nt, dt=1e-3 if noise >= .5 else None, ns=ns, noise=noise)
+    emul.clear_plans()
+
+
+def test_pseudospectral_32_rule_defaults_40_steps(emul, oracle_np):
+    """the script's own configuration (128^2, dt = .01, Re = 1000, vm_ic), its first 40 steps, snapshots every 20"""
+    pc.check_ps32(emul, oracle_np, 128, 40, dt=.01, ns=2, noise=0.)
+
+
+def test_pseudospectral_32_rule_errors(emul):
+    from cfd_julia_b200.common import VmkError
+    dx, dy, x, y = grid(32)
+    with pytest.raises(VmkError) as e:  # the sub-grids are (n/2)^2 and the smallest transform is 32 points
+        emul.numerical_ps32(32, 32, 1, dx, dy, .01, 1000., x, y, vm_field(32), 1)
+    assert e.value.code == 1
+    dx, dy, x, y = grid(64)
+    with pytest.raises(VmkError):
+        emul.numerical_ps32(64, 64, 1, dx, 2 * dy, .01, 1000., x, y, vm_field(64), 1)
+
+
 def test_pseudospectral_errors(emul):
     from cfd_julia_b200.common import Plan, VmkError
     n = 64
@@ -140,6 +164,7 @@ def test_pseudospectral_errors(emul):
 def test_pseudospectral_then_finite_difference(emul, oracle_c, oracle_np):
     """the solvers share buffers and tables inside one plan: interleaving them must not disturb either"""
     pc.check_ps23(emul, oracle_np, 64, 2)
+    pc.check_ps32(emul, oracle_np, 64, 2)
     pc.check_numerical(emul, oracle_c, vm_field(64), 3, .01, 1000.)
     pc.check_hybrid(emul, oracle_np, 64, 2)
     pc.check_ps23(emul, oracle_np, 64, 2)

@@ -1,5 +1,6 @@
-"""GPU suite (-m gpu), SURVEY 8f row f3: the pseudo-spectral solver with the 2/3 rule
-(22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl) through the C ABI of libvmk.so against the literal numpy
+"""GPU suite (-m gpu), SURVEY 8f row f3: the pseudo-spectral solvers with the 2/3 rule
+(22_NS2D_PseudoSpectral_23_Rule/pseudospectral_23_rule.jl) and the 3/2 rule (21_NS2D_PseudoSpectral_32_Rule/
+pseudospectral_32_rule.jl) through the C ABI of libvmk.so against the literal numpy
 restatement (oracle_np.ps_numerical: full complex spectra, numpy C2C transforms).  Tolerance: relative L2 <= 1e-10.
 
 (The file sorts last on purpose: it was added after the round's GPU budget was spent, so its kernels were validated on
@@ -52,3 +53,32 @@ def test_pseudospectral_8192_properties(gpu):
     assert e1 < e0 and (e0 - e1) / e0 < 1e-3
     assert rel_l2(ut[:n, :n], w0) < 1e-3  # two steps of dt = 1e-4 barely move the field
     gpu.clear_plans()
+
+
+@pytest.mark.parametrize("n,nt,ns,noise", [(64, 20, 4, 1.), (128, 50, 5, .05), (256, 10, 2, .5), (512, 10, 1, .05),
+                                            (1024, 10, 2, .05), (2048, 3, 1, .05), (4096, 2, 1, .05)])
+def test_pseudospectral_32_rule(gpu, oracle_np, n, nt, ns, noise):
+    pc.check_ps32(gpu, oracle_np, n, nt, dt=1e-3 if noise >= .5 else None, ns=ns, noise=noise)
+    if n >= 1024:
+        gpu.clear_plans()
+
+
+def test_pseudospectral_32_rule_defaults_500_steps(gpu, oracle_np):
+    """the script's own configuration (128^2, dt = .01, Re = 1000, vm_ic), first 500 of its 2000 steps"""
+    pc.check_ps32(gpu, oracle_np, 128, 500, dt=.01, ns=10, noise=0.)
+
+
+def test_pseudospectral_rules_agree_8192(gpu):
+    """full size (12288-point padded transforms as 3 x 4096), no oracle run: on a well-resolved field both de-aliasing
+    rules compute the same Jacobian up to the field's spectral tail (the periodic image of vm_ic has a 1e-7 kink in its
+    derivative at the box edge; 256^2, two steps of dt = 1e-3: 1.1e-12 on the emulator), so the two solvers must agree"""
+    n = 8192
+    dx, dy, x, y = grid(n)
+    w = vm_field(n)
+    u32 = gpu.numerical_ps32(n, n, 2, dx, dy, 1e-4, 1000., x, y, w, 1)
+    gpu.clear_plans()
+    u23 = gpu.numerical_ps23(n, n, 2, dx, dy, 1e-4, 1000., x, y, w, 1)
+    gpu.clear_plans()
+    assert np.isfinite(u32).all() and abs(u32[:n, :n].mean()) < 1e-12
+    assert np.array_equal(u32[n, :], u32[0, :]) and np.array_equal(u32[:, n], u32[:, 0])
+    assert rel_l2(u32, u23) < 1e-9
