@@ -1003,12 +1003,13 @@ int ensure_ps23(vmk_plan* p, double dx) {
   if (!p->ops.kp) return fail(VMK_ESIZE, "the pseudo-spectral solver supports grids up to 8192^2");
   const int n = p->N;
   const size_t spec = sizeof(double2) * (size_t)(n / 2) * n;
-  if (!p->ptab) {
+  if (!p->ptab) {  // (ptab is allocated last: a failed attempt is resumed, not repeated)
     VMK_TRY(p->ops.kp_configure(&p->res_kp));
-    VMK_TRY(dev_alloc(p, (void**)&p->pV[0], spec));
-    VMK_TRY(dev_alloc(p, (void**)&p->pV[1], spec));
-    VMK_TRY(dev_alloc(p, (void**)&p->pA0, sizeof(double2) * n));
-    VMK_TRY(dev_alloc(p, (void**)&p->ptab, sizeof(double) * 8 * n));
+    auto once = [&](void** ptr, size_t bytes) -> int { return *ptr ? 0 : dev_alloc(p, ptr, bytes); };
+    VMK_TRY(once((void**)&p->pV[0], spec));
+    VMK_TRY(once((void**)&p->pV[1], spec));
+    VMK_TRY(once((void**)&p->pA0, sizeof(double2) * n));
+    VMK_TRY(once((void**)&p->ptab, sizeof(double) * 8 * n));
     p->ps_dx = 0;
   }
   if (p->ps_dx != dx) {
@@ -1124,18 +1125,19 @@ int ensure_ps32(vmk_plan* p, double dx) {
   if (p->N < 64) return fail(VMK_ESIZE, "the 3/2-rule solver supports grids of 64^2 .. 8192^2");
   VMK_TRY(ensure_kx(p));
   const size_t L = (size_t)p->N / 2, W = 2 * L + 1, c2 = sizeof(double2);
-  if (!p->child) {
-    VMK_TRY(vmk_plan_create((int64_t)L, (int64_t)L, &p->child));
+  if (!p->qtab) {  // (qtab is allocated last: a failed attempt is resumed, not repeated)
+    if (!p->child) VMK_TRY(vmk_plan_create((int64_t)L, (int64_t)L, &p->child));
     VMK_TRY(ensure_kx(p->child));
-    VMK_TRY(dev_alloc(p, (void**)&p->qS, c2 * (L + 1) * W));
-    VMK_TRY(dev_alloc(p, (void**)&p->qJ, c2 * (L + 1) * W));
-    VMK_TRY(dev_alloc(p, (void**)&p->qY, c2 * 4 * (L + 1) * 3 * L));
-    VMK_TRY(dev_alloc(p, (void**)&p->qVF, c2 * 36 * (L / 2) * L));
-    VMK_TRY(dev_alloc(p, (void**)&p->qT9, c2 * 9 * (L / 2) * L));
-    VMK_TRY(dev_alloc(p, (void**)&p->qPi, c2 * (L + 1) * 3 * L));
-    VMK_TRY(dev_alloc(p, (void**)&p->qF, sizeof(double) * 36 * (L + 2) * L));
-    VMK_TRY(dev_alloc(p, (void**)&p->qtw, c2 * 3 * L));
-    VMK_TRY(dev_alloc(p, (void**)&p->qtab, sizeof(double) * 5 * W));
+    auto once = [&](void** ptr, size_t bytes) -> int { return *ptr ? 0 : dev_alloc(p, ptr, bytes); };
+    VMK_TRY(once((void**)&p->qS, c2 * (L + 1) * W));
+    VMK_TRY(once((void**)&p->qJ, c2 * (L + 1) * W));
+    VMK_TRY(once((void**)&p->qY, c2 * 4 * (L + 1) * 3 * L));
+    VMK_TRY(once((void**)&p->qVF, c2 * 36 * (L / 2) * L));
+    VMK_TRY(once((void**)&p->qT9, c2 * 9 * (L / 2) * L));
+    VMK_TRY(once((void**)&p->qPi, c2 * (L + 1) * 3 * L));
+    VMK_TRY(once((void**)&p->qF, sizeof(double) * 36 * (L + 2) * L));
+    VMK_TRY(once((void**)&p->qtw, c2 * 3 * L));
+    VMK_TRY(once((void**)&p->qtab, sizeof(double) * 5 * W));
     p->q_dx = 0;
   }
   if (p->q_dx != dx) {

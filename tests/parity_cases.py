@@ -192,6 +192,26 @@ def check_ps32(cm, onp, n, nt, **kw):
     return check_ps23(cm, onp, n, nt, rule=32, **kw)
 
 
+def check_spectral_tgv(cm, which, n, nt, dt=.01, re=10., tol=1e-12):
+    """Closed-form answer for the spectral-space solvers (hybrid / ps23 / ps32), independent of any oracle: the
+    Taylor-Green field is an eigenfunction whose Jacobian vanishes, so each RK3/CN stage multiplies it by
+    (1 - d_s)/(1 + d_s), d_s = alpha_s (dt/2) 2 nq^2 / re (hybrid.jl:29-66; tests/test_oracle.py pins the numpy
+    restatements on the same answer)."""
+    nq = 4.
+    dx, dy, x, y = grid(n)
+    w0 = 2 * nq * np.cos(nq * x)[:, None] * np.cos(nq * y)[None, :]
+    fac = 1.
+    for alpha in (8. / 15., 2. / 15., 1. / 3.):
+        d = alpha * (.5 * dt * 2 * nq**2 / re)
+        fac *= (1. - d) / (1. + d)
+    wn = np.zeros((n + 2, n + 2), order="F")
+    wn[1:n + 2, 1:n + 2] = w0
+    numerical = {"hybrid": cm.numerical_hybrid, "ps23": cm.numerical_ps23, "ps32": cm.numerical_ps32}[which]
+    ut = numerical(n, n, nt, dx, dy, dt, re, x, y, wn, 1)
+    assert rel_l2(ut, w0 * fac**nt) < tol
+    return ut
+
+
 def check_ldc(cm, onp, n, nt, dt=None, re=100., from_rest=False, tol=TOL_RUN):
     """18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl `numerical` against the numpy/scipy restatement
     (oracle_np.ldc_numerical).  from_rest: the script's own initial condition (wn = sn = 0, the lid drives the flow);

@@ -144,6 +144,13 @@ def test_pseudospectral_32_rule_errors(emul):
         emul.numerical_ps32(64, 64, 1, dx, 2 * dy, .01, 1000., x, y, vm_field(64), 1)
 
 
+@pytest.mark.parametrize("which", ["hybrid", "ps23", "ps32"])
+def test_spectral_solvers_tgv_known_answer(emul, which):
+    """closed-form answer (decaying Taylor-Green eigenfunction), no oracle involved"""
+    pc.check_spectral_tgv(emul, which, 64, 25)
+    pc.check_spectral_tgv(emul, which, 256, 3)
+
+
 def test_pseudospectral_errors(emul):
     from cfd_julia_b200.common import Plan, VmkError
     n = 64

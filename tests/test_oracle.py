@@ -109,3 +109,52 @@ def test_divisor_tables_bitwise(oracle_c, oracle_np):
     # hermitian symmetry that makes the real-input FFT legitimate
     idx = (-np.arange(n)) % n
     assert np.array_equal(d, d[idx][:, idx])
+
+
+def tgv_spectral_known_answer(n, nt, dt, re, nq=4.):
+    """Known answer for the three spectral-space scripts (hybrid.jl, pseudospectral_23_rule.jl, pseudospectral_32_rule.jl):
+    the Taylor-Green field w0 = 2 nq cos(nq x) cos(nq y) is an eigenfunction of the Laplacian with psi = w / (2 nq^2), so
+    its Jacobian vanishes identically (also the discrete Arakawa one: J(a, c a) = 0) and every RK3/Crank-Nicolson stage
+    (hybrid.jl:40-66) just multiplies the four modes (+-nq, +-nq) by (1 - d_s)/(1 + d_s), d_s = alpha_s (dt/2) k2 / re,
+    k2 = 2 nq^2 (hx = 1 on the 2 pi box)."""
+    x = 2 * np.pi / n * np.arange(n + 1)
+    w0 = 2 * nq * np.cos(nq * x)[:, None] * np.cos(nq * x)[None, :]
+    k2 = 2 * nq**2
+    fac = 1.
+    for alpha in (8. / 15., 2. / 15., 1. / 3.):
+        d = alpha * (.5 * dt * k2 / re)
+        fac *= (1. - d) / (1. + d)
+    return w0, w0 * fac**nt
+
+
+@pytest.mark.parametrize("which", ["hybrid", "ps23", "ps32"])
+def test_spectral_scripts_tgv_known_answer(oracle_np, which):
+    """pins the numpy restatements of the three spectral-space scripts on a closed-form answer (no recorded reference
+    output exists for them)"""
+    n, nt, dt, re = 64, 25, .01, 10.
+    w0, exact = tgv_spectral_known_answer(n, nt, dt, re)
+    wn = np.zeros((n + 2, n + 2), order="F")
+    wn[1:n + 2, 1:n + 2] = w0
+    dx = 2 * np.pi / n
+    if which == "hybrid":
+        ut = oracle_np.hybrid_numerical(n, n, nt, dx, dx, dt, re, wn)
+    else:
+        ut = oracle_np.ps_numerical(int(which[2:]), n, n, nt, dx, dx, dt, re, wn)
+    assert np.linalg.norm(ut - exact) / np.linalg.norm(exact) < 1e-12
+    assert 0.2 < np.abs(ut).max() / np.abs(w0).max() < 0.5  # the decay over 25 steps is substantial: exp(-2 nq^2 t / re)
+
+
+def test_pseudospectral_rules_dealias(oracle_np):
+    """the two de-aliasing rules must agree (to rounding) on a field whose products stay inside both retained bands, and
+    differ from the aliased product otherwise: checks the band edges of both restatements against each other"""
+    n = 128  # 2/3 rule: retained band -42 .. 41
+    dx = 2 * np.pi / n
+    k2 = oracle_np.wavespace(n, n, dx, dx)
+    rng = np.random.default_rng(3)
+    kk = np.abs(np.fft.fftfreq(n, 1. / n))
+    band = (kk[:, None] <= 20) & (kk[None, :] <= 20)  # products reach |k| <= 40 < 42: inside both retained bands
+    wf = np.fft.fft2(rng.uniform(-1, 1, (n, n))) * band
+    wf[0, 0] = 0
+    j23 = oracle_np.ps23_jacobian(n, n, dx, dx, wf, k2)
+    j32 = oracle_np.ps32_jacobian(n, n, dx, dx, wf, k2)
+    assert np.linalg.norm(j23 - j32) / np.linalg.norm(j32) < 1e-13

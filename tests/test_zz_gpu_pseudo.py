@@ -82,3 +82,11 @@ def test_pseudospectral_rules_agree_8192(gpu):
     assert np.isfinite(u32).all() and abs(u32[:n, :n].mean()) < 1e-12
     assert np.array_equal(u32[n, :], u32[0, :]) and np.array_equal(u32[:, n], u32[:, 0])
     assert rel_l2(u32, u23) < 1e-9
+
+
+@pytest.mark.parametrize("which", ["hybrid", "ps23", "ps32"])
+def test_spectral_solvers_tgv_known_answer(gpu, which):
+    """closed-form answer (decaying Taylor-Green eigenfunction), no oracle involved; 1024^2 x 100 steps"""
+    pc.check_spectral_tgv(gpu, which, 64, 100)
+    pc.check_spectral_tgv(gpu, which, 1024, 100, tol=1e-11)
+    gpu.clear_plans()
