@@ -83,6 +83,25 @@ def check_golden(cm):
     assert rel_l2(out, g["out"]) < TOL_RUN
 
 
+def check_golden_f_rows(cm):
+    """committed fixtures of SURVEY 8f's rows (tests/golden/make_golden.py --f-rows)"""
+    g = np.load(f"{GOLD}/spectral_64_20.npz")
+    n, nt = 64, int(g["nt"])
+    dx, dy, x, y = grid(n)
+    w0 = np.asfortranarray(g["w0"].copy())
+    args = (n, n, nt, float(g["dx"]), float(g["dy"]), float(g["dt"]), float(g["re"]), x, y, w0, 1)
+    assert rel_l2(cm.numerical_hybrid(*args), g["hybrid"]) < TOL_RUN
+    assert rel_l2(cm.numerical_ps23(*args), g["ps23"]) < TOL_RUN
+    assert rel_l2(cm.numerical_ps32(*args), g["ps32"]) < TOL_RUN
+    g = np.load(f"{GOLD}/ldc_32_20.npz")
+    n, nt = 32, int(g["nt"])
+    wn, sn = np.asfortranarray(g["w0"].copy()), np.asfortranarray(g["s0"].copy())
+    rms = np.zeros(nt)
+    cm.numerical_ldc(n, n, nt, float(g["dx"]), float(g["dx"]), float(g["dt"]), float(g["re"]), wn, sn, rms)
+    assert rel_l2(wn, g["wn"]) < TOL_RUN and rel_l2(sn, g["sn"]) < TOL_RUN
+    assert np.max(np.abs(rms / g["rms"] - 1.)) < 1e-8
+
+
 def check_order_jl(cm, n):
     """The reference's only recorded outputs: fft_p.jl L2 errors hard-coded at order.jl:13."""
     from cfd_julia_b200.common import compute_l2norm_bnds

@@ -208,6 +208,10 @@ def test_golden(emul):
     pc.check_golden(emul)
 
 
+def test_golden_f_rows(emul):
+    pc.check_golden_f_rows(emul)
+
+
 @pytest.mark.parametrize("n", [32, 64, 128, 256, 512])
 def test_order_jl(emul, n):
     pc.check_order_jl(emul, n)

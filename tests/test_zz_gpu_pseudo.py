@@ -90,3 +90,8 @@ def test_spectral_solvers_tgv_known_answer(gpu, which):
     pc.check_spectral_tgv(gpu, which, 64, 100)
     pc.check_spectral_tgv(gpu, which, 1024, 100, tol=1e-11)
     gpu.clear_plans()
+
+
+def test_golden_f_rows(gpu):
+    """committed fixtures (tests/golden/spectral_64_20.npz, ldc_32_20.npz)"""
+    pc.check_golden_f_rows(gpu)
