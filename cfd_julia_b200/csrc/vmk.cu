@@ -49,6 +49,7 @@
 #include <math.h>
 
 #include <map>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -62,6 +63,15 @@
 #include "vmk_pseudo32.cuh"
 
 using namespace vmk;
+
+// serialises the entry points of one plan; recursive because vmk_numerical & co. call vmk_upload / vmk_step themselves
+#ifdef VMK_NO_GUARD  // (test builds only: shows that tests/test_emul.py's two-thread case fails without the lock)
+#define VMK_GUARD(p) (void)0
+#else
+#define VMK_GUARD(p)                                   \
+  std::unique_lock<std::recursive_mutex> guard__;      \
+  if (p) guard__ = std::unique_lock<std::recursive_mutex>((p)->mu)
+#endif
 
 #define VMK_TRY(expr)            \
   do {                           \
@@ -381,6 +391,8 @@ enum { KI_K1 = 0, KI_K2, KI_K3, KI_K4, KI_COUNT };
 }  // namespace
 
 struct vmk_plan {
+  // one host thread at a time per plan (the reference is single-threaded; a second thread blocks here)
+  std::recursive_mutex mu;
   int N = 0, M = 0, rank = 0, nranks = 1, NJ = 0, log2NJ = 0, j0 = 0;
   int sms = 0;
   int device = 0;  // CUDA device the plan lives on (the one current at creation)
@@ -1488,6 +1500,7 @@ struct PeerBlob {
 size_t vmk_peer_blob_bytes(void) { return sizeof(PeerBlob); }
 
 int vmk_peer_export(vmk_plan* p, void* blob) {
+  VMK_GUARD(p);
   if (!p || !blob) return fail(VMK_EARG, "NULL argument");
   PeerBlob* b = static_cast<PeerBlob*>(blob);
   void* ptrs[kPeerBufs] = {p->w[0], p->w[1], p->w[2], p->psi, p->T, p->V, p->flags};
@@ -1497,6 +1510,7 @@ int vmk_peer_export(vmk_plan* p, void* blob) {
 
 // blobs: nranks blobs in rank order (own entry ignored): one process per GPU, handles via CUDA IPC
 int vmk_peer_import(vmk_plan* p, const void* blobs) {
+  VMK_GUARD(p);
   if (!p || !blobs) return fail(VMK_EARG, "NULL argument");
   const PeerBlob* b = static_cast<const PeerBlob*>(blobs);
   for (int r = 0; r < p->nranks; r++) {
@@ -1519,6 +1533,7 @@ int vmk_peer_import(vmk_plan* p, const void* blobs) {
 // all ranks live in this process (one host thread driving several devices, the Julia model):
 // plans[r] is rank r's plan; peer access must already be enabled between the devices
 int vmk_peer_attach_local(vmk_plan* p, vmk_plan* const* plans) {
+  VMK_GUARD(p);
   if (!p || !plans) return fail(VMK_EARG, "NULL argument");
   VMK_TRY(be_set_device(p->device));
   for (int r = 0; r < p->nranks; r++) {
@@ -1536,6 +1551,7 @@ int vmk_peer_attach_local(vmk_plan* p, vmk_plan* const* plans) {
 }
 
 int vmk_barrier_hook(vmk_plan* p, void (*fn)(void*), void* user) {
+  VMK_GUARD(p);
   if (!p) return fail(VMK_EARG, "plan is NULL");
   p->barrier_fn = fn;
   p->barrier_user = user;
@@ -1544,6 +1560,7 @@ int vmk_barrier_hook(vmk_plan* p, void (*fn)(void*), void* user) {
 
 // ---- reference-signature entry points on host arrays -----------------------------------------------
 int vmk_fps(vmk_plan* p, double dx, double dy, const double* f, double* s, double eps) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!f || !s) return fail(VMK_EARG, "f or s is NULL");
   VMK_TRY(ensure_divisor(p, dx, dy, eps));
@@ -1555,6 +1572,7 @@ int vmk_fps(vmk_plan* p, double dx, double dy, const double* f, double* s, doubl
 }
 
 int vmk_ps_fft(vmk_plan* p, double dx, double dy, const double* f, double* u, double eps) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!f || !u) return fail(VMK_EARG, "f or u is NULL");
   VMK_TRY(ensure_divisor(p, dx, dy, eps));
@@ -1568,6 +1586,7 @@ int vmk_ps_fft(vmk_plan* p, double dx, double dy, const double* f, double* u, do
 }
 
 int vmk_rhs(vmk_plan* p, double dx, double dy, double re, const double* w, double* r, double* s, double* f) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!w || !r || !s) return fail(VMK_EARG, "w, r or s is NULL");
   VMK_TRY(ensure_divisor(p, dx, dy, 1.e-6));  // vm_rhs calls fps with the default eps (Common.jl:136)
@@ -1588,6 +1607,7 @@ int vmk_rhs(vmk_plan* p, double dx, double dy, double re, const double* w, doubl
 }
 
 int vmk_upload(vmk_plan* p, const double* wn) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!wn) return fail(VMK_EARG, "wn is NULL");
   VMK_TRY(upload_ghosted(p, wn, p->w[0]));
@@ -1597,6 +1617,7 @@ int vmk_upload(vmk_plan* p, const double* wn) {
 }
 
 int vmk_step(vmk_plan* p, double dx, double dy, double dt, double re, int64_t nsteps) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!p->uploaded) return fail(VMK_ESTATE, "vmk_step before vmk_upload");
   if (nsteps < 0) return fail(VMK_EARG, "nsteps < 0");
@@ -1639,6 +1660,7 @@ int vmk_step(vmk_plan* p, double dx, double dy, double dt, double re, int64_t ns
 }
 
 int vmk_download(vmk_plan* p, double* wn, double* psi) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!p->uploaded) return fail(VMK_ESTATE, "vmk_download before vmk_upload");
   if (wn) VMK_TRY(download_ghosted(p, p->w[0], wn));
@@ -1647,12 +1669,14 @@ int vmk_download(vmk_plan* p, double* wn, double* psi) {
 }
 
 int vmk_sync(vmk_plan* p) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   return sync_and_check(p);
 }
 
 int vmk_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, double re, double* wn, double* out,
                   int64_t freq, vmk_snapshot_fn snap, void* user) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!wn) return fail(VMK_EARG, "wn is NULL");
   if (nt < 0) return fail(VMK_EARG, "nt < 0");
@@ -1682,6 +1706,7 @@ int vmk_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, doub
 
 int vmk_hybrid_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
                          double* ut, int64_t freq, vmk_snapshot_fn snap, void* user) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!wn || !ut) return fail(VMK_EARG, "wn or ut is NULL");
   if (nt < 0) return fail(VMK_EARG, "nt < 0");
@@ -1715,6 +1740,7 @@ int vmk_hybrid_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double d
 
 int vmk_ps23_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
                        double* ut, int64_t freq, vmk_snapshot_fn snap, void* user) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!wn || !ut) return fail(VMK_EARG, "wn or ut is NULL");
   if (nt < 0) return fail(VMK_EARG, "nt < 0");
@@ -1749,6 +1775,7 @@ int vmk_ps23_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt,
 
 int vmk_ps32_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, double re, const double* wn,
                        double* ut, int64_t freq, vmk_snapshot_fn snap, void* user) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!wn || !ut) return fail(VMK_EARG, "wn or ut is NULL");
   if (nt < 0) return fail(VMK_EARG, "nt < 0");
@@ -1799,6 +1826,7 @@ int vmk_read_field(const char* path, double* x, double* y, double* w, int64_t ca
 
 int vmk_ldc_numerical(vmk_plan* p, int64_t nx, int64_t ny, int64_t nt, double dx, double dy, double dt, double re,
                       double* wn, double* sn, double* rms) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!wn || !sn || (nt > 0 && !rms)) return fail(VMK_EARG, "wn, sn or rms is NULL");
   if (nt < 0) return fail(VMK_EARG, "nt < 0");
@@ -1885,6 +1913,7 @@ void* vmk_stream(vmk_plan* p) {
 }
 
 int vmk_step_elapsed_ms(vmk_plan* p, double* ms) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!ms) return fail(VMK_EARG, "ms is NULL");
   if (!p->ev_valid) return fail(VMK_ESTATE, "no vmk_step call to time");
@@ -1893,6 +1922,7 @@ int vmk_step_elapsed_ms(vmk_plan* p, double* ms) {
 
 int vmk_profile_steps(vmk_plan* p, double dx, double dy, double dt, double re, int64_t nsteps, double* ms,
                       int64_t* launches) {
+  VMK_GUARD(p);
   VMK_TRY(check_plan(p));
   if (!p->uploaded) return fail(VMK_ESTATE, "vmk_profile_steps before vmk_upload");
   for (int k = 0; k < KI_COUNT; k++) {
@@ -1914,6 +1944,7 @@ int vmk_profile_steps(vmk_plan* p, double dx, double dy, double dt, double re, i
 int64_t vmk_launch_count(vmk_plan* p) { return p ? p->launches : 0; }
 
 int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
+  VMK_GUARD(p);
   if (!p || !key) return fail(VMK_EARG, "NULL argument");
   const std::string k(key);
   int* knob = k == "v_pieces" ? &p->v_pieces : k == "k1_prefetch" ? &p->k1_prefetch : k == "k2_prefetch" ? &p->k2_prefetch

@@ -168,10 +168,12 @@ VMK_HD void p32_spectra_body(const Ctx& c, const P32Args& a) {
     p32_mode(a, kxc, kp + L, srow[kp + L], ga);  // ky = ky'
     p32_mode(a, kxc, kp, srow[kp], gb);          // ky = ky' - L
     if (kp == 0) p32_mode(a, kxc, 2 * L, srow[2 * L], ge);  // ky = +L
+#pragma unroll
     for (int ry = 0; ry < 3; ry++) {
       const double2 wa = ld_ro2(a.twM + (M - kp * ry) % M);      // w^{-ky' ry}
       const double2 wb = ld_ro2(a.twM + (L - kp) * ry);          // w^{-(ky'-L) ry}
       const double2 we = ld_ro2(a.twM + (M - L * ry) % M);       // w^{-L ry}
+#pragma unroll
       for (int q = 0; q < 4; q++) {
         double2 y = cadd(cmul(ga[q], wa), cmul(gb[q], wb));
         if (kp == 0) y = cadd(y, cmul(ge[q], we));

@@ -15,8 +15,12 @@
  *     describes it.  The library never falls back to a CPU path: without a usable CUDA device every
  *     compute entry point fails with VMK_ECUDA.
  *   - Entry points taking host pointers are synchronous (they return after the device->host copy), because
- *     Julia only roots ccall arguments for the duration of the call.  A plan must not be used from two
- *     host threads at once.
+ *     Julia only roots ccall arguments for the duration of the call.
+ *   - Threads: the reference is single-threaded.  Every entry point that takes a plan holds that plan's (recursive)
+ *     mutex for the duration of the call, so calls on ONE plan from several host threads are serialised, and different
+ *     plans run concurrently.  vmk_step is asynchronous: the lock covers the enqueue, the stream orders the work.
+ *     vmk_plan_destroy must not race with other calls on the same plan.  The library never calls back into the host
+ *     language except through the snapshot callback, on the calling thread.
  */
 #ifndef VMK_H_
 #define VMK_H_

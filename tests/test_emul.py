@@ -204,6 +204,36 @@ def test_lid_driven_cavity_errors(emul):
         emul.numerical_ldc(n, n, 1, 1. / n, 1. / n, 1e-3, 100., np.zeros((n, n), order="F"), w, rms)
 
 
+def test_plan_is_serialised_across_host_threads(emul, oracle_c):
+    """a plan shared by two host threads (ctypes releases the GIL around the calls) -- the per-plan mutex
+    must serialise the entry points; without it the two solves interleave on the same device buffers"""
+    import threading
+    n = 256
+    dx, dy, x, y = grid(n)
+    rng = np.random.default_rng(1)
+    fs = [np.asfortranarray(rng.uniform(-1, 1, (n, n))) for _ in range(2)]
+    refs = []
+    for f in fs:
+        s = np.zeros((n + 2, n + 2), order="F")
+        oracle_c.fps(n, n, dx, dy, f, s)
+        refs.append(s)
+    emul.plan(n, n)  # created once, shared
+    outs = [[np.zeros((n + 2, n + 2), order="F") for _ in range(4)] for _ in range(2)]
+
+    def work(i):
+        for s in outs[i]:
+            emul.fps(n, n, dx, dy, None, None, None, None, fs[i], s)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for i in range(2):
+        for s in outs[i]:
+            assert rel_l2(s[1:n + 1, 1:n + 1], refs[i][1:n + 1, 1:n + 1]) < 1e-12
+
+
 def test_golden(emul):
     pc.check_golden(emul)
 
