@@ -29,7 +29,10 @@ def main():
     import parity_cases as pc
     from helpers import grid, noise_field, rel_l2, vm_field
     from oracle import oracle_np as onp
-    cm = Common(VmkLibrary(os.path.join(ROOT, "cfd_julia_b200", "libvmk.so"), "vmk_"))
+    if os.environ.get("VMK_QUICK_EMUL"):  # dry run of this script on the host emulator
+        cm = Common(VmkLibrary(os.path.join(ROOT, "tests", "emul", "libvmk_emul.so"), "vmke_"))
+    else:
+        cm = Common(VmkLibrary(os.path.join(ROOT, "cfd_julia_b200", "libvmk.so"), "vmk_"))
     say("library loaded", round(time.time() - t0, 2), "s")
     cases = [(23, 64, 5, 1.), (32, 64, 5, 1.), (23, 256, 3, .5), (32, 256, 3, .5), (23, 1024, 2, .05), (32, 1024, 2, .05)]
     for rule, n, nt, noise in cases:
