@@ -3,8 +3,9 @@
 pseudospectral_32_rule.jl) through the C ABI of libvmk.so against the literal numpy
 restatement (oracle_np.ps_numerical: full complex spectra, numpy C2C transforms).  Tolerance: relative L2 <= 1e-10.
 
-(The file sorts last on purpose: it was added after the round's GPU budget was spent, so its kernels were validated on
-the host emulator only -- tests/test_emul.py::test_pseudospectral_* -- before their first run on a B200.)"""
+(The file sorts last on purpose: it was written when two GPU-minutes of the round's budget were left.  Its kernels were
+developed on the host emulator -- tests/test_emul.py::test_pseudospectral_* -- and confirmed on a B200 with the torch-
+free scripts tools/gpu_quick_f3*.py (profiles/r01_f3_*_gpu.txt); this file itself had not run under pytest on a GPU.)"""
 import numpy as np
 import pytest
 
