@@ -82,11 +82,7 @@ numerical(nx, ny, nt, Δx, Δy, Δt, re, x, y, wn::Matrix{Float64}, ns) = begin
   m = Ref(1)
   cb = Ref{Function}(k -> begin
     @show k
-    open("vm$(m[]).txt", "w") do io
-      for j ∈ 1:ny + 1 for i ∈ 1:nx + 1
-        write(io, "$(x[i]) $(y[j]) $(wn[i + 1, j + 1])\n")
-      end end
-    end
+    write_field("vm$(m[]).txt", x, y, wn[2:nx+2, 2:ny+2])  # vm.jl:81-85, through the library's writer
     m[] += 1
   end)
   out = Array{Float64}(undef, nx + 1, ny + 1)
