@@ -57,8 +57,10 @@ def test_pseudospectral_8192_properties(gpu):
     gpu.clear_plans()
 
 
+# (the oracle's 1.5n-point numpy transforms dominate the run time of these cases: 2 steps at 4096^2 are ~100 s of host
+# FFTs, so the largest oracle comparison is 2048^2 and 8192^2 is covered by test_pseudospectral_rules_agree_8192)
 @pytest.mark.parametrize("n,nt,ns,noise", [(64, 20, 4, 1.), (128, 50, 5, .05), (256, 10, 2, .5), (512, 10, 1, .05),
-                                            (1024, 10, 2, .05), (2048, 3, 1, .05), (4096, 2, 1, .05)])
+                                            (1024, 6, 2, .05), (2048, 2, 1, .05)])
 def test_pseudospectral_32_rule(gpu, oracle_np, n, nt, ns, noise):
     pc.check_ps32(gpu, oracle_np, n, nt, dt=1e-3 if noise >= .5 else None, ns=ns, noise=noise)
     if n >= 1024:
