@@ -429,10 +429,10 @@ struct vmk_plan {
   double2* qS = nullptr;    // state [L+1][2L+1]
   double2* qJ = nullptr;
   double2* qY = nullptr;    // [4][L+1][3][L]
-  double2* qVF = nullptr;   // [4][9][L/2][L]
-  double2* qT9 = nullptr;   // [9][L/2][L]
+  double2* qVF = nullptr;   // [4][L/2][9][L]
+  double2* qT9 = nullptr;   // [L/2][9][L]
   double2* qPi = nullptr;   // [L+1][3][L]
-  double* qF = nullptr;     // [4][9] slabs of the child plan, (L+2) x L each
+  double* qF = nullptr;     // [4] real-space batches: (9L+2) rows x L (the 9 sub-grids of one field + two halo rows)
   double2* qtw = nullptr;   // [3L]
   double* qtab = nullptr;   // 5 x [2L+1]
   double q_dx = 0;
@@ -1238,29 +1238,59 @@ P32Args p32_args(vmk_plan* p, int stage, double dt, double re) {
   return a;
 }
 
-// one RK3 stage on the child plan's stream
+// one RK3 stage on the child plan's stream.  The 9 sub-grids of a field are one batch for K3 / K1: 9L rows of L points
+// (the kernels take the row count and pitch as arguments; only the plan-level launchers assume a square slab)
 int ps32_stage(vmk_plan* p, int stage, double dt, double re) {
   vmk_plan* ch = p->child;
-  const size_t L = (size_t)p->N / 2, slab = (L + 2) * L, blk = (L / 2) * L;
+  const size_t L = (size_t)p->N / 2, rows = 9 * L, slab = (rows + 2) * L, blk = (L / 2) * rows;
   const P32Args a = p32_args(p, stage, dt, re);
   VMK_TRY(launch_p32<P32Spectra>(ch, a, (L + 1) * L));                    // i k wf [/ k2], folded along j   :113-155
   VMK_TRY(launch_kx(ch, p->qY, p->qY, (int)(12 * (L + 1)), 1));           // ifft along j (3 sub-rows each)  :157-160
   VMK_TRY(launch_p32<P32Fold>(ch, a, 4 * 3 * (L / 2) * L));               // folded along i
-  for (int q = 0; q < 4; q++)
-    for (int sub = 0; sub < 9; sub++)                                      // ifft along i, 9 sub-grids per field
-      VMK_TRY(launch_k3_rows(ch, p->qVF + (size_t)(q * 9 + sub) * blk, p->qF + (size_t)(q * 9 + sub) * slab));
-  double2* child_T = ch->T;
-  int rc = 0;
-  for (int sub = 0; sub < 9 && !rc; sub++) {
-    double* f1 = p->qF + (size_t)sub * slab;
-    rc = launch_kp_product(ch, f1, p->qF + (size_t)(9 + sub) * slab, p->qF + (size_t)(18 + sub) * slab,
-                           p->qF + (size_t)(27 + sub) * slab);            // j1 j2 - j3 j4                   :163-166
-    if (rc) break;
-    ch->T = p->qT9 + (size_t)sub * blk;
-    rc = launch_k1(ch, f1);                                                // fft along i                     :168
+  const int npairs = (int)(rows / 2);
+  const int work = rowpair_units(ch, npairs, 1);
+  for (int q = 0; q < 4; q++) {                                            // ifft along i: 9 sub-grids per launch
+    K3Args k;
+    double* out = p->qF + (size_t)q * slab;
+    k.T = p->qVF + (size_t)q * blk;
+    k.pieces = 0;
+    k.prefetch = 0;
+    k.tw = ch->tw;
+    k.psi = out;
+    k.lo_dst = out + (rows + 1) * L;  // the halo rows of the batch are written and never read
+    k.hi_dst = out;
+    k.NJ = (int)rows;
+    k.npairs = npairs;
+    VMK_TRY(ch->ops.k3(work < ch->res_k3 ? work : ch->res_k3, k, ch->st));
+    ch->launches++;
   }
-  ch->T = child_T;
-  VMK_TRY(rc);
+  {
+    KPProdArgs k;                                                          // j1 j2 - j3 j4                   :163-166
+    k.q1 = p->qF + L;
+    k.q2 = p->qF + slab + L;
+    k.q3 = p->qF + 2 * slab + L;
+    k.q4 = p->qF + 3 * slab + L;
+    k.n = rows * L;
+    size_t want = (k.n / 2 + kK5Threads - 1) / kK5Threads;
+    const size_t cap = (size_t)ch->sms * 16;
+    const int grid = (int)(want < cap ? want : cap);
+    VMK_TRY((be_launch<KPProduct, KPProdArgs, kK5Threads, 4>(grid < 1 ? 1 : grid, 0, k, ch->st)));
+    ch->launches++;
+  }
+  {
+    K1Args k;                                                              // fft along i                     :168
+    k.w = p->qF;
+    k.S = nullptr;
+    k.Tloc = p->qT9;
+    k.tw = ch->tw;
+    k.NJ = (int)rows;
+    k.npairs = npairs;
+    k.k_own0 = 0;
+    k.k_own1 = (int)(L / 2);
+    k.prefetch = 0;
+    VMK_TRY(ch->ops.k1(work < ch->res_k1 ? work : ch->res_k1, k, ch->st));
+    ch->launches++;
+  }
   VMK_TRY(launch_p32<P32Unfold>(ch, a, (L + 1) * 3 * L));                 // unfolded along i, x nx ny/(nxe nye)  :176
   VMK_TRY(launch_kx(ch, p->qPi, p->qPi, (int)(3 * (L + 1)), 0));          // fft along j
   VMK_TRY(launch_p32<P32Update>(ch, a, (L + 1) * (2 * L + 1)));           // unfolded along j + the RK3/CN update  :41-66

@@ -19,8 +19,9 @@
 // an O(1) non-Hermitian part here (jf[-L, ky] is taken from the padded spectrum's mode -L alone, :171-174); the final
 // field real(ifft(wnf)) on the nx x ny grid (:71) folds +L and -L back together (p32_final_body).
 //
-// One stage = E1 spectra -> KX (12 (L+1) inverse L-point rows, in place) -> E2 fold along i -> 36 x K3_L -> 9 products
-// -> 9 x K1_L -> E3 unfold along i -> KX (3 (L+1) forward rows, in place) -> E4 unfold along j + mode update.
+// One stage = E1 spectra -> KX (12 (L+1) inverse L-point rows, in place) -> E2 fold along i -> 4 x K3_L (each over the
+// 9 sub-grids of one field: 9L rows of L points) -> product -> K1_L (9L rows) -> E3 unfold along i -> KX (3 (L+1)
+// forward rows, in place) -> E4 unfold along j + mode update: 12 launches.
 // Every pass works in natural index order on global memory: a deliberately plain first version (many passes over the
 // spectra, scattered stores in KX) whose arithmetic was fixed first as a numpy model (tools/ps32_model.py, 3e-16
 // against the literal restatement of the script with white-noise input); fusing E1/E4 into the row transforms the way
@@ -101,8 +102,8 @@ struct P32Args {
   double2* S;            // [L+1][2L+1] state
   double2* J;            // [L+1][2L+1] previous stage's jf
   double2* Y;            // [4][L+1][3][L]: E1 output, transformed in place by KX, E2 input
-  double2* VF;           // [4][3 rx][3 ry][L/2][L]: K3_L inputs
-  const double2* T9;     // [3 rx][3 ry][L/2][L]: K1_L outputs
+  double2* VF;           // [4][L/2][9 sub-grids (3 rx + ry)][L]: K3_L input of one launch per field (9L rows of L points)
+  const double2* T9;     // [L/2][9 sub-grids][L]: K1_L output of one launch
   double2* Pi;           // [L+1][3][L]: E3 output, transformed in place by KX, E4 input
   const double2* Xn;     // init:  [L][N] forward-j of K1_N(w0) (row 0 packed), natural order
   double2* Un;           // final: [L][N] N-grid half spectrum (row 0 packed), natural order
@@ -206,7 +207,7 @@ VMK_HD void p32_fold_body(const Ctx& c, const P32Args& a) {
         const double2 v1 = V(kp), v2 = cconj(V(L - kp));
         y = cadd(cmul(v1, ld_ro2(a.twM + (M - kp * rx) % M)), cmul(v2, ld_ro2(a.twM + (L - kp) * rx)));
       }
-      a.VF[((((size_t)q * 3 + rx) * 3 + ry) * h + kp) * L + py] = y;
+      a.VF[(((size_t)q * h + kp) * 9 + (rx * 3 + ry)) * L + py] = y;
     }
   }
 }
@@ -221,16 +222,17 @@ VMK_HD void p32_unfold_body(const Ctx& c, const P32Args& a) {
     const int ry = (int)(r % 3), kx = (int)(r / 3), kk = kx % L;
     double2 acc = mk2(0.0, 0.0);
     for (int rx = 0; rx < 3; rx++) {
-      const double2* blk = a.T9 + (size_t)(rx * 3 + ry) * h * L;
+      const double2* blk = a.T9 + (size_t)(rx * 3 + ry) * L + py;  // [kx'][9 sub-grids][py]
+      const size_t pitch = (size_t)9 * L;
       double2 tv;
       if (kk == 0) {
-        tv = mk2(blk[py].x, 0.0);
+        tv = mk2(blk[0].x, 0.0);
       } else if (kk == h) {
-        tv = mk2(blk[py].y, 0.0);
+        tv = mk2(blk[0].y, 0.0);
       } else if (kk < h) {
-        tv = blk[(size_t)kk * L + py];
+        tv = blk[(size_t)kk * pitch];
       } else {
-        tv = cconj(blk[(size_t)(L - kk) * L + py]);
+        tv = cconj(blk[(size_t)(L - kk) * pitch]);
       }
       acc = cadd(acc, cmul(tv, ld_ro2(a.twM + kx * rx)));
     }
