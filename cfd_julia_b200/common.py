@@ -98,6 +98,13 @@ class Plan:
         self.lib.check(self.lib.profile_steps(self.handle, dx, dy, dt, re, nsteps, ms, n))
         return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(("k1", "k2", "k3", "k4"))}
 
+    def profile_read(self):
+        """Per-class kernel time since the last read (after set_option("profile", 1)); see vmk_profile_read."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        self.lib.check(self.lib.profile_read(self.handle, ms, n))
+        return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(("k1", "k2", "k3", "k4"))}
+
     def set_option(self, key: str, value: int):
         self.lib.check(self.lib.set_option(self.handle, key.encode(), value))
 

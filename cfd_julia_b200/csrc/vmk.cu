@@ -35,6 +35,7 @@
 #define vmk_stream vmke_stream
 #define vmk_step_elapsed_ms vmke_step_elapsed_ms
 #define vmk_profile_steps vmke_profile_steps
+#define vmk_profile_read vmke_profile_read
 #define vmk_launch_count vmke_launch_count
 #define vmk_set_option vmke_set_option
 #define vmk_device_bytes vmke_device_bytes
@@ -1106,7 +1107,9 @@ int launch_kp_product(vmk_plan* p, double* q1, const double* q2, const double* q
   size_t want = (a.n / 2 + kK5Threads - 1) / kK5Threads;
   const size_t cap = (size_t)p->sms * 16;
   const int grid = (int)(want < cap ? want : cap);
+  Timed t(p, KI_K4);
   VMK_TRY((be_launch<KPProduct, KPProdArgs, kK5Threads, 4>(grid < 1 ? 1 : grid, 0, a, p->st)));
+  t.done();
   p->launches++;
   return 0;
 }
@@ -1193,7 +1196,9 @@ int launch_kx(vmk_plan* q, const double2* in, double2* out, int nrows, int inver
   a.nrows = nrows;
   a.inverse = inverse;
   const int work = (nrows + q->ops.fpc - 1) / q->ops.fpc;
+  Timed t(q, KI_K2);
   VMK_TRY(q->ops.kx(work < q->res_kx ? work : q->res_kx, a, q->st));
+  t.done();
   q->launches++;
   return 0;
 }
@@ -1203,7 +1208,9 @@ int launch_p32(vmk_plan* q, const P32Args& a, size_t items) {
   size_t want = (items + kK5Threads - 1) / kK5Threads;
   const size_t cap = (size_t)q->sms * 16;
   const int grid = (int)(want < cap ? want : cap);
+  Timed t(q, KI_K4);
   VMK_TRY((be_launch<Body, P32Args, kK5Threads, 4>(grid < 1 ? 1 : grid, 0, a, q->st)));
+  t.done();
   q->launches++;
   return 0;
 }
@@ -1261,7 +1268,9 @@ int ps32_stage(vmk_plan* p, int stage, double dt, double re) {
     k.hi_dst = out;
     k.NJ = (int)rows;
     k.npairs = npairs;
+    Timed t(ch, KI_K3);
     VMK_TRY(ch->ops.k3(work < ch->res_k3 ? work : ch->res_k3, k, ch->st));
+    t.done();
     ch->launches++;
   }
   {
@@ -1274,7 +1283,9 @@ int ps32_stage(vmk_plan* p, int stage, double dt, double re) {
     size_t want = (k.n / 2 + kK5Threads - 1) / kK5Threads;
     const size_t cap = (size_t)ch->sms * 16;
     const int grid = (int)(want < cap ? want : cap);
+    Timed t(ch, KI_K4);
     VMK_TRY((be_launch<KPProduct, KPProdArgs, kK5Threads, 4>(grid < 1 ? 1 : grid, 0, k, ch->st)));
+    t.done();
     ch->launches++;
   }
   {
@@ -1288,7 +1299,9 @@ int ps32_stage(vmk_plan* p, int stage, double dt, double re) {
     k.k_own0 = 0;
     k.k_own1 = (int)(L / 2);
     k.prefetch = 0;
+    Timed t(ch, KI_K1);
     VMK_TRY(ch->ops.k1(work < ch->res_k1 ? work : ch->res_k1, k, ch->st));
+    t.done();
     ch->launches++;
   }
   VMK_TRY(launch_p32<P32Unfold>(ch, a, (L + 1) * 3 * L));                 // unfolded along i, x nx ny/(nxe nye)  :176
@@ -1813,6 +1826,7 @@ int vmk_ps32_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt,
   VMK_TRY(ensure_ps32(p, dx));
   const size_t L = (size_t)p->N / 2;
   const int64_t child_launches0 = p->child->launches;
+  p->child->profiling = p->profiling;
   VMK_TRY(upload_ghosted(p, wn, p->w[0]));
   VMK_TRY(be_event_record(p->ev0, p->st));
   VMK_TRY(launch_k1(p, p->w[0]));                               // wnf = fft(data), nx x ny   :24
@@ -1959,14 +1973,33 @@ int vmk_profile_steps(vmk_plan* p, double dx, double dy, double dt, double re, i
     p->prof_ms[k] = 0;
     p->prof_n[k] = 0;
   }
+  const bool was = p->profiling;
   p->profiling = true;
   int rc = vmk_step(p, dx, dy, dt, re, nsteps);
   if (!rc) rc = collect_profile(p);
-  p->profiling = false;
+  p->profiling = was;
   VMK_TRY(rc);
   for (int k = 0; k < KI_COUNT; k++) {
     if (ms) ms[k] = p->prof_ms[k];
     if (launches) launches[k] = p->prof_n[k];
+  }
+  return VMK_OK;
+}
+
+int vmk_profile_read(vmk_plan* p, double* ms, int64_t* launches) {
+  VMK_GUARD(p);
+  VMK_TRY(check_plan(p));
+  VMK_TRY(collect_profile(p));
+  if (p->child) VMK_TRY(collect_profile(p->child));
+  for (int k = 0; k < KI_COUNT; k++) {
+    if (ms) ms[k] = p->prof_ms[k] + (p->child ? p->child->prof_ms[k] : 0.0);
+    if (launches) launches[k] = p->prof_n[k] + (p->child ? p->child->prof_n[k] : 0);
+    p->prof_ms[k] = 0;
+    p->prof_n[k] = 0;
+    if (p->child) {
+      p->child->prof_ms[k] = 0;
+      p->child->prof_n[k] = 0;
+    }
   }
   return VMK_OK;
 }
@@ -1989,6 +2022,9 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
     if (value < lo || value > hi) return fail(VMK_EARG, "option value out of range");
     *knob = (int)value;
     drop_graphs(p);
+  } else if (k == "profile") {
+    p->profiling = value != 0;  // events around every kernel of the following calls; read with vmk_profile_read
+    if (p->child) p->child->profiling = p->profiling;
   } else if (k == "graph") {
     p->use_graph = value != 0;
   } else if (k == "k4_rows") {

@@ -162,9 +162,16 @@ int vmk_step_elapsed_ms(vmk_plan* plan, double* ms);
  * the launch counts */
 int vmk_profile_steps(vmk_plan* plan, double dx, double dy, double dt, double re, int64_t nsteps, double* ms,
                       int64_t* launches);
+/* With the option "profile" set to 1, every kernel of the following calls on this plan (any solver) is bracketed by
+ * CUDA events; vmk_profile_read sums them per class since the last read -- ms[0] row-forward transforms (K1), ms[1]
+ * spectrum-row kernels (K2, KH, KP, the batched row FFT of the 3/2 rule), ms[2] row-inverse transforms (K3), ms[3]
+ * pointwise kernels (K4, products, the fold / unfold / update passes) -- and resets the sums.  (CUDA graphs are not
+ * used while profiling.) */
+int vmk_profile_read(vmk_plan* plan, double* ms, int64_t* launches);
 /* kernels launched by this plan since creation */
 int64_t vmk_launch_count(vmk_plan* plan);
 /* tuning knobs (integers; defaults are the measured best, see profiles/r01_notes.md):
+ *   "profile"     0      1: bracket every kernel with events (see vmk_profile_read)
  *   "graph"       1      replay the step (kernels, copies, barriers) from a CUDA graph
  *   "k4_rows"     32     rows marched by one K4 thread column (shortened automatically on small slabs)
  *   "k4_ahead"    4      rows ahead of the march that K4 prefetches into L2 (0 = off)

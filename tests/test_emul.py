@@ -234,6 +234,31 @@ def test_plan_is_serialised_across_host_threads(emul, oracle_c):
             assert rel_l2(s[1:n + 1, 1:n + 1], refs[i][1:n + 1, 1:n + 1]) < 1e-12
 
 
+def test_profile_option_counts_every_kernel_class(emul):
+    """set_option("profile", 1) + vmk_profile_read: per-class launch counts of one step of each spectral-space solver
+    (k1 row-forward, k2 spectrum-row kernels, k3 row-inverse, k4 pointwise), summed over the plan and its inner plan"""
+    n = 64
+    dx, dy, x, y = grid(n)
+    w = vm_field(n)
+    p = emul.plan(n, n)
+    p.set_option("profile", 1)
+    p.profile_read()
+    emul.numerical_hybrid(n, n, 1, dx, dy, .01, 1000., x, y, w, 1)
+    got = {k: v["launches"] for k, v in p.profile_read().items()}
+    assert got == {"k1": 4, "k2": 4, "k3": 7, "k4": 3}  # init K1+KH; per stage 2 K3, K4, K1, KH; final K3
+    emul.numerical_ps23(n, n, 1, dx, dy, .01, 1000., x, y, w, 1)
+    got = {k: v["launches"] for k, v in p.profile_read().items()}
+    assert got == {"k1": 4, "k2": 5, "k3": 13, "k4": 3}  # per stage 4 K3, product, K1, KP; final KP(4) + K3
+    emul.numerical_ps32(n, n, 1, dx, dy, .01, 1000., x, y, w, 1)
+    got = p.profile_read()
+    # init: K1, KX, E0; per stage: E1, KX, E2, 4 K3, product, K1, E3, KX, E4; final: E5, KX, K3
+    assert {k: v["launches"] for k, v in got.items()} == {"k1": 4, "k2": 8, "k3": 13, "k4": 17}
+    assert all(v["ms"] >= 0 for v in got.values())
+    p.set_option("profile", 0)
+    emul.numerical_ps23(n, n, 1, dx, dy, .01, 1000., x, y, w, 1)
+    assert sum(v["launches"] for v in p.profile_read().values()) == 0
+
+
 def test_golden(emul):
     pc.check_golden(emul)
 
