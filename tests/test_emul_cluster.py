@@ -79,3 +79,17 @@ def test_property_checks_used_at_full_size(emul_cl, oracle_c):
     tg._check_modes_residual(emul_cl, n, hi, 1e-13)
     tg._check_modes(emul_cl, n, lo, 1e-13)
     tg._tiled_run(emul_cl, oracle_c, 512, 64, 2)
+
+
+def test_spectral_solvers_refuse_cluster_sizes(emul_cl):
+    """the hybrid / pseudo-spectral solvers have no cluster variant (rows of 16384 / 32768 points; here: the cluster
+    test build at 128): VMK_ESIZE with a message, not a crash"""
+    from cfd_julia_b200.common import VmkError
+    n = 128
+    dx, dy, x, y = grid(n)
+    w = vm_field(n)
+    for fn in (emul_cl.numerical_hybrid, emul_cl.numerical_ps23, emul_cl.numerical_ps32):
+        with pytest.raises(VmkError) as e:
+            fn(n, n, 1, dx, dy, .01, 1000., x, y, w, 1)
+        assert e.value.code == 1 and "8192" in str(e.value)
+    emul_cl.clear_plans()
