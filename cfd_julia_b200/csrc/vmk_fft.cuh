@@ -1,7 +1,7 @@
 // vmk_fft.cuh -- CTA-level power-of-two complex FP64 FFT, data in registers, exchanged through
 // padded shared memory.  Replaces the reference's FFTW calls (Common.jl:117 fft, :123 ifft).
 //
-// Scheme (derivation and numpy spec: tools/fft_proto.py):
+// Scheme (derivation and numpy spec: tests/models/fft_proto.py):
 //   * N = 2^M points, E = 2^LE values per thread, T = N/E threads per transform.
 //   * forward = in-place mixed-radix DIF: pass k does radix-2^b_k butterflies on position bits
 //     [lo_k, hi_k) entirely in registers, multiplies by W_{2^hi_k}^{low*p}, and the values go back
@@ -11,7 +11,7 @@
 //   * the spectral side never needs natural order: the divide, the real-pair unpack and the
 //     transposed store are all index-agnostic, so no reordering pass exists anywhere.
 //   * shared memory address of position pos is pos + (pos >> b_last): conflict-free 128-bit
-//     accesses for every pass (checked with the bank model in tools/fft_proto.py).
+//     accesses for every pass (checked with the bank model in tests/models/fft_proto.py).
 #pragma once
 #include "vmk_common.cuh"
 

@@ -23,7 +23,7 @@
 // 9 sub-grids of one field: 9L rows of L points) -> product -> K1_L (9L rows) -> E3 unfold along i -> KX (3 (L+1)
 // forward rows, in place) -> E4 unfold along j + mode update: 12 launches.
 // Every pass works in natural index order on global memory: a deliberately plain first version (many passes over the
-// spectra, scattered stores in KX) whose arithmetic was fixed first as a numpy model (tools/ps32_model.py, 3e-16
+// spectra, scattered stores in KX) whose arithmetic was fixed first as a numpy model (tests/models/ps32_model.py, 3e-16
 // against the literal restatement of the script with white-noise input); fusing E1/E4 into the row transforms the way
 // KP does for the 2/3 rule is the obvious next step.
 #pragma once

@@ -187,7 +187,7 @@ if __name__ == "__main__":
         e2 = np.abs(dit_inv(a, M, bits) / N - x).max()
         print(M, bits, "fwd err", e1, "roundtrip err", e2)
     import sys, os
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
     from oracle import oracle_np as onp
     for M in (5, 6):
         N = 1 << M

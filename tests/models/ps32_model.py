@@ -173,7 +173,7 @@ class Model32:
 if __name__ == "__main__":
     import os
     import sys
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
     from oracle import oracle_np as o
     for n, amp in ((16, 1.), (32, 1.), (64, .05)):
         dx = 2 * np.pi / n

@@ -5,7 +5,7 @@ restatement (oracle_np.ps_numerical: full complex spectra, numpy C2C transforms)
 
 (The file sorts last on purpose: it was written when two GPU-minutes of the round's budget were left.  Its kernels were
 developed on the host emulator -- tests/test_emul.py::test_pseudospectral_* -- and confirmed on a B200 with the torch-
-free scripts tools/gpu_quick_f3*.py (profiles/r01_f3_*_gpu.txt); of this file the golden, closed-form and 64^2 cases
+free scripts tests/quick/gpu_quick_f3*.py (profiles/r01_f3_*_gpu.txt); of this file the golden, closed-form and 64^2 cases
 have run under pytest on a B200 (6 passed), the larger sizes and the 500-step runs had not when the budget ended.)"""
 import numpy as np
 import pytest
