@@ -184,6 +184,67 @@ VMK_HD void p32_spectra_body(const Ctx& c, const P32Args& a) {
   }
 }
 
+// E1 fused into the inverse row transform (opt-in, set_option "ps32_fuse"): row = (q, kx, ry); the transform's inputs
+// Y[q][kx][ry][ky'] are computed from S in its load stage instead of being written by p32_spectra_body and read back --
+// one write and one read of the 12 (L+1) L-point spectra less per stage.  Output layout as kx_body's (E2 unchanged).
+struct KXSArgs {
+  P32Args a;
+  const double2* tw;  // the FFT engine's tables
+  int nrows;          // 12 (L + 1)
+};
+
+template <class C>
+VMK_HD void kxs_body(const Ctx& c, const KXSArgs& ka) {
+  using F = Fft<C>;
+  constexpr int N = C::N, E = C::E, T = C::T, P = C::P;
+  constexpr int bl = C::bits(P - 1), rl = 1 << bl;
+  static_assert(!C::SPLIT, "kxs_body uses the plain exchange buffer");
+  const P32Args& a = ka.a;
+  double2* tw = F::tables(c.smem);
+  F::load_tables(c, tw, ka.tw);
+  c.sync();
+  const int g = c.tid / T, t = c.tid % T;
+  double2* sm = F::xbuf(c.smem, g);
+  const int L = a.L, M = 3 * L, W = 2 * L + 1;  // L == N
+  const int nblocks = (ka.nrows + C::FPC - 1) / C::FPC;
+  for (int rb = c.bid; rb < nblocks; rb += c.nblk) {
+    const int slot = rb * C::FPC + g;
+    const bool active = slot < ka.nrows;
+    const int row = active ? slot : ka.nrows - 1;  // spare slots redo the last row, only the store is conditional
+    const int ry = row % 3, kx = (row / 3) % (L + 1), q = row / (3 * (L + 1));
+    const int kxc = kx + L;
+    const double2* srow = a.S + (size_t)kx * W;
+    const bool xdir = (q == 0 || q == 3), div = (q == 0 || q == 2);
+    const double cxr = ld_ro(a.cc + kxc), dxr = ld_ro(a.dd + kxc), mpr = ld_ro(a.mp + kxc), mmr = ld_ro(a.mm + kxc);
+    const double kxx = ld_ro(a.ksq + kxc);
+    // i S D(kx, col) [/ k2] / (2 N^2) for one mode column (p32_mode restricted to the row's q)
+    auto mode = [&](int col) {
+      const double2 s = srow[col];
+      double f = xdir ? cxr * ld_ro(a.mp + col) + dxr * ld_ro(a.mm + col) : mpr * ld_ro(a.cc + col) + mmr * ld_ro(a.dd + col);
+      f = f * a.scale;
+      if (div) f = f * (1.0 / (kxx + ld_ro(a.ksq + col)));
+      return mk2(-s.y * f, s.x * f);
+    };
+    double2 v[E];
+    static_for<0, E>([&](auto e_) {
+      constexpr int e = decltype(e_)::value, u = e / rl, p = e % rl;
+      const int kp = F::k_of_pos(((t + T * u) << bl) | p);
+      double2 y = cadd(cmul(mode(kp + L), ld_ro2(a.twM + (M - kp * ry) % M)),   // ky = ky'
+                       cmul(mode(kp), ld_ro2(a.twM + (L - kp) * ry)));          // ky = ky' - L
+      if (kp == 0) y = cadd(y, cmul(mode(2 * L), ld_ro2(a.twM + (M - L * ry) % M)));  // ky = +L
+      v[e] = y;
+    });
+    c.sync();  // the previous row's last exchange has been read everywhere
+    F::inverse(c, v, sm, tw, t);
+    if (active) {
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        a.Y[(size_t)row * N + F::template own_pos<e>(t)] = v[e];
+      });
+    }
+  }
+}
+
 // E2: fold along i.  VF[q][rx][ry][kx'][py] = sum over kx = kx' mod L (Hermitian completion in kx) of V w^{-kx rx};
 // row kx' = 0 packs the (real) kx' = 0 and kx' = L/2 lines as K3 expects
 VMK_HD void p32_fold_body(const Ctx& c, const P32Args& a) {

@@ -231,6 +231,26 @@ def check_spectral_tgv(cm, which, n, nt, dt=.01, re=10., tol=1e-12):
     return ut
 
 
+def check_ps32_fused(cm, onp, n, nt, noise=.5):
+    """the opt-in fused kernel of the 3/2 rule (set_option "ps32_fuse": spectra computed in the load stage of the inverse
+    row transform) against the default path -- the arithmetic is the same, so the fields must be bit-identical -- and
+    against the oracle"""
+    dx, dy, x, y = grid(n)
+    w = vm_field(n) + noise * noise_field(n, 5)
+    p = cm.plan(n, n)
+    p.set_option("ps32_fuse", 0)
+    a = cm.numerical_ps32(n, n, nt, dx, dy, 1e-3, 1000., x, y, w, 1)
+    l0 = p.launch_count
+    p.set_option("ps32_fuse", 1)
+    try:
+        b = cm.numerical_ps32(n, n, nt, dx, dy, 1e-3, 1000., x, y, w, 1)
+    finally:
+        p.set_option("ps32_fuse", 0)
+    assert p.launch_count - l0 == 7 + 33 * nt  # 4 (upload, K1, KX, E0) + 11 per stage, one less than the default + 3
+    assert np.array_equal(a, b)
+    assert rel_l2(b, onp.ps_numerical(32, n, n, nt, dx, dy, 1e-3, 1000., w)) < TOL_RUN
+
+
 def check_ldc(cm, onp, n, nt, dt=None, re=100., from_rest=False, tol=TOL_RUN):
     """18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl `numerical` against the numpy/scipy restatement
     (oracle_np.ldc_numerical).  from_rest: the script's own initial condition (wn = sn = 0, the lid drives the flow);

@@ -133,6 +133,11 @@ def test_pseudospectral_32_rule_defaults_40_steps(emul, oracle_np):
     pc.check_ps32(emul, oracle_np, 128, 40, dt=.01, ns=2, noise=0.)
 
 
+@pytest.mark.parametrize("n,nt", [(64, 3), (128, 2), (512, 1)])
+def test_pseudospectral_32_rule_fused_option(emul, oracle_np, n, nt):
+    pc.check_ps32_fused(emul, oracle_np, n, nt)
+
+
 def test_pseudospectral_32_rule_errors(emul):
     from cfd_julia_b200.common import VmkError
     dx, dy, x, y = grid(32)

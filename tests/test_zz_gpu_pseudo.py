@@ -99,3 +99,10 @@ def test_spectral_solvers_tgv_known_answer(gpu, which):
 def test_golden_f_rows(gpu):
     """committed fixtures (tests/golden/spectral_64_20.npz, ldc_32_20.npz)"""
     pc.check_golden_f_rows(gpu)
+
+
+@pytest.mark.parametrize("n,nt", [(64, 5), (256, 3), (1024, 2)])
+def test_pseudospectral_32_rule_fused_option(gpu, oracle_np, n, nt):
+    """opt-in kernel (default off; emulator-validated only when it was written): must equal the default path bit for bit"""
+    pc.check_ps32_fused(gpu, oracle_np, n, nt)
+    gpu.clear_plans()
