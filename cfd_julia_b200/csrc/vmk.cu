@@ -112,6 +112,8 @@ struct SizeOps {
   int (*kx)(int grid, const KXArgs&, Stream&);
   int (*kxs_configure)(int* res);
   int (*kxs)(int grid, const KXSArgs&, Stream&);
+  int (*kxf_configure)(int* res);
+  int (*kxf)(int grid, const KXSArgs&, Stream&);
 };
 
 template <class C>
@@ -141,6 +143,10 @@ struct KXBody {
 template <class C>
 struct KXSBody {
   VMK_HD static void run(const Ctx& c, const KXSArgs& a) { kxs_body<C>(c, a); }
+};
+template <class C>
+struct KXFBody {
+  VMK_HD static void run(const Ctx& c, const KXSArgs& a) { kxf_body<C>(c, a); }
 };
 struct P32Init {
   VMK_HD static void run(const Ctx& c, const P32Args& a) { p32_init_body(c, a); }
@@ -303,6 +309,8 @@ SizeOps make_cluster_ops() {
   o.kx = nullptr;
   o.kxs_configure = nullptr;
   o.kxs = nullptr;
+  o.kxf_configure = nullptr;
+  o.kxf = nullptr;
   return o;
 }
 
@@ -345,6 +353,8 @@ SizeOps make_ops() {
     o.kx = nullptr;
     o.kxs_configure = nullptr;
     o.kxs = nullptr;
+    o.kxf_configure = nullptr;
+    o.kxf = nullptr;
   } else {
     o.kh_configure = [](int* r) -> int { return be_configure<KHBody<C>, KHArgs, C::CT, C::MINB>(C::SMEM_BYTES, r); };
     o.kh = [](int grid, const KHArgs& a, Stream& s) -> int {
@@ -361,6 +371,10 @@ SizeOps make_ops() {
     o.kxs_configure = [](int* r) -> int { return be_configure<KXSBody<C>, KXSArgs, C::CT, C::MINB>(C::SMEM_BYTES, r); };
     o.kxs = [](int grid, const KXSArgs& a, Stream& s) -> int {
       return be_launch<KXSBody<C>, KXSArgs, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    };
+    o.kxf_configure = [](int* r) -> int { return be_configure<KXFBody<C>, KXSArgs, C::CT, C::MINB>(C::SMEM_BYTES, r); };
+    o.kxf = [](int grid, const KXSArgs& a, Stream& s) -> int {
+      return be_launch<KXFBody<C>, KXSArgs, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
     };
   }
   o.fill_ksqperm = &fill_ccperm<C>;  // the same register-order permutation as the divisor table
@@ -451,8 +465,8 @@ struct vmk_plan {
   double2* qtw = nullptr;   // [3L]
   double* qtab = nullptr;   // 5 x [2L+1]
   double q_dx = 0;
-  int res_kx = 0, res_kxs = 0;
-  int ps32_fuse = 0;  // 1: spectra computed in the load stage of the inverse row transform (kxs_body)
+  int res_kx = 0, res_kxs = 0, res_kxf = 0;
+  int ps32_fuse = 0;  // 1: spectra computed in the load stage of the inverse row transform (kxs_body); 2: and folded along i there (kxf_body)
   // lid-driven cavity (vmk_ldc_numerical), allocated on first use: node arrays (n+1)^2 with n = N/2
   double* cw[3] = {nullptr, nullptr, nullptr};  // wn, wtA, wtB
   double* cs = nullptr;                         // sn
@@ -1266,7 +1280,18 @@ int ps32_stage(vmk_plan* p, int stage, double dt, double re) {
   vmk_plan* ch = p->child;
   const size_t L = (size_t)p->N / 2, rows = 9 * L, slab = (rows + 2) * L, blk = (L / 2) * rows;
   const P32Args a = p32_args(p, stage, dt, re);
-  if (p->ps32_fuse) {                                                     // both of the following in one kernel
+  if (p->ps32_fuse == 2) {                                                // spectra, fold along i and ifft along j in one kernel
+    if (!ch->res_kxf) VMK_TRY(ch->ops.kxf_configure(&ch->res_kxf));
+    KXSArgs k;
+    k.a = a;
+    k.tw = ch->tw;
+    k.nrows = (int)(36 * (L / 2));
+    const int units = (k.nrows + ch->ops.fpc - 1) / ch->ops.fpc;
+    Timed t(ch, KI_K2);
+    VMK_TRY(ch->ops.kxf(units < ch->res_kxf ? units : ch->res_kxf, k, ch->st));
+    t.done();
+    ch->launches++;
+  } else if (p->ps32_fuse) {                                              // both of the following in one kernel
     if (!ch->res_kxs) VMK_TRY(ch->ops.kxs_configure(&ch->res_kxs));
     KXSArgs k;
     k.a = a;
@@ -1281,7 +1306,7 @@ int ps32_stage(vmk_plan* p, int stage, double dt, double re) {
     VMK_TRY(launch_p32<P32Spectra>(ch, a, (L + 1) * L));                  // i k wf [/ k2], folded along j   :113-155
     VMK_TRY(launch_kx(ch, p->qY, p->qY, (int)(12 * (L + 1)), 1));         // ifft along j (3 sub-rows each)  :157-160
   }
-  VMK_TRY(launch_p32<P32Fold>(ch, a, 4 * 3 * (L / 2) * L));               // folded along i
+  if (p->ps32_fuse != 2) VMK_TRY(launch_p32<P32Fold>(ch, a, 4 * 3 * (L / 2) * L));  // folded along i
   const int npairs = (int)(rows / 2);
   const int work = rowpair_units(ch, npairs, 1);
   for (int q = 0; q < 4; q++) {                                            // ifft along i: 9 sub-grids per launch
@@ -2051,7 +2076,8 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
     *knob = (int)value;
     drop_graphs(p);
   } else if (k == "ps32_fuse") {
-    p->ps32_fuse = value != 0;
+    if (value < 0 || value > 2) return fail(VMK_EARG, "ps32_fuse: 0, 1 or 2");
+    p->ps32_fuse = (int)value;
   } else if (k == "profile") {
     p->profiling = value != 0;  // events around every kernel of the following calls; read with vmk_profile_read
     if (p->child) p->child->profiling = p->profiling;

@@ -245,6 +245,81 @@ VMK_HD void kxs_body(const Ctx& c, const KXSArgs& ka) {
   }
 }
 
+// E1 + E2 fused into the inverse row transform (opt-in, set_option "ps32_fuse" = 2).  The fold along i is linear in kx
+// (with a conjugation on the mirrored term), so it commutes with the transform along j: conj(V[k][py]) is the inverse
+// transform of conj(Y[k][-ky' mod L]).  K3's input is therefore  VF = ifft_j(YF)  with, for kx' >= 1,
+//   YF[kx'][ky'] = Y[kx'][ky'] w^{-kx' rx} + conj(Y[L-kx'][-ky']) w^{(L-kx') rx}
+// and for the packed row (real parts in E2 = Hermitian parts here)
+//   YF[0][ky'] = (Y[0][ky'] + conj Y[0][-ky'])/2 + Y[L][ky'] w^{-L rx} + conj(Y[L][-ky']) w^{L rx}
+//                + i ( Y[L/2][ky'] w^{-(L/2) rx} + conj(Y[L/2][-ky']) w^{(L/2) rx} ),
+// Y being p32_spectra_body's folded spectra, all computed from S in the load stage (tests/models/ps32_model.py,
+// spectra_folded: 2e-16 against fold-after-transform).  Row = (q, rx, ry, kx'): 36 (L/2) transforms instead of
+// 12 (L+1), but the spectra are never written or re-read and E2 disappears.
+template <class C>
+VMK_HD void kxf_body(const Ctx& c, const KXSArgs& ka) {
+  using F = Fft<C>;
+  constexpr int E = C::E, T = C::T, P = C::P;
+  constexpr int bl = C::bits(P - 1), rl = 1 << bl;
+  static_assert(!C::SPLIT, "kxf_body uses the plain exchange buffer");
+  const P32Args& a = ka.a;
+  double2* tw = F::tables(c.smem);
+  F::load_tables(c, tw, ka.tw);
+  c.sync();
+  const int g = c.tid / T, t = c.tid % T;
+  double2* sm = F::xbuf(c.smem, g);
+  const int L = a.L, M = 3 * L, W = 2 * L + 1, h = L / 2;  // L == N
+  const int nblocks = (ka.nrows + C::FPC - 1) / C::FPC;
+  for (int rb = c.bid; rb < nblocks; rb += c.nblk) {
+    const int slot = rb * C::FPC + g;
+    const bool active = slot < ka.nrows;
+    const int row = active ? slot : ka.nrows - 1;  // spare slots redo the last row, only the store is conditional
+    const int kxp = row % h, ry = (row / h) % 3, rx = (row / (3 * h)) % 3, q = row / (9 * h);
+    const bool xdir = (q == 0 || q == 3), div = (q == 0 || q == 2);
+    // Y[q][kx][ry][kp] of p32_spectra_body
+    auto yval = [&](int kx, int kp) {
+      const int kxc = kx + L;
+      const double2* srow = a.S + (size_t)kx * W;
+      const double cxr = ld_ro(a.cc + kxc), dxr = ld_ro(a.dd + kxc), mpr = ld_ro(a.mp + kxc), mmr = ld_ro(a.mm + kxc);
+      const double kxx = ld_ro(a.ksq + kxc);
+      auto mode = [&](int col) {
+        const double2 s = srow[col];
+        double f = xdir ? cxr * ld_ro(a.mp + col) + dxr * ld_ro(a.mm + col) : mpr * ld_ro(a.cc + col) + mmr * ld_ro(a.dd + col);
+        f = f * a.scale;
+        if (div) f = f * (1.0 / (kxx + ld_ro(a.ksq + col)));
+        return mk2(-s.y * f, s.x * f);
+      };
+      double2 y = cadd(cmul(mode(kp + L), ld_ro2(a.twM + (M - kp * ry) % M)), cmul(mode(kp), ld_ro2(a.twM + (L - kp) * ry)));
+      if (kp == 0) y = cadd(y, cmul(mode(2 * L), ld_ro2(a.twM + (M - L * ry) % M)));
+      return y;
+    };
+    double2 v[E];
+    static_for<0, E>([&](auto e_) {
+      constexpr int e = decltype(e_)::value, u = e / rl, p = e % rl;
+      const int kp = F::k_of_pos(((t + T * u) << bl) | p);
+      const int km = (L - kp) % L;  // -ky' mod L
+      if (kxp >= 1) {
+        v[e] = cadd(cmul(yval(kxp, kp), ld_ro2(a.twM + (M - kxp * rx) % M)),
+                    cmul(cconj(yval(L - kxp, km)), ld_ro2(a.twM + (L - kxp) * rx)));
+      } else {
+        const double2 wl = ld_ro2(a.twM + (M - L * rx) % M), wh = ld_ro2(a.twM + (M - h * rx) % M);
+        const double2 y0 = cadd(cscale(cadd(yval(0, kp), cconj(yval(0, km))), .5),
+                                cadd(cmul(yval(L, kp), wl), cmul(cconj(yval(L, km)), cconj(wl))));
+        const double2 yh = cadd(cmul(yval(h, kp), wh), cmul(cconj(yval(h, km)), cconj(wh)));
+        v[e] = mk2(y0.x - yh.y, y0.y + yh.x);  // y0 + i yh
+      }
+    });
+    c.sync();  // the previous row's last exchange has been read everywhere
+    F::inverse(c, v, sm, tw, t);
+    if (active) {
+      double2* dst = a.VF + (((size_t)q * h + kxp) * 9 + (rx * 3 + ry)) * L;
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        dst[F::template own_pos<e>(t)] = v[e];
+      });
+    }
+  }
+}
+
 // E2: fold along i.  VF[q][rx][ry][kx'][py] = sum over kx = kx' mod L (Hermitian completion in kx) of V w^{-kx rx};
 // row kx' = 0 packs the (real) kx' = 0 and kx' = L/2 lines as K3 expects
 VMK_HD void p32_fold_body(const Ctx& c, const P32Args& a) {

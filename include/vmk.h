@@ -172,7 +172,8 @@ int vmk_profile_read(vmk_plan* plan, double* ms, int64_t* launches);
 int64_t vmk_launch_count(vmk_plan* plan);
 /* tuning knobs (integers; defaults are the measured best, see profiles/r01_notes.md):
  *   "ps32_fuse"   0      3/2 rule: 1 = the four derivative spectra are computed in the load stage of the inverse row
- *                        transform instead of being written and read back (validated on the host emulator only so far)
+ *                        transform instead of being written and read back; 2 = and folded along i there, so that the
+ *                        transform writes K3's input directly (both validated on the host emulator only so far)
  *   "profile"     0      1: bracket every kernel with events (see vmk_profile_read)
  *   "graph"       1      replay the step (kernels, copies, barriers) from a CUDA graph
  *   "k4_rows"     32     rows marched by one K4 thread column (shortened automatically on small slabs)

@@ -82,6 +82,27 @@ class Model32:
             VF[:, rx, :, 0, :] = y0.real + 1j * yh.real
         return VF
 
+    # E1 + E2 as ONE spectral-space pass (design for the next fusion step, not yet a kernel): the fold along i is linear
+    # in kx (with a conjugation on the mirrored term), so it commutes with the transform along j -- conj(V[k][py]) is the
+    # inverse transform of conj(Y[k][-ky' mod L]) -- and K3's input can be produced as  VF = ifft_j(YF)  with YF computed
+    # from S directly.  The packed row takes real parts in E2; in spectral space Re(v) is (Y[ky'] + conj Y[-ky'])/2.
+    def spectra_folded(self, S):
+        L = self.L
+        h = L // 2
+        Y = self.spectra(S)                                   # [q][kx][ry][ky']
+        Ym = np.conj(Y[..., np.mod(-np.arange(L), L)])        # conj(Y[..][-ky' mod L]): spectrum of conj(V)
+        YF = np.zeros((4, 3, 3, h, L), complex)
+        for rx in range(3):
+            kxp = np.arange(1, h)
+            yi = (Y[:, kxp] * self.w(-kxp * rx)[None, :, None, None] +
+                  Ym[:, L - kxp] * self.w(-(kxp - L) * rx)[None, :, None, None])
+            YF[:, rx, :, 1:, :] = np.transpose(yi, (0, 2, 1, 3))
+            wl, wh = self.w(-L * rx), self.w(-h * rx)
+            y0 = (Y[:, 0] + Ym[:, 0]) / 2 + Y[:, L] * wl + Ym[:, L] * np.conj(wl)
+            yh = Y[:, h] * wh + Ym[:, h] * np.conj(wh)
+            YF[:, rx, :, 0, :] = y0 + 1j * yh
+        return YF
+
     @staticmethod
     def k3(VF):  # [..., L/2 (packed), L(py)] -> real [..., px, py]: out[px] = sum over the Hermitian-completed kx'
         h, L = VF.shape[-2], VF.shape[-1]
@@ -191,3 +212,7 @@ if __name__ == "__main__":
             S = m.step(S)
         u = m.field(S)
         print(n, np.linalg.norm(u - ref) / np.linalg.norm(ref))
+        # the one-pass form of E1 + E2 equals the two-pass form
+        a = m.fold_i(np.fft.ifft(m.spectra(S), axis=-1) * m.L)
+        b = np.fft.ifft(m.spectra_folded(S), axis=-1) * m.L
+        print("   folded-spectra form vs fold after transform:", np.linalg.norm(a - b) / np.linalg.norm(a))

@@ -231,23 +231,27 @@ def check_spectral_tgv(cm, which, n, nt, dt=.01, re=10., tol=1e-12):
     return ut
 
 
-def check_ps32_fused(cm, onp, n, nt, noise=.5):
-    """the opt-in fused kernel of the 3/2 rule (set_option "ps32_fuse": spectra computed in the load stage of the inverse
-    row transform) against the default path -- the arithmetic is the same, so the fields must be bit-identical -- and
-    against the oracle"""
+def check_ps32_fused(cm, onp, n, nt, noise=.5, mode=1):
+    """the opt-in fused kernels of the 3/2 rule (set_option "ps32_fuse") against the default path and the oracle.
+    mode 1: spectra computed in the load stage of the inverse row transform -- same arithmetic, so the fields must be
+    bit-identical; mode 2: also folded along i there (fold before the transform instead of after: equal to rounding)"""
     dx, dy, x, y = grid(n)
     w = vm_field(n) + noise * noise_field(n, 5)
     p = cm.plan(n, n)
     p.set_option("ps32_fuse", 0)
     a = cm.numerical_ps32(n, n, nt, dx, dy, 1e-3, 1000., x, y, w, 1)
     l0 = p.launch_count
-    p.set_option("ps32_fuse", 1)
+    p.set_option("ps32_fuse", mode)
     try:
         b = cm.numerical_ps32(n, n, nt, dx, dy, 1e-3, 1000., x, y, w, 1)
     finally:
         p.set_option("ps32_fuse", 0)
-    assert p.launch_count - l0 == 7 + 33 * nt  # 4 (upload, K1, KX, E0) + 11 per stage, one less than the default + 3
-    assert np.array_equal(a, b)
+    per_stage = {1: 11, 2: 10}[mode]  # default: 12
+    assert p.launch_count - l0 == 7 + 3 * per_stage * nt  # 4 (upload, K1, KX, E0) + stages + 3 (final field)
+    if mode == 1:
+        assert np.array_equal(a, b)
+    else:
+        assert rel_l2(b, a) < 1e-13
     assert rel_l2(b, onp.ps_numerical(32, n, n, nt, dx, dy, 1e-3, 1000., w)) < TOL_RUN
 
 

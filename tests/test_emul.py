@@ -133,9 +133,17 @@ def test_pseudospectral_32_rule_defaults_40_steps(emul, oracle_np):
     pc.check_ps32(emul, oracle_np, 128, 40, dt=.01, ns=2, noise=0.)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("n,nt", [(64, 3), (128, 2), (512, 1)])
-def test_pseudospectral_32_rule_fused_option(emul, oracle_np, n, nt):
-    pc.check_ps32_fused(emul, oracle_np, n, nt)
+def test_pseudospectral_32_rule_fused_option(emul, oracle_np, n, nt, mode):
+    pc.check_ps32_fused(emul, oracle_np, n, nt, mode=mode)
+
+
+def test_pseudospectral_32_rule_fused_white_noise_and_option_range(emul, oracle_np):
+    from cfd_julia_b200.common import VmkError
+    pc.check_ps32_fused(emul, oracle_np, 64, 2, noise=1., mode=2)
+    with pytest.raises(VmkError):
+        emul.plan(64, 64).set_option("ps32_fuse", 3)
 
 
 def test_pseudospectral_32_rule_errors(emul):

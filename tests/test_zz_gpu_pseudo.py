@@ -101,8 +101,10 @@ def test_golden_f_rows(gpu):
     pc.check_golden_f_rows(gpu)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("n,nt", [(64, 5), (256, 3), (1024, 2)])
-def test_pseudospectral_32_rule_fused_option(gpu, oracle_np, n, nt):
-    """opt-in kernel (default off; emulator-validated only when it was written): must equal the default path bit for bit"""
-    pc.check_ps32_fused(gpu, oracle_np, n, nt)
+def test_pseudospectral_32_rule_fused_option(gpu, oracle_np, n, nt, mode):
+    """opt-in kernels (default off; emulator-validated only when they were written): mode 1 must equal the default path
+    bit for bit, mode 2 to rounding"""
+    pc.check_ps32_fused(gpu, oracle_np, n, nt, mode=mode)
     gpu.clear_plans()
