@@ -22,6 +22,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -32,7 +33,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "vortex_merger_grid_point_steps_per_s_8192x8192_fp64"
+def metric_name(n):
+    """BASELINE.json's metric, named after the grid the run actually used."""
+    return f"vortex_merger_grid_point_steps_per_s_{n}x{n}_fp64"
+
+
 UNIT = "grid-point-steps/s"
 BYTES_PER_POINT_STEP = 232.0  # SURVEY 8d
 # algorithmic bytes per grid point per launch (DESIGN.md): K1/K2/K3 read 8 + write 8; K4 reads w, psi (+wn) and writes
@@ -110,10 +115,21 @@ def vm_initial_condition(n, j0=0, nj=None):
     return dx, w
 
 
-def cpu_sample(n, steps, warmup=0):
-    """The oracle port on the host cores: returns (grid-point-steps/s, threads, seconds per step)."""
+def host_threads():
+    """Hardware threads this process may use (affinity mask), ignoring OMP_NUM_THREADS: torch.distributed.run
+    exports OMP_NUM_THREADS=1 to its workers, which made round 1's reference arm run on one thread."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample(n, steps, warmup=0, threads=None):
+    """The oracle port on the host cores with an explicit OpenMP thread count:
+    returns (grid-point-steps/s, threads, seconds per step)."""
     from oracle import oracle_c as oc
     oc.build()
+    oc.set_num_threads(threads or host_threads())
     dx, w = vm_initial_condition(n)
     dt = min(.01, DT * (8192. / n)**2)
     if warmup:
@@ -124,28 +140,101 @@ def cpu_sample(n, steps, warmup=0):
     return n * n * steps / el, oc.num_threads(), el / steps
 
 
+def julia_probe(n, dt):
+    """the real reference, if this box has it.  `julia` on PATH + CFD_JULIA_REFERENCE pointing at a
+    checkout of the reference -> time vm.jl's own `numerical` through oracle/julia_shim/time_vm.jl (1 Julia thread,
+    as the reference runs).  Otherwise say what is missing; never fatal."""
+    exe = shutil.which("julia")
+    if not exe:
+        return {"julia": "absent", "which": None}
+    ref = os.environ.get("CFD_JULIA_REFERENCE", "")
+    if not os.path.isdir(ref):
+        return {"julia": "present, reference checkout absent (set CFD_JULIA_REFERENCE)", "which": exe}
+    try:
+        out = subprocess.run([exe, "-t", "1", os.path.join(ROOT, "oracle", "julia_shim", "time_vm.jl"), str(n), "1",
+                              repr(dt)], capture_output=True, text=True, timeout=900)
+        last = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if out.returncode == 0 and last:
+            return {"julia": "ran", "which": exe, **json.loads(last[-1])}
+        return {"julia": f"failed rc={out.returncode}", "which": exe, "stderr": out.stderr[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"julia": f"failed: {e}", "which": exe}
+
+
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the CPU.  Julia + FFTW.jl are not in the image, so this is
-    the oracle port (kind "port"), all host threads (OpenMP), on a bounded 4096^2 sample of the workload."""
+    """--impl reference: the reference's algorithm on the CPU at the SAME grid as the b200 arm.  Julia + FFTW.jl are
+    not in the image, so this is the oracle port (kind "port") with all host threads (OpenMP, count set explicitly);
+    a 1-thread figure (the reference itself is single-threaded, vm.jl:24) is reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n = args.cpu_n
-    v, threads, s_per_step = cpu_sample(n, args.steps, args.warmup)
+    n = args.n
+    nthr = host_threads()
+    # bounded: at 8192^2 one RK3 step of the port is ~2 s on 16 threads; cap the run at ~3 minutes
+    dt = min(.01, DT * (8192. / n)**2)
+    v1 = t1 = None
+    if not args.no_cpu_1thread:
+        # one step on ONE thread, on a grid small enough to stay below ~30 s (per-point cost is size-independent
+        # to within the log N of the FFT)
+        n1 = min(n, 4096)
+        v1, _, t1 = cpu_sample(n1, 1, 0, threads=1)
+    steps, warm = args.steps, min(args.warmup, 1)
+    v, threads, s_per_step = cpu_sample(n, 1, 0, threads=nthr)  # probe one step
+    budget_s = 170.
+    steps = int(max(1, min(steps, budget_s // max(s_per_step, 1e-9))))
+    if steps > 1:
+        v, threads, s_per_step = cpu_sample(n, steps, warm, threads=nthr)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": metric_name(n), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "vortex merger 8192x8192 periodic, Re=1000, RK3 + FFT Poisson (BASELINE configs[3])",
-                   "sample": f"{n}x{n} grid, same IC and Re, dt scaled with dx^2"},
+        "config": workload_config(n, dt),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"oracle/vm_oracle.c (OpenMP, {threads} threads), {args.steps} RK3 steps at {n}x{n}; "
-                                   "Julia/FFTW.jl absent from the image"},
+                         "sample": f"oracle/vm_oracle.c (OpenMP, {threads} threads set explicitly; OMP_NUM_THREADS of the "
+                                   f"launcher ignored), {steps} RK3 steps of the same {n}x{n} workload, "
+                                   f"{s_per_step:.2f} s/step; Julia/FFTW.jl absent from the image",
+                         "value_1thread": v1,
+                         "sample_1thread": None if v1 is None else
+                         f"1 RK3 step at {min(n, 4096)}x{min(n, 4096)} on 1 thread ({t1:.1f} s); the Julia reference is "
+                         "single-threaded (vm.jl:24)",
+                         "host_threads": nthr, **julia_probe(min(n, 2048), min(.01, DT * (8192. / min(n, 2048))**2))},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def workload_config(n, dt):
+    return {"workload": f"vortex merger {n}x{n} periodic, Re=1000, dt={dt:.3g}, RK3 + FFT Poisson "
+                        + ("(BASELINE configs[3])" if n == 8192 else
+                           "(BASELINE configs[4])" if n == 32768 else "(not the headline size)")}
+
+
+def parity_probe(lib, Plan, n, world, rank, gather, steps=3):
+    """Outside the timed region: `steps` RK3 steps of an n x n vortex merger on the SAME rank layout as the benchmark,
+    compared with the C oracle on every rank's slab -- so that the scaling runs carry multi-GPU correctness."""
+    from oracle import oracle_c as oc
+    oc.build()
+    oc.set_num_threads(max(1, host_threads() // max(world, 1)))
+    dx, w0 = vm_initial_condition(n)
+    dt = min(.01, 1e-4 * (8192. / n)**2)
+    plan = Plan(lib, n, n, rank, world)
+    if world > 1:
+        plan.attach_peers(gather)
+    plan.upload(w0)
+    plan.step(dx, dx, dt, RE, steps)
+    plan.sync()
+    w = np.zeros_like(w0)
+    psi = np.zeros_like(w0)
+    plan.download(w, psi)
+    ref = w0.copy(order="F")
+    _, psi_ref = oc.numerical(n, n, steps, dx, dx, dt, RE, ref)
+    nj = n // world
+    sl = (slice(None), slice(rank * nj + 1, rank * nj + nj + 1))  # the rank's own interior columns, all i
+    ew = float(np.linalg.norm(w[sl] - ref[sl]) / np.linalg.norm(ref[sl]))
+    ep = float(np.linalg.norm(psi[sl] - psi_ref[sl]) / np.linalg.norm(psi_ref[sl]))
+    return plan, {"n": n, "steps": steps, "rel_l2_w": ew, "rel_l2_psi": ep}
 
 
 def main():
@@ -157,7 +246,8 @@ def main():
     ap.add_argument("--n", "--size", dest="n", type=int, default=8192,
                     help="grid size (default: the BASELINE workload); use --size under torchrun, whose own parser "
                          "takes a bare --n for an abbreviation of its options")
-    ap.add_argument("--cpu-n", type=int, default=4096, help="grid size of the --impl reference sample")
+    ap.add_argument("--no-cpu-1thread", action="store_true", help="reference arm: skip the 1-thread sample")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed 1024^2 x 3-step oracle comparison")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -259,8 +349,12 @@ def main():
                 "kernels": kern,
                 "step": {"achieved": step_gbs, "frac": step_gbs / peak, "frac_of_8TBs": step_gbs / 8000.,
                          "bytes_per_point_step": BYTES_PER_POINT_STEP}}
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this command at 8192^2 on one
+    # GPU (profiles/traffic.json, tools/ncu_summary.py); a capture exists for that configuration only
+    roofline["kernel_times"] = ("CUDA events around every launch in a separate un-graphed pass (vmk_profile_steps); "
+                                "their sum can exceed the graph-replayed step, use them as shares")
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if top and os.path.exists(traffic_file):
+    if top and world == 1 and n == 8192 and os.path.exists(traffic_file):
         try:
             roofline["traffic"] = json.load(open(traffic_file)).get(top)
         except Exception:  # noqa: BLE001
@@ -287,26 +381,45 @@ def main():
                "d2h_bytes_per_step": slab_bytes * world / K,
                "call": f"vmk_numerical(nt={K}) on a pinned host array: upload + {K} steps + download"}
 
+    # ---- parity, outside the timed region, on the same rank layout (all ranks take part) -------------------------------
+    parity = None
+    if not args.no_parity:
+        def _gather2(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        pn = min(n, 1024)
+        pplan, parity = parity_probe(lib, Plan, pn, world, rank, _gather2 if dist is not None else None)
+        if dist is not None:
+            t = torch.tensor([parity["rel_l2_w"], parity["rel_l2_psi"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            parity["rel_l2_w"], parity["rel_l2_psi"] = float(t[0].item()), float(t[1].item())
+            dist.barrier()
+        pplan.close()
+        parity["against"] = "oracle/vm_oracle.c, max over ranks of each rank's own slab"
+        parity["ok"] = bool(parity["rel_l2_w"] < 1e-10 and parity["rel_l2_psi"] < 1e-10)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, threads, sps = cpu_sample(n, 2)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle/vm_oracle.c (OpenMP, {threads} threads): 2 RK3 steps of the same {n}x{n} workload, "
-                         f"{sps:.2f} s/step; Julia/FFTW.jl absent from the image"}
+               "sample": f"oracle/vm_oracle.c (OpenMP, {threads} threads set explicitly): 2 RK3 steps of the same {n}x{n} "
+                         f"workload, {sps:.2f} s/step; Julia/FFTW.jl absent from the image",
+               **julia_probe(min(n, 2048), min(.01, 1e-4 * (8192. / min(n, 2048))**2))}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(n), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"vortex merger {n}x{n} periodic, Re=1000, dt={DT:.3g}, RK3 + FFT Poisson "
-                                   + ("(BASELINE configs[3])" if n == 8192 else "(not the headline size)"),
+            "config": {**workload_config(n, DT),
                        "l2": f"working set {plan.device_bytes / 1e9:.1f} GB >> 126 MB L2, no flush needed",
                        "parallelism": f"slab{world}" if world > 1 else "single GPU",
-                       "exchange": "peer loads/stores over NVLink inside K2/K3/K4 + device-side flag barrier"
+                       "exchange": "peer stores over NVLink inside K1/K2/K3/K4 + device-side flag barriers"
                        if world > 1 else None,
                        "cuda_graph": True},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "parity": parity,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -47,6 +47,8 @@ def lib():
                                          C.POINTER(C.c_double), _dp, _dp]
         L.orc_fft2.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_set_num_threads.restype = None
         _lib = L
     return _lib
 
@@ -110,3 +112,7 @@ def fft2(a, sign=-1):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int):
+    lib().orc_set_num_threads(int(n))

@@ -8,9 +8,11 @@ vm.jl:12-90, tgv.jl:82-90, fft_p.jl:8-42) but uses numpy's pocketfft instead of 
 radix-2 FFT, so the two oracles cross-check each other's FFT and index conventions.
 Arrays are Fortran-ordered (column-major, like Julia); "ghosted" = shape (nx+2, ny+2).
 
-Parity pin: order.jl:13 (five fft_p.jl L2 errors) -- see tests/test_oracle.py.  Beyond that
-pin and the analytic Taylor-Green solution the reference's outputs are unrecorded and Julia
-is not installed here: "parity unpinned".
+Parity pins (tests/test_oracle.py): order.jl:13 (five fft_p.jl L2 errors); the outputs of the reference's own
+Python twins of script 19 run unmodified (tests/golden/make_ref_fixtures.py -> tests/golden/ref_py_*.npz, agreement
+4e-16..4e-15 on vorticity, streamfunction, rhs); the analytic Taylor-Green solution.  The Julia scripts themselves
+cannot run here (no julia / FFTW), so the f-row solvers (hybrid, pseudo-spectral, cavity) stay pinned only through
+the shared Arakawa / Poisson pieces and closed-form solutions: "parity unpinned" for their script-specific parts.
 """
 from __future__ import annotations
 

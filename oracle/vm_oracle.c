@@ -25,13 +25,18 @@
  * scaled by 1/N (inverse), which is FFTW's published definition, evaluated by an iterative
  * radix-2 Cooley-Tukey with twiddles rounded from long double.
  *
- * Parity pin: the only recorded outputs of the reference on this path are the five L2 errors
- * of fft_p.jl hard-coded at 13_Poisson_Solver_FFT_Spectral/specrtral_vs_FDM/order.jl:13;
- * tests/test_oracle.py checks orc_ps_fft against all five.  The stencil/RK3 part has no
- * recorded reference output (the reference ships no tests): it is pinned only against the
- * analytic Taylor-Green solution (tgv.jl:87) and against the independent numpy restatement
- * in oracle/oracle_np.py.  Julia is not installed in the build container, so the reference
- * itself cannot be run: beyond those pins, "parity unpinned".
+ * Parity pins (tests/test_oracle.py):
+ *   (1) the five L2 errors of fft_p.jl hard-coded at 13_Poisson_Solver_FFT_Spectral/specrtral_vs_FDM/order.jl:13
+ *       (orc_ps_fft reproduces all five);
+ *   (2) outputs of the REFERENCE'S OWN CODE for the whole step: its two Python twins of script 19
+ *       (19_NS2D_Vortex_Merger/Python_Vectorized/fdm_vortex_merge_vectorized.py:31-129,221-256 and
+ *       Python/fdm_vortex_merger.py), executed unmodified in the build container with a pyfftw->numpy.fft shim by
+ *       tests/golden/make_ref_fixtures.py; committed as tests/golden/ref_py_*.npz (vorticity + streamfunction after
+ *       10-50 RK3 steps at 32^2..128^2, one rhs and one Poisson solve on white noise).  This file agrees with them
+ *       to 4e-16..4e-15 (gate 1e-12);
+ *   (3) the analytic Taylor-Green solution (tgv.jl:87) and the independent numpy restatement oracle/oracle_np.py.
+ * The Julia scripts themselves cannot run here (no julia, no libfftw3, un-vendored Unroll/Utils packages), so there
+ * is no oracle/_ref build; the Julia-vs-Python-twin differences are listed in make_ref_fixtures.py (rounding level).
  *
  * Layout: all arrays are column-major like Julia.  "ghosted" = (nx+2) x (ny+2) doubles,
  * element (i,j) 1-based at [(i-1) + (nx+2)*(j-1)].
@@ -370,6 +375,15 @@ double orc_l2norm_bnds(int nx, int ny, const double *r) {
 
 /* plain 2-D DFT for the FFT-kernel unit tests: a is nx x ny interleaved complex, in place */
 int orc_fft2(int nx, int ny, double *a, int sign) { return fft2d(nx, ny, (cplx *)a, sign); }
+
+/* bench.py sets the thread count explicitly (torchrun exports OMP_NUM_THREADS=1 to its workers) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 int orc_num_threads(void) {
 #ifdef _OPENMP

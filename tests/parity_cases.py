@@ -53,11 +53,16 @@ def check_numerical(cm, oc, w0, nt, dt, re, tol=TOL_RUN):
     wa = w0.copy(order="F")
     wb = w0.copy(order="F")
     out = cm.numerical_tgv(n, n, nt, dx, dy, dt, re, wa)
-    ref, _ = oc.numerical(n, n, nt, dx, dy, dt, re, wb)
+    ref, psi_ref = oc.numerical(n, n, nt, dx, dy, dt, re, wb)
     assert out.shape == (n + 1, n + 1)
     assert rel_l2(out, ref) < tol
     assert rel_l2(wa, wb) < tol  # wn mutated in place, ghosts valid
     assert np.array_equal(out, wa[1:n + 2, 1:n + 2])
+    # north_star: vorticity AND streamfunction.  The plan still holds the run's state: psi of the last rhs
+    # evaluation (stage 3's input), which is what the reference's `s` holds on return (vm.jl:60, Common.jl:123,138-146)
+    psi = np.zeros_like(wa)
+    cm.plan(n, n).download(None, psi)
+    assert rel_l2(psi, psi_ref) < tol
     return out
 
 
@@ -81,6 +86,44 @@ def check_golden(cm):
     wn = np.asfortranarray(g["w0"].copy())
     out = cm.numerical_tgv(64, 64, int(g["nt"]), float(g["dx"]), float(g["dy"]), float(g["dt"]), float(g["re"]), wn)
     assert rel_l2(out, g["out"]) < TOL_RUN
+
+
+# ---- vectors computed by the REFERENCE'S OWN code (its Python twins of script 19, tests/golden/make_ref_fixtures.py)
+REF_PY = ("vec_64_50", "vec_128_20", "loop_32_10")
+# The twins differ from vm.jl / Common.jl at rounding level only (no wavenumber wrap, `gg` inside j1..j3, lap/re,
+# (1/3)*w instead of w/3, rhs also on the duplicate point): observed 4e-16 .. 4e-15 for both oracles and the kernels.
+TOL_REF_PY = 1e-12
+
+
+def check_ref_py(numerical, vm_rhs, tag):
+    """`numerical(n, nt, dx, dy, dt, re, wn)` mutates wn; `vm_rhs(n, dx, dy, re, w, r, s, f)` fills r, s, f -- bound to
+    an oracle or to a library under test.  Same initial field as the reference run (identical initial conditions),
+    then vorticity and streamfunction after the fixture's number of steps, and one rhs / Poisson solve on white noise."""
+    g = np.load(f"{GOLD}/ref_py_{tag}.npz")
+    n, nt = int(g["n"]), int(g["nsteps"])
+    dx, dy, dt, re = float(g["dx"]), float(g["dy"]), float(g["dt"]), float(g["re"])
+    assert np.array_equal(vm_field(n), g["w0"])  # this repo's vm_ic + ghost fill == the twin's, bit for bit
+    wn = np.asfortranarray(g["w0"].copy())
+    numerical(n, nt, dx, dy, dt, re, wn)
+    assert rel_l2(wn, g["w"]) < TOL_REF_PY
+    r, s, f = np.zeros_like(wn), np.zeros_like(wn), np.zeros((n, n), order="F")
+    vm_rhs(n, dx, dy, re, wn, r, s, f)  # the twin's `s` on exit is fps(-w_final) + periodic fill (:252-253)
+    assert rel_l2(s, g["s"]) < TOL_REF_PY
+    if "noise_w" in g:
+        w = np.asfortranarray(g["noise_w"].copy())
+        vm_rhs(n, dx, dy, re, w, r, s, f)
+        assert rel_l2(s, g["noise_s"]) < TOL_REF_PY
+        assert rel_l2(r[1:n + 1, 1:n + 1], g["noise_r"]) < TOL_REF_PY
+
+
+def check_ref_py_lib(cm, tag):
+    check_ref_py(lambda n, nt, dx, dy, dt, re, wn: cm.numerical_tgv(n, n, nt, dx, dy, dt, re, wn),
+                 lambda n, dx, dy, re, w, r, s, f: cm.vm_rhs(n, n, dx, dy, re, w, None, None, None, None, r, s, f), tag)
+
+
+def check_ref_py_oracle(o, tag):
+    check_ref_py(lambda n, nt, dx, dy, dt, re, wn: o.numerical(n, n, nt, dx, dy, dt, re, wn),
+                 lambda n, dx, dy, re, w, r, s, f: o.vm_rhs(n, n, dx, dy, re, w, r, s, f), tag)
 
 
 def check_golden_f_rows(cm):

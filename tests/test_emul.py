@@ -370,3 +370,9 @@ def _slab_run(emul, oracle_c, n, nranks):
         assert rel_l2(psis[r][:, rows], s[:, rows]) < 1e-12
     for p in plans:
         p.close()
+
+
+@pytest.mark.parametrize("tag", pc.REF_PY)
+def test_ref_py_fixtures(emul, tag):
+    """vectors computed by the reference's own Python twins of script 19 (tests/golden/make_ref_fixtures.py)"""
+    pc.check_ref_py_lib(emul, tag)

@@ -42,6 +42,14 @@ def test_rhs_noise(gpu, oracle_c, n):
         gpu.clear_plans()
 
 
+@pytest.mark.parametrize("tag", pc.REF_PY)
+def test_ref_py_fixtures(gpu, tag):
+    """The CUDA path against vectors computed by the REFERENCE'S OWN code: its two Python twins of script 19, run
+    unmodified (tests/golden/make_ref_fixtures.py): vorticity and streamfunction after 10-50 RK3 steps from the twin's
+    initial field, plus one rhs / Poisson solve on white noise.  Tolerance 1e-12 (parity_cases.TOL_REF_PY)."""
+    pc.check_ref_py_lib(gpu, tag)
+
+
 def test_rhs_vm_ic(gpu, oracle_c):
     pc.check_rhs(gpu, oracle_c, vm_field(128))
 

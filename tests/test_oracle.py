@@ -6,6 +6,8 @@ import os
 import numpy as np
 import pytest
 
+import parity_cases as pc
+
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -158,3 +160,14 @@ def test_pseudospectral_rules_dealias(oracle_np):
     j23 = oracle_np.ps23_jacobian(n, n, dx, dx, wf, k2)
     j32 = oracle_np.ps32_jacobian(n, n, dx, dx, wf, k2)
     assert np.linalg.norm(j23 - j32) / np.linalg.norm(j32) < 1e-13
+
+
+# ---- pinned on the reference's own code: its Python twins of script 19 run unmodified (make_ref_fixtures.py) ----
+@pytest.mark.parametrize("tag", pc.REF_PY)
+def test_ref_py_oracle_c(oracle_c, tag):
+    pc.check_ref_py_oracle(oracle_c, tag)
+
+
+@pytest.mark.parametrize("tag", pc.REF_PY)
+def test_ref_py_oracle_np(oracle_np, tag):
+    pc.check_ref_py_oracle(oracle_np, tag)
