@@ -22,7 +22,8 @@ def gpu():
     import cfd_julia_b200
     from cfd_julia_b200.common import Common
     lib = cfd_julia_b200.default_library()  # raises if libvmk.so is missing: no fallback
-    assert lib.prefix == "vmk_" and lib.path.endswith("libvmk.so")
+    # (VMK_LIB: an explicitly chosen build of the same CUDA library, e.g. tools/devbuild.sh during kernel tuning)
+    assert lib.prefix == "vmk_" and (lib.path.endswith("libvmk.so") or os.environ.get("VMK_LIB") == lib.path)
     cm = Common(lib)
     yield cm
     cm.clear_plans()
