@@ -100,14 +100,6 @@ struct SizeOps {
   int (*k1)(int grid, const K1Args&, Stream&);
   int (*k2)(int grid, const K2Args&, Stream&);
   int (*k3)(int grid, const K3Args&, Stream&);
-  // K2 as two independent half-size CTAs per SM (k2h_body; N = 8192 on one GPU), null elsewhere
-  size_t twn_h;                                  // twiddle entries of the N/2-point configuration
-  int dif_n;                                     // entries of the decimation twiddle table
-  void (*fill_tw_h)(double2*);
-  void (*fill_ccperm_h)(const double* cccos, double* out);  // [2][N/2]
-  int (*k2h_configure)(int* res);
-  int (*k2h)(int grid, const K2HArgs&, Stream&);
-  int (*k3s)(int grid, const K3Args&, Stream&);  // K3 for K2H's pieces (k3_body<.., true, true>)
   // hybrid RK3/CN solver (vmk_hybrid.cuh); null for the cluster sizes
   int (*kh_configure)(int* res);
   int (*kh)(int grid, const KHArgs&, Stream&);
@@ -135,14 +127,6 @@ struct K2Body {
 template <class C, bool PIECES = false>
 struct K3Body {
   VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, PIECES>(c, a); }
-};
-template <class CH, class CF>
-struct K2HBody {
-  VMK_HD static void run(const Ctx& c, const K2HArgs& a) { k2h_body<CH, CF>(c, a); }
-};
-template <class C>
-struct K3SBody {
-  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, true, true>(c, a); }
 };
 template <class C>
 struct KHBody {
@@ -316,13 +300,6 @@ SizeOps make_cluster_ops() {
     return a.pieces ? be_launch_cluster<K3CBody<C, Q, true>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s)
                     : be_launch_cluster<K3CBody<C, Q>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
   };
-  o.twn_h = 0;
-  o.dif_n = 0;
-  o.fill_tw_h = nullptr;
-  o.fill_ccperm_h = nullptr;
-  o.k2h_configure = nullptr;
-  o.k2h = nullptr;
-  o.k3s = nullptr;
   o.kh_configure = nullptr;
   o.kh = nullptr;
   o.fill_ksqperm = nullptr;
@@ -340,8 +317,6 @@ SizeOps make_cluster_ops() {
 template <int M>
 SizeOps make_ops() {
   using C = typename CfgFor<M>::type;
-  using CM = typename CfgMain<M>::type;  // K1/K2/K3: same radices, tables and shared-memory footprint as C
-  static_assert(CM::TWN == C::TWN && CM::SMEM_BYTES == C::SMEM_BYTES && CM::FPC == C::FPC && CM::CT == C::CT, "");
   SizeOps o;
   o.twn = C::TWN;
   o.smem = C::SMEM_BYTES;
@@ -350,59 +325,25 @@ SizeOps make_ops() {
   o.fill_tw = &fill_twiddles<C>;
   o.fill_ccperm = &fill_ccperm<C>;
   o.configure = [](int* r1, int* r2, int* r3) -> int {
-    VMK_TRY((be_configure<K1Body<CM>, K1Args, C::CT, C::MINB>(C::SMEM_BYTES, r1)));
-    VMK_TRY((be_configure<K2Body<CM>, K2Args, C::CT, C::MINB>(C::SMEM_BYTES, r2)));
-    VMK_TRY((be_configure<K3Body<CM>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, r3)));
+    VMK_TRY((be_configure<K1Body<C>, K1Args, C::CT, C::MINB>(C::SMEM_BYTES, r1)));
+    VMK_TRY((be_configure<K2Body<C>, K2Args, C::CT, C::MINB>(C::SMEM_BYTES, r2)));
+    VMK_TRY((be_configure<K3Body<C>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, r3)));
     int dummy = 0;
-    VMK_TRY((be_configure<K2Body<CM, true>, K2Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
-    VMK_TRY((be_configure<K3Body<CM, true>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
+    VMK_TRY((be_configure<K2Body<C, true>, K2Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
+    VMK_TRY((be_configure<K3Body<C, true>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
     return 0;
   };
   o.k1 = [](int grid, const K1Args& a, Stream& s) -> int {
-    return be_launch<K1Body<CM>, K1Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    return be_launch<K1Body<C>, K1Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
   };
   o.k2 = [](int grid, const K2Args& a, Stream& s) -> int {
-    return a.pieces ? be_launch<K2Body<CM, true>, K2Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s)
-                    : be_launch<K2Body<CM>, K2Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    return a.pieces ? be_launch<K2Body<C, true>, K2Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s)
+                    : be_launch<K2Body<C>, K2Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
   };
   o.k3 = [](int grid, const K3Args& a, Stream& s) -> int {
-    return a.pieces ? be_launch<K3Body<CM, true>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s)
-                    : be_launch<K3Body<CM>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    return a.pieces ? be_launch<K3Body<C, true>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s)
+                    : be_launch<K3Body<C>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
   };
-  o.twn_h = 0;
-  o.dif_n = 0;
-  o.fill_tw_h = nullptr;
-  o.fill_ccperm_h = nullptr;
-  o.k2h_configure = nullptr;
-  o.k2h = nullptr;
-  o.k3s = nullptr;
-  if constexpr (HalfCfg<M>::available && !C::SPLIT) {
-    using CH = typename HalfCfg<M>::type;
-    using FH = Fft<CH>;
-    o.twn_h = CH::TWN;
-    o.dif_n = CH::T * (CH::E >> CH::bits(0));
-    o.fill_tw_h = &fill_twiddles<CH>;
-    o.fill_ccperm_h = [](const double* cccos, double* out) {
-      constexpr int bl = CH::bits(CH::P - 1), rl = 1 << bl;
-      for (int g = 0; g < 2; g++)
-        for (int u = 0; u < CH::E / rl; u++)
-          for (int p = 0; p < rl; p++)
-            for (int t = 0; t < CH::T; t++)
-              out[(size_t)g * CH::N + (u * rl + p) * CH::T + t] =
-                  cccos[2 * FH::k_of_pos(((t + CH::T * u) << bl) | p) + g];
-    };
-    o.k2h_configure = [](int* r) -> int {
-      int dummy = 0;
-      VMK_TRY((be_configure<K3SBody<CM>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
-      return be_configure<K2HBody<CH, CM>, K2HArgs, CH::CT, CH::MINB>(CH::SMEM_BYTES, r);
-    };
-    o.k2h = [](int grid, const K2HArgs& a, Stream& s) -> int {
-      return be_launch<K2HBody<CH, CM>, K2HArgs, CH::CT, CH::MINB>(grid, CH::SMEM_BYTES, a, s);
-    };
-    o.k3s = [](int grid, const K3Args& a, Stream& s) -> int {
-      return be_launch<K3SBody<CM>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
-    };
-  }
   if constexpr (C::SPLIT) {  // (measurement / test configurations with the split exchange buffer)
     o.kh_configure = nullptr;
     o.kh = nullptr;
@@ -442,7 +383,7 @@ SizeOps make_ops() {
 
 bool ops_for(int M, SizeOps* o) {
   switch (M) {
-#ifdef VMK_DEV_SIZES  // kernel-tuning builds only (tools/devbuild.sh): two sizes instead of thirteen, ~1 min of ptxas
+#ifdef VMK_DEV_SIZES  // kernel-tuning builds only (tools/devbuild.sh): two sizes instead of thirteen, ~2 min of ptxas
     case 10: *o = make_ops<10>(); return true;
     case 13: *o = make_ops<13>(); return true;
     default: return false;
@@ -502,12 +443,6 @@ struct vmk_plan {
   double* bbcos = nullptr;
   double* cccos = nullptr;
   double* ccperm = nullptr;
-  // K2 as half-size CTAs (k2h_body): tables and occupancy; k2_split: -1 auto (on where available), 0 off, 1 on
-  double2* tw_h = nullptr;
-  double2* dif_tw = nullptr;  // [dif_n] W_N^id
-  double2* wj = nullptr;      // [N/2] W_N^n
-  double* ccperm_h = nullptr; // [2][N/2]
-  int res_k2h = 0, k2_split = -1;
   double* staging = nullptr;  // (NJ+2) x (N+2), allocated on first host-array call
   // hybrid solver (vmk_hybrid_numerical), allocated on first use
   double2* hW = nullptr;      // vorticity spectrum [N/2][N], register order
@@ -627,10 +562,6 @@ int ensure_divisor(vmk_plan* p, double dx, double dy, double eps) {
   std::vector<double> cp(n);
   p->ops.fill_ccperm(c.data(), cp.data());
   VMK_TRY(be_h2d(p->ccperm, cp.data(), sizeof(double) * n, p->st));
-  if (p->ccperm_h) {
-    p->ops.fill_ccperm_h(c.data(), cp.data());
-    VMK_TRY(be_h2d(p->ccperm_h, cp.data(), sizeof(double) * n, p->st));
-  }
   VMK_TRY(be_sync(p->st));
   p->div_aa = -2.0 / (dx * dx) - 2.0 / (dy * dy);  // :101
   p->div_dx = dx;
@@ -733,12 +664,6 @@ int rowpair_units(const vmk_plan* p, int npairs, int g) {
   return (nblocks + g - 1) / g;
 }
 
-// one GPU, N = 8192: K2 as two independent half-size CTAs per SM (k2h_body), with K1 / K3 doing the outer radix-2
-// butterfly of the transform along j (k1_body / k3_body <.., SPLITJ>)
-bool k2_split_on(const vmk_plan* p) {
-  return p->nranks == 1 && p->v_pieces && p->ops.k2h && p->tw_h && p->k2_split != 0;
-}
-
 // K1 + the forward transpose of the distributed FFT.  On P > 1 GPUs the launch is split into `a2a_chunks` ranges
 // of row pairs; as soon as a range is done, its columns of the rows owned by the other ranks are copied into those
 // ranks' T buffers by the copy engines on a second stream (NJ/chunks*16-byte contiguous pieces over NVLink), while
@@ -816,24 +741,6 @@ int launch_k1(vmk_plan* p, const double* src) {
 // next launch transforms the following rows.
 int launch_k2(vmk_plan* p, double sign) {
   const int P = p->nranks, R = (p->N / 2) / P;
-  if (k2_split_on(p)) {
-    K2HArgs a;
-    a.T = p->T;
-    a.V = p->V;
-    a.tw = p->tw_h;
-    a.dif = p->dif_tw;
-    a.bbcos = p->bbcos;
-    a.cccos = p->cccos;
-    a.ccperm = p->ccperm_h;
-    a.aa = p->div_aa;
-    a.scale = sign / (2.0 * (double)p->N * (double)p->N);
-    a.nitems = p->N;
-    Timed t(p, KI_K2);
-    VMK_TRY(p->ops.k2h(a.nitems < p->res_k2h ? a.nitems : p->res_k2h, a, p->st));
-    p->launches++;
-    t.done();
-    return 0;
-  }
   const int push = p->k2_push >= 0 ? p->k2_push : 1;  // measured: direct NVLink stores beat staged engine copies
   int chunks = (P > 1 && !push) ? (p->a2a_chunks > 0 ? p->a2a_chunks : 4) : 1;
   while (chunks > 1 && (R % chunks || R / chunks < 1)) chunks--;
@@ -892,7 +799,6 @@ int launch_k3_rows(vmk_plan* p, const double2* V, double* out) {
   a.T = V;
   a.pieces = 0;
   a.prefetch = 0;
-  a.wj = nullptr;
   a.tw = p->tw;
   a.psi = out;
   a.lo_dst = out + (size_t)(p->NJ + 1) * p->N;
@@ -919,13 +825,9 @@ int launch_k3(vmk_plan* p) {
   a.hi_dst = p->peer_psi[next];
   a.NJ = p->NJ;
   a.npairs = p->NJ / 2;
-  a.wj = p->wj;
   const int work = rowpair_units(p, a.npairs, 1) * p->ops.cluster;
   Timed t(p, KI_K3);
-  if (k2_split_on(p))
-    VMK_TRY(p->ops.k3s(work < p->res_k3 ? work : p->res_k3, a, p->st));
-  else
-    VMK_TRY(p->ops.k3(work < p->res_k3 ? work : p->res_k3, a, p->st));
+  VMK_TRY(p->ops.k3(work < p->res_k3 ? work : p->res_k3, a, p->st));
   t.done();
   p->launches++;
   return 0;
@@ -1032,10 +934,6 @@ int ensure_divisor_cavity(vmk_plan* p, double dx, double dy) {
   VMK_TRY(be_h2d(p->bbcos, b.data(), sizeof(double) * N, p->st));
   VMK_TRY(be_h2d(p->cccos, c.data(), sizeof(double) * N, p->st));
   VMK_TRY(be_h2d(p->ccperm, cp.data(), sizeof(double) * N, p->st));
-  if (p->ccperm_h) {
-    p->ops.fill_ccperm_h(c.data(), cp.data());
-    VMK_TRY(be_h2d(p->ccperm_h, cp.data(), sizeof(double) * N, p->st));
-  }
   VMK_TRY(be_sync(p->st));
   p->div_aa = 0.0;
   p->div_dx = dx;
@@ -1423,7 +1321,6 @@ int ps32_stage(vmk_plan* p, int stage, double dt, double re) {
     k.T = p->qVF + (size_t)q * blk;
     k.pieces = 0;
     k.prefetch = 0;
-    k.wj = nullptr;
     k.tw = ch->tw;
     k.psi = out;
     k.lo_dst = out + (rows + 1) * L;  // the halo rows of the batch are written and never read
@@ -1613,25 +1510,6 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     std::vector<double2> tw(ops.twn ? ops.twn : 1);
     ops.fill_tw(tw.data());
     if ((rc = be_h2d(p->tw, tw.data(), sizeof(double2) * tw.size(), p->st))) break;
-    if (ops.k2h && nranks == 1) {  // K2 as half-size CTAs: its own twiddle tables and W_N^n (K1's / K3's butterfly)
-      if ((rc = ops.k2h_configure(&p->res_k2h))) break;
-      if ((rc = dev_alloc(p, (void**)&p->tw_h, sizeof(double2) * ops.twn_h))) break;
-      if ((rc = dev_alloc(p, (void**)&p->dif_tw, sizeof(double2) * ops.dif_n))) break;
-      if ((rc = dev_alloc(p, (void**)&p->wj, sizeof(double2) * (p->N / 2)))) break;
-      if ((rc = dev_alloc(p, (void**)&p->ccperm_h, sizeof(double) * p->N))) break;
-      std::vector<double2> th(ops.twn_h), wn(p->N / 2);
-      ops.fill_tw_h(th.data());
-      const long double tau = 6.283185307179586476925286766559005768L;
-      for (int n = 0; n < p->N / 2; n++) {
-        const long double ang = tau * (long double)n / (long double)p->N;
-        wn[n].x = (double)cosl(ang);
-        wn[n].y = (double)(-sinl(ang));
-      }
-      if ((rc = be_h2d(p->tw_h, th.data(), sizeof(double2) * th.size(), p->st))) break;
-      if ((rc = be_h2d(p->dif_tw, wn.data(), sizeof(double2) * ops.dif_n, p->st))) break;
-      if ((rc = be_h2d(p->wj, wn.data(), sizeof(double2) * wn.size(), p->st))) break;
-      if ((rc = be_sync(p->st))) break;  // (the host vectors go out of scope)
-    }
     if ((rc = be_sync(p->st))) break;
   } while (0);
   if (rc) {
@@ -1678,10 +1556,6 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_free(p->bbcos);
   be_free(p->cccos);
   be_free(p->ccperm);
-  be_free(p->tw_h);
-  be_free(p->dif_tw);
-  be_free(p->wj);
-  be_free(p->ccperm_h);
   be_free(p->staging);
   be_free(p->hW);
   be_free(p->hJ);
@@ -2199,11 +2073,11 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
               : k == "cl_prefetch" ? &p->cl_prefetch
               : k == "k4_ahead" ? &p->k4_ahead : k == "a2a_chunks" ? &p->a2a_chunks
               : k == "a2a_engine" ? &p->a2a_engine : k == "a2a_ctas" ? &p->a2a_ctas
-              : k == "k2_push" ? &p->k2_push : k == "k2_split" ? &p->k2_split : nullptr;
+              : k == "k2_push" ? &p->k2_push : nullptr;
   if (knob) {
     const int64_t hi = k == "a2a_ctas" ? 4096 : k == "a2a_chunks" ? 8 : 64;
     const int64_t lo = (k == "a2a_ctas" || k.find("group") != std::string::npos) ? 1
-                       : (k == "a2a_engine" || k == "k2_push" || k == "cl_prefetch" || k == "k2_split") ? -1 : 0;
+                       : (k == "a2a_engine" || k == "k2_push" || k == "cl_prefetch") ? -1 : 0;
     if (value < lo || value > hi) return fail(VMK_EARG, "option value out of range");
     *knob = (int)value;
     drop_graphs(p);

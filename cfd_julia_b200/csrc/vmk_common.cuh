@@ -185,28 +185,6 @@ VMK_HD void ld_stream4(const double2* p, double2& a, double2& b) {
   b = p[1];
 #endif
 }
-// Shared-memory accesses of the FFT exchanges as explicit instructions: volatile asm statements keep their order
-// relative to each other, so the SOURCE decides where the stores of one butterfly sit relative to the loads and stores
-// of the next (vmk_fft.cuh pipelines them against the FP64 work of the neighbouring butterfly; with plain C++ accesses
-// the compiler gathered all loads of a pass in front of and all stores behind its arithmetic).
-VMK_HD double2 lds2(const double2* p) {
-#ifdef __CUDA_ARCH__
-  double2 r;
-  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(a));
-  return r;
-#else
-  return *p;
-#endif
-}
-VMK_HD void sts2(double2* p, double2 v) {
-#ifdef __CUDA_ARCH__
-  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
-#else
-  *p = v;
-#endif
-}
 // Asynchronous 16-byte copy global -> shared (LDGSTS): no destination registers and no scoreboard wait, so a thread
 // can put the next row's loads in flight while its registers still hold the current row.  The data is visible to
 // the issuing thread after cp_async_wait_all(), to the rest of the CTA after a barrier on top of that.
@@ -214,15 +192,6 @@ VMK_HD void cp_async16(void* smem_dst, const void* gsrc) {
 #ifdef __CUDA_ARCH__
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-#else
-  memcpy(smem_dst, gsrc, 16);
-#endif
-}
-// the same through L1 (.ca): for lanes that fetch the two 16-byte halves of a 32-byte sector with two instructions
-VMK_HD void cp_async16_ca(void* smem_dst, const void* gsrc) {
-#ifdef __CUDA_ARCH__
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 #else
   memcpy(smem_dst, gsrc, 16);
 #endif

@@ -100,16 +100,9 @@ struct Net<1, SIGN, OFF> {
 // exchange instead of one) and the table of the first pass is stored as one octant.  Both shrink shared memory so that
 // a separate full-row LANDING buffer fits next to them: the next row's asynchronous copies are then issued a whole
 // row ahead instead of only during the last butterflies (used for N = 8192, where one row fills an SM).
-// PAIR_: pass 0 gives a thread ADJACENT positions (butterfly id = 2 t + u instead of t + T u).  The row-facing sides of
-// the kernels then work on 16-/32-byte units per thread without any lane exchange: K2 stores its (j, j+1) pieces
-// straight from registers (the lane-pair shuffle + selects it replaces were 13 % of K2's stall samples,
-// profiles/r02_notes.md), K3 stores and K1 reads two adjacent doubles per access.  Lanes then touch every second slot in
-// the pass-0 layout, which a swizzle (bit 0 ^= bit 3 of the position) keeps conflict-free for 128-bit accesses.
-template <int M_, int LE_, int P_, int B0_, int B1_, int B2_, int CT_, int MINB_, int B3_ = 0, bool SPLIT_ = false,
-          bool PAIR_ = false>
+template <int M_, int LE_, int P_, int B0_, int B1_, int B2_, int CT_, int MINB_, int B3_ = 0, bool SPLIT_ = false>
 struct FftCfg {
   static constexpr bool SPLIT = SPLIT_;
-  static constexpr bool PAIR0 = PAIR_ && !SPLIT_ && ((1 << LE_) >> B0_) == 2;
   static constexpr int M = M_, N = 1 << M_, LE = LE_, E = 1 << LE_, T = N >> LE_, P = P_;
   static constexpr int CT = CT_ > T ? CT_ : T;  // CTA threads
   static constexpr int FPC = CT / T;            // transforms per CTA
@@ -122,7 +115,6 @@ struct FftCfg {
   }
   VMK_HD static constexpr int lo(int k) { return hi(k) - bits(k); }
   static constexpr int PADSH = bits(P_ - 1);
-  static constexpr bool SWZ0 = PAIR0 && PADSH >= 4;  // (a 16-slot quarter-warp span must not cross a padding step)
   static constexpr int SMN = N + (N >> PADSH);  // padded complex slots per transform
   // twiddle tables: pass k < P-1 uses W_{Bk}^x, Bk = 2^hi(k); full wave if small, else half wave
   VMK_HD static constexpr bool tw_full(int k) { return (1 << hi(k)) <= 1024; }
@@ -172,47 +164,13 @@ template <> struct CfgFor<13> { using type = FftCfg<13, 5, 3, 4, 4, 5, 256, 1, 0
 #else
 template <> struct CfgFor<13> { using type = FftCfg<13, 5, 3, 4, 4, 5, 256, 1>; };
 #endif
-// the configuration of the main-path kernels K1/K2/K3 (pairs where the size allows it); the cluster kernels and the
-// spectral-space solvers' own kernels keep CfgFor
-template <int M>
-struct CfgMain { using type = typename CfgFor<M>::type; };
-#if !defined(VMK_M13_T512) && !defined(VMK_M13_SPLIT) && !defined(VMK_NO_PAIR0)
-template <> struct CfgMain<13> { using type = FftCfg<13, 5, 3, 4, 4, 5, 256, 1, 0, false, true>; };
-#ifndef VMK_SPLIT_TEST
-template <> struct CfgMain<9>  { using type = FftCfg<9, 4, 3, 3, 3, 3, 128, 4, 0, false, true>; };
-template <> struct CfgMain<10> { using type = FftCfg<10, 4, 3, 3, 3, 4, 128, 4, 0, false, true>; };
-template <> struct CfgMain<11> { using type = FftCfg<11, 4, 3, 3, 4, 4, 128, 3, 0, false, true>; };
-#endif
-#endif
-
-
-// the N/2-point configuration of K2's half-size CTAs (k2h_body): 32 values per thread, two CTAs of 128 threads per SM
-template <int M>
-struct HalfCfg { static constexpr bool available = false; };
-#if !defined(VMK_M13_T512) && !defined(VMK_M13_SPLIT)
-template <> struct HalfCfg<13> {
-  static constexpr bool available = true;
-  using type = FftCfg<12, 5, 3, 4, 4, 4, 128, 2>;
-};
-#ifdef VMK_HALF_TEST  // test builds only (tests/emul): the same path at sizes the CPU suite can afford
-template <> struct HalfCfg<10> {
-  static constexpr bool available = true;
-  using type = FftCfg<9, 5, 2, 4, 5, 0, 16, 2>;
-};
-#endif
-#endif
 
 // ---- the engine --------------------------------------------------------------------------------
 template <class C>
 struct Fft {
   static constexpr int E = C::E, T = C::T, P = C::P, M = C::M, N = C::N;
 
-  VMK_HD static int addr(int pos) {
-    if constexpr (C::SWZ0)
-      return (pos ^ ((pos >> 3) & 1)) + (pos >> C::PADSH);
-    else
-      return pos + (pos >> C::PADSH);
-  }
+  VMK_HD static int addr(int pos) { return pos + (pos >> C::PADSH); }
 
   // shared-memory carving: [transform g: exchange buffer | landing buffer] ... [twiddle tables]
   VMK_HD static double2* xbuf(unsigned char* smem, int g) {
@@ -229,7 +187,7 @@ struct Fft {
   template <int K>
   VMK_HD static int base_pos(int t, int u, int& low) {
     constexpr int l = C::lo(K), h = C::hi(K);
-    const int id = (K == 0 && C::PAIR0) ? 2 * t + u : t + T * u;
+    const int id = t + T * u;
     low = id & ((1 << l) - 1);
     return ((id >> l) << h) | low;
   }
@@ -258,28 +216,6 @@ struct Fft {
         constexpr int q = decltype(q_)::value;
         sm[addr(bp | (q << l))] = v[u * r + q];
       });
-    });
-  }
-
-  // butterfly U of pass K alone (explicit instructions, see lds2 / sts2): the unit of the software pipeline below
-  template <int K, int U>
-  VMK_HD static void load_bfly(double2 (&v)[E], const double2* sm, int t) {
-    constexpr int b = C::bits(K), r = 1 << b, l = C::lo(K);
-    int low;
-    const int bp = base_pos<K>(t, U, low);
-    static_for<0, r>([&](auto q_) {
-      constexpr int q = decltype(q_)::value;
-      v[U * r + q] = lds2(sm + addr(bp | (q << l)));
-    });
-  }
-  template <int K, int U>
-  VMK_HD static void store_bfly(const double2 (&v)[E], double2* sm, int t) {
-    constexpr int b = C::bits(K), r = 1 << b, l = C::lo(K);
-    int low;
-    const int bp = base_pos<K>(t, U, low);
-    static_for<0, r>([&](auto q_) {
-      constexpr int q = decltype(q_)::value;
-      sts2(sm + addr(bp | (q << l)), v[U * r + q]);
     });
   }
 
@@ -365,13 +301,9 @@ struct Fft {
   // forward pass K on registers: radix network, then twiddle.  v[u*r+p] <- y[p].
   template <int K>
   VMK_HD static void fwd_compute(double2 (&v)[E], const double2* tw, int t) {
-    constexpr int r = 1 << C::bits(K);
-    static_for<0, E / r>([&](auto u_) { fwd_bfly<K, decltype(u_)::value>(v, tw, t); });
-  }
-  template <int K, int u>
-  VMK_HD static void fwd_bfly(double2 (&v)[E], const double2* tw, int t) {
     constexpr int b = C::bits(K), r = 1 << b;
-    {
+    static_for<0, E / r>([&](auto u_) {
+      constexpr int u = decltype(u_)::value;
       double2 a[r];
       static_for<0, r>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
@@ -400,18 +332,14 @@ struct Fft {
           });
         });
       }
-    }
+    });
   }
   // inverse pass K: conjugate twiddle, then conjugate network.  v[u*r+q] <- x[q].
   template <int K>
   VMK_HD static void inv_compute(double2 (&v)[E], const double2* tw, int t) {
-    constexpr int r = 1 << C::bits(K);
-    static_for<0, E / r>([&](auto u_) { inv_bfly<K, decltype(u_)::value>(v, tw, t); });
-  }
-  template <int K, int u>
-  VMK_HD static void inv_bfly(double2 (&v)[E], const double2* tw, int t) {
     constexpr int b = C::bits(K), r = 1 << b;
-    {
+    static_for<0, E / r>([&](auto u_) {
+      constexpr int u = decltype(u_)::value;
       double2 a[r];
       int low;
       (void)base_pos<K>(t, u, low);
@@ -438,36 +366,15 @@ struct Fft {
         constexpr int q = decltype(q_)::value;
         v[u * r + q] = a[brev(q, b)];
       });
-    }
+    });
   }
 
   // registers hold pass-0 layout (natural positions) on entry, last-pass layout on exit
-  //
-  // Software pipeline (non-split configurations): a pass is  [loads of all butterflies] [butterfly 0] [stores 0]
-  // [butterfly 1] [stores 1] ... barrier.  A thread reads and writes only its own slots on either side of a barrier,
-  // so the stores of butterfly u may leave as soon as it is done: they and the later butterflies' loads travel
-  // through the shared-memory pipe while the FP64 pipe works on the neighbouring butterfly.  With all stores behind
-  // all arithmetic (the literal compute -> exchange form) the two pipes alternated: 3.5 K cycles per 8192-point pass
-  // against 2.8 K in this order (tools/ubench/overlap.cu, variants 2 and 10).
   VMK_HD static void forward(const Ctx& c, double2 (&v)[E], double2* sm, const double2* tw, int t) {
     static_for<0, P>([&](auto k_) {
       constexpr int K = decltype(k_)::value;
-      if constexpr (C::SPLIT) {
-        fwd_compute<K>(v, tw, t);
-        if constexpr (K < P - 1) exchange<K, K + 1>(c, v, sm, t);
-      } else {
-        constexpr int r = 1 << C::bits(K);
-        static_for<0, E / r>([&](auto u_) {
-          constexpr int U = decltype(u_)::value;
-          fwd_bfly<K, U>(v, tw, t);
-          if constexpr (K < P - 1) store_bfly<K, U>(v, sm, t);
-        });
-        if constexpr (K < P - 1) {
-          c.sync();
-          constexpr int rn = 1 << C::bits(K + 1);
-          static_for<0, E / rn>([&](auto u_) { load_bfly<K + 1, decltype(u_)::value>(v, sm, t); });
-        }
-      }
+      fwd_compute<K>(v, tw, t);
+      if constexpr (K < P - 1) exchange<K, K + 1>(c, v, sm, t);
     });
   }
   // registers hold last-pass layout on entry, pass-0 layout (natural positions) on exit
@@ -478,25 +385,10 @@ struct Fft {
                              Hook&& after_last_exchange) {
     static_for<0, P>([&](auto k_) {
       constexpr int K = P - 1 - decltype(k_)::value;
-      if constexpr (C::SPLIT) {
-        inv_compute<K>(v, tw, t);
-        if constexpr (K > 0) {
-          exchange<K, K - 1>(c, v, sm, t);
-          if constexpr (K == 1) after_last_exchange();
-        }
-      } else {
-        constexpr int r = 1 << C::bits(K);
-        static_for<0, E / r>([&](auto u_) {
-          constexpr int U = decltype(u_)::value;
-          inv_bfly<K, U>(v, tw, t);
-          if constexpr (K > 0) store_bfly<K, U>(v, sm, t);
-        });
-        if constexpr (K > 0) {
-          c.sync();
-          constexpr int rn = 1 << C::bits(K - 1);
-          static_for<0, E / rn>([&](auto u_) { load_bfly<K - 1, decltype(u_)::value>(v, sm, t); });
-          if constexpr (K == 1) after_last_exchange();
-        }
+      inv_compute<K>(v, tw, t);
+      if constexpr (K > 0) {
+        exchange<K, K - 1>(c, v, sm, t);
+        if constexpr (K == 1) after_last_exchange();
       }
     });
   }

@@ -106,23 +106,11 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
     {
       const double* r0 = rows;
       const double* r1 = r0 + N;
-      if constexpr (C::PAIR0) {
-        // the thread's positions come in adjacent pairs (registers q and E/2 + q): one 16-byte read per row and pair
-        static_for<0, E / 2>([&](auto q_) {
-          constexpr int q = decltype(q_)::value;
-          const int pos = F::template own_pos<q>(t);
-          const double2 x = lds2(reinterpret_cast<const double2*>(r0 + pos));
-          const double2 y = lds2(reinterpret_cast<const double2*>(r1 + pos));
-          v[q] = active ? mk2(x.x, y.x) : mk2(0.0, 0.0);
-          v[E / 2 + q] = active ? mk2(x.y, y.y) : mk2(0.0, 0.0);
-        });
-      } else {
-        static_for<0, E>([&](auto e_) {
-          constexpr int e = decltype(e_)::value;
-          const int pos = F::template own_pos<e>(t);
-          v[e] = active ? mk2(r0[pos], r1[pos]) : mk2(0.0, 0.0);
-        });
-      }
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        const int pos = F::template own_pos<e>(t);
+        v[e] = active ? mk2(r0[pos], r1[pos]) : mk2(0.0, 0.0);
+      });
     }
     c.sync();  // all rows are in registers
     // SPLIT: the landing buffer is a buffer of its own, so the next pair's rows start streaming in right away;
@@ -235,25 +223,12 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
     if (rb < nblocks && row < a.nrows) {
       // PIECES (single GPU): work item `row` is the piece index; its spectrum row is kx = k(idx = row)
       const int trow = PIECES ? F::k_of_pos(halfspec_pos<C>(row)) : a.rloc0 + row;
-      if constexpr (PIECES) {
-        // one GPU: the spectrum row is one contiguous run of N elements (no per-element segment arithmetic)
-        const double2* src = a.T + (size_t)trow * N;
-        static_for<0, E>([&](auto e_) {
-          constexpr int e = decltype(e_)::value;
-          const int j = F::template own_pos<e>(t);
-          if constexpr (C::PAIR0)
-            cp_async16_ca(land + F::land_addr(j), src + j);
-          else
-            cp_async16(land + F::land_addr(j), src + j);
-        });
-      } else {
-        static_for<0, E>([&](auto e_) {
-          constexpr int e = decltype(e_)::value;
-          const int j = F::template own_pos<e>(t);
-          cp_async16(land + F::land_addr(j),
-                     a.T + ((size_t)(j >> a.log2NJ) * a.R + trow) * a.NJ + (j & (a.NJ - 1)));
-        });
-      }
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        const int j = F::template own_pos<e>(t);
+        cp_async16(land + F::land_addr(j),
+                   a.T + ((size_t)(j >> a.log2NJ) * a.R + trow) * a.NJ + (j & (a.NJ - 1)));
+      });
     }
     cp_async_commit();
   };
@@ -364,17 +339,7 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
     F::inverse(c, v, sm, tw, t, [&] {
       if constexpr (!C::SPLIT) issue_row(rb + c.nblk);
     });
-    if constexpr (PIECES && C::PAIR0) {
-      // the thread holds columns j (register q) and j + 1 (register E/2 + q): the 32-byte pieces leave as they are
-      if (active) {
-        double2* dst = a.V + (size_t)row * 2;
-        static_for<0, E / 2>([&](auto q_) {
-          constexpr int q = decltype(q_)::value;
-          const int j = F::template own_pos<q>(t);
-          st_stream4(dst + (size_t)(j >> 1) * N, v[q], v[E / 2 + q]);
-        });
-      }
-    } else if constexpr (PIECES) {
+    if constexpr (PIECES) {
       // lanes 2m, 2m+1 hold columns j, j+1 of every register: one shuffle per register pair gives each lane both
       // halves of one 32-byte piece (even lane: register e, odd lane: register e+1)
       const bool odd = (t & 1) != 0;
@@ -404,137 +369,6 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
   cp_async_wait_all();
 }
 
-// ======================================== K2H ===================================================
-// K2 for one GPU and N = 8192 as TWO independent CTAs per SM (profiles/r02_notes.md).  An 8192-point row fills the
-// register file of an SM, so k2_body runs one CTA per SM and all eight warps of it are in the same phase after every
-// barrier: the FP64 pipe idles while the shared-memory pipe moves an exchange and vice versa (time = sum of the two).
-// Two independent CTAs drift out of phase and fill each other's gaps (tools/ubench/overlap.cu: 3.5 K -> 2.3 K cycles
-// per pass).  What makes half-size CTAs possible is the first radix-2 decimation of the transform along j:
-//     X[2k'+g] = FFT_{N/2}{ (x[n] + (-1)^g x[n + N/2]) W_N^{g n} }[k'],   g = 0, 1
-// -- the two parity classes g of the spectrum are independent N/2-point problems.  Work item (kx, g) reads the whole
-// row (the sibling item re-reads it: an L2 hit), forms its class's input on the fly, transforms, divides by the
-// divisor at ky = 2k'+g, transforms back and stores   e[n] (g = 0)  or  o[n] (g = 1),  n < N/2, where the solution
-// row is  u[n] = e[n] + W_N^{-n} o[n],  u[n + N/2] = e[n] - W_N^{-n} o[n]:  that last butterfly is done by K3's load
-// stage (k3_body<.., SPLITJ>), which therefore pairs the rows (n, n + N/2) instead of (n, n + 1).
-// Loads: the first half of the next row lands asynchronously in the thread's own pass-0 slots (as in k2_body), the
-// second half -- there is no room for it -- is pulled into L2 by one bulk prefetch a whole item ahead and read with
-// all 32 loads of the thread in flight at once when the item starts.
-// (Having K1 emit the decimated half-rows instead needs 16-byte scattered stores there: measured, 3x slower K1 and
-// +50 % DRAM traffic from partially written sectors.)
-struct K2HArgs {
-  const double2* T;      // spectrum rows [N/2][N] (K1's output, one GPU)
-  double2* V;            // [n < N/2][idx < N/2][2]: (e, o) pieces in K3's consumption order (K2Args::pieces)
-  const double2* tw;     // twiddle tables of the N/2-point configuration
-  const double2* dif;    // [2 T] W_N^{id}, id < 2 T: twiddles of the decimation (the rest by compile-time W_32^q)
-  const double* bbcos;   // [N]
-  const double* cccos;   // [N]
-  const double* ccperm;  // [2][N/2]: cccos[2 k' + g] in the register order of the N/2-point configuration
-  double aa, scale;
-  int nitems;            // N: (N/2 spectrum rows) x (2 parity classes)
-};
-
-template <class CH, class CF>  // CH: the N/2-point configuration (E = 32, T = 128), CF: the N-point one (K3's order)
-VMK_HD void k2h_body(const Ctx& c, const K2HArgs& a) {
-  using F = Fft<CH>;
-  constexpr int NH = CH::N, N = 2 * NH, E = CH::E, T = CH::T, P = CH::P;
-  constexpr int bl = CH::bits(P - 1), rl = 1 << bl, r0 = 1 << CH::bits(0);
-  static_assert(CH::FPC == 1 && !CH::SPLIT && !CH::PAIR0 && CF::N == N, "configuration");
-  static_assert(N / (NH / r0) == 32, "decimation twiddles: W_N^(id + (NH/r0) q) = dif[id] W_32^q");
-  double2* tw = F::tables(c.smem);
-  F::load_tables(c, tw, a.tw);
-  c.sync();
-  const int t = c.tid;
-  double2* sm = F::xbuf(c.smem, 0);
-  double2 wd[E / r0];  // W_N^id of the thread's pass-0 butterflies
-  static_for<0, E / r0>([&](auto u_) {
-    constexpr int u = decltype(u_)::value;
-    wd[u] = ld_ro2(a.dif + t + T * u);
-  });
-  auto row_of = [&](int item) { return a.T + (size_t)Fft<CF>::k_of_pos(halfspec_pos<CF>(item >> 1)) * N; };
-  // first half of the item's row -> own pass-0 slots (asynchronous); second half -> L2
-  auto issue_row = [&](int item) {
-    if (item < a.nitems) {
-      const double2* src = row_of(item);
-      static_for<0, E>([&](auto e_) {
-        constexpr int e = decltype(e_)::value;
-        const int n = F::template own_pos<e>(t);
-        cp_async16(sm + F::addr(n), src + n);
-      });
-      if (t == 0) prefetch_l2_bulk(src + NH, (unsigned)(NH * sizeof(double2)));
-    }
-    cp_async_commit();
-  };
-  issue_row(c.bid);
-  for (int item = c.bid; item < a.nitems; item += c.nblk) {
-    const int idx = item >> 1, g = item & 1;
-    const int kx = Fft<CF>::k_of_pos(halfspec_pos<CF>(idx));
-    const double2* src = a.T + (size_t)kx * N;
-    double2 v[E];
-    static_for<0, E>([&](auto e_) {
-      constexpr int e = decltype(e_)::value;
-      v[e] = ld_stream2(src + NH + F::template own_pos<e>(t));  // x[n + N/2]: 32 loads in flight
-    });
-    cp_async_wait_all();
-    // ---- decimation: (x0 + x1) or (x0 - x1) W_N^n,  n = id + (NH/r0) q -> W_N^id (table) times W_32^q (constant)
-    static_for<0, E>([&](auto e_) {
-      constexpr int e = decltype(e_)::value;
-      const double2 x0 = lds2(sm + F::addr(F::template own_pos<e>(t)));
-      if (g == 0)
-        v[e] = cadd(x0, v[e]);
-      else
-        v[e] = mul_const<32, e % r0, -1>(cmul(csub(x0, v[e]), wd[e / r0]));
-    });
-    F::forward(c, v, sm, tw, t);
-    // ---- divide (registers hold the last-pass layout: butterfly id = t + T*u, digit p; ky = 2 k' + g) ------------
-    if (kx == 0) {
-      // packed DC/Nyquist row (see k2_body): the mirror N - ky of ky = 2k'+g is 2k''+g with
-      // k'' = (NH - k') mod NH (g = 0) or NH - 1 - k' (g = 1): inside this item's class
-      double2 cm[E];
-      F::template store_smem<P - 1>(v, sm, t);
-      c.sync();
-      static_for<0, E>([&](auto e_) {
-        constexpr int e = decltype(e_)::value, u = e / rl, p = e % rl;
-        const int kp = F::k_of_pos(((t + T * u) << bl) | p);
-        const int km = g == 0 ? ((NH - kp) & (NH - 1)) : NH - 1 - kp;
-        cm[e] = sm[F::addr(F::pos_of_k(km))];
-      });
-      const double ab0 = a.aa + ld_ro(a.bbcos + 0), abn = a.aa + ld_ro(a.bbcos + N / 2);
-      static_for<0, E>([&](auto e_) {
-        constexpr int e = decltype(e_)::value, u = e / rl, p = e % rl;
-        const int ky = 2 * F::k_of_pos(((t + T * u) << bl) | p) + g;
-        const double2 cmv = cm[e], ck = v[e];
-        const double cc = ld_ro(a.cccos + ky);
-        const double g0 = 0.5 * a.scale * rcp_rn(ab0 + cc), gn = 0.5 * a.scale * rcp_rn(abn + cc);
-        double2 pp = cscale(mk2(ck.x + cmv.x, ck.y - cmv.y), g0);        // A^' = (C + conj Cm)/2 * g
-        const double2 qq = cscale(mk2(ck.y + cmv.y, cmv.x - ck.x), gn);  // B^' = -i(C - conj Cm)/2 * g
-        if (ky == 0) pp = mk2(0.0, 0.0);                                  // e[1,1] = 0, Common.jl:118
-        v[e] = mk2(pp.x - qq.y, pp.y + qq.x);                             // A^' + i B^'
-      });
-      c.sync();
-    } else {
-      const double ab = a.aa + ld_ro(a.bbcos + kx);
-      const double* cp = a.ccperm + (size_t)g * NH;
-      double dd[E];
-      static_for<0, E>([&](auto e_) {
-        constexpr int e = decltype(e_)::value;
-        dd[e] = ab + ld_ro(cp + e * T + t);  // (aa + bb cos kx) + cc cos ky
-      });
-      static_for<0, E>([&](auto e_) {
-        constexpr int e = decltype(e_)::value;
-        v[e] = cscale(v[e], a.scale * rcp_fast(dd[e]));
-      });
-    }
-    F::inverse(c, v, sm, tw, t, [&] { issue_row(item + c.nblk); });
-    double2* dst = a.V + (size_t)idx * 2 + g;
-    static_for<0, E>([&](auto e_) {
-      constexpr int e = decltype(e_)::value;
-      const int n = F::template own_pos<e>(t);
-      st_stream2(dst + (size_t)n * N, v[e]);
-    });
-  }
-  cp_async_wait_all();
-}
-
 // ======================================== K3 ====================================================
 struct K3Args {
   const double2* T;   // local solution buffer V after K2: U[kx][jl]
@@ -545,12 +379,9 @@ struct K3Args {
   int NJ, npairs;
   int pieces;         // 1: T is laid out [pair][idx][2] (see K2Args::pieces): contiguous, coalesced reads
   int prefetch;       // cluster kernels: bulk L2 prefetch of the next pair's pieces
-  const double2* wj;  // SPLITJ: [N/2] W_N^n
 };
 
-// SPLITJ (with PIECES, one GPU): the pieces are K2H's (e[n], o[n]) and work item n yields the rows n and n + N/2:
-// U_n = e + W_N^{-n} o, U_{n+N/2} = e - W_N^{-n} o (the last butterfly of the transform along j, see k2h_body).
-template <class C, bool PIECES, bool SPLITJ = false>
+template <class C, bool PIECES>
 VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
   using F = Fft<C>;
   constexpr int N = C::N, E = C::E, T = C::T, P = C::P, NI = N / 2 / T;
@@ -584,10 +415,7 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
   for (int pb = c.bid; pb < nblocks; pb += c.nblk) {
     const int pair = pb * C::FPC + g;
     const bool active = pair < a.npairs;
-    const int jl = SPLITJ ? pair : 2 * pair;           // first row of the item
-    const int jl2 = SPLITJ ? pair + a.NJ / 2 : jl + 1;  // second row
-    double2 wjn = mk2(1.0, 0.0);
-    if constexpr (SPLITJ) wjn = ld_ro2(a.wj + (active ? pair : 0));
+    const int jl = 2 * pair;
     double2 v[E];
     if constexpr (C::SPLIT) {
       double2 ua[NI], ub[NI];
@@ -653,14 +481,6 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
                                         : a.T + (size_t)F::k_of_pos(halfspec_pos<C>(idx)) * a.NJ + jl;
             ld_stream4(src, ua[i - b * NH], ub[i - b * NH]);
           });
-          if constexpr (SPLITJ) {
-            static_for<0, NH>([&](auto i_) {
-              constexpr int ii = decltype(i_)::value;
-              const double2 e = ua[ii], wo = cmulc(ub[ii], wjn);  // o W_N^{-n}
-              ua[ii] = cadd(e, wo);
-              ub[ii] = csub(e, wo);
-            });
-          }
         }
         if constexpr (b == 0) c.sync();  // the previous pair's last exchange has been read everywhere
         // Z = U_j + i U_j+1 in position order (Z[N-k] from the conjugates), straight into the last-pass layout
@@ -685,29 +505,16 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
     F::inverse(c, v, sm, tw, t);
     if (active) {
       double* r0 = a.psi + (size_t)(jl + 1) * N;
-      double* r1 = a.psi + (size_t)(jl2 + 1) * N;
-      const bool first = (jl == 0), last = (jl2 + 1 == a.NJ);
-      if constexpr (C::PAIR0) {
-        // adjacent positions in registers q and E/2 + q: 16-byte stores
-        static_for<0, E / 2>([&](auto q_) {
-          constexpr int q = decltype(q_)::value;
-          const int pos = F::template own_pos<q>(t);
-          const double2 x = mk2(v[q].x, v[E / 2 + q].x), y = mk2(v[q].y, v[E / 2 + q].y);
-          st_stream2(reinterpret_cast<double2*>(r0 + pos), x);
-          st_stream2(reinterpret_cast<double2*>(r1 + pos), y);
-          if (first) st_stream2(reinterpret_cast<double2*>(a.lo_dst + pos), x);
-          if (last) st_stream2(reinterpret_cast<double2*>(a.hi_dst + pos), y);
-        });
-      } else {
-        static_for<0, E>([&](auto e_) {
-          constexpr int e = decltype(e_)::value;
-          const int pos = F::template own_pos<e>(t);
-          st_stream1(r0 + pos, v[e].x);
-          st_stream1(r1 + pos, v[e].y);
-          if (first) st_stream1(a.lo_dst + pos, v[e].x);
-          if (last) st_stream1(a.hi_dst + pos, v[e].y);
-        });
-      }
+      double* r1 = r0 + N;
+      const bool first = (jl == 0), last = (jl + 2 == a.NJ);
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        const int pos = F::template own_pos<e>(t);
+        st_stream1(r0 + pos, v[e].x);
+        st_stream1(r1 + pos, v[e].y);
+        if (first) st_stream1(a.lo_dst + pos, v[e].x);
+        if (last) st_stream1(a.hi_dst + pos, v[e].y);
+      });
     }
   }
   cp_async_wait_all();

@@ -376,23 +376,3 @@ def _slab_run(emul, oracle_c, n, nranks):
 def test_ref_py_fixtures(emul, tag):
     """vectors computed by the reference's own Python twins of script 19 (tests/golden/make_ref_fixtures.py)"""
     pc.check_ref_py_lib(emul, tag)
-
-
-@pytest.fixture(scope="module")
-def emul_half(emul):
-    """K2 as two independent half-size CTAs per SM (k2h_body) + K3's SPLITJ load stage: production uses them at 8192^2 on
-    one GPU; this build enables the same path at 1024^2."""
-    from cfd_julia_b200._lib import VmkLibrary
-    from cfd_julia_b200.common import Common
-    return Common(VmkLibrary(os.path.join(ROOT, "tests", "emul", "libvmk_emul_half.so"), "vmke_"))
-
-
-def test_half_cta_path(emul_half, oracle_c):
-    n = 1024
-    pc.check_fps_noise(emul_half, oracle_c, n)
-    pc.check_rhs(emul_half, oracle_c, noise_field(n, seed=5))
-    pc.check_numerical(emul_half, oracle_c, vm_field(n), 2, stable_dt(n, 1000.), 1000.)
-    # the option switches back to the one-CTA-per-row K2 (same results to rounding)
-    emul_half.plan(n, n).set_option("k2_split", 0)
-    pc.check_fps_noise(emul_half, oracle_c, n)
-    emul_half.clear_plans()
