@@ -497,10 +497,11 @@ struct vmk_plan {
   Stream st, st_copy, st_copy2;
   Event ev0, ev1, ev_join, ev_join2, ev_chunk[8];
   int a2a_chunks = 0 /* auto */, a2a_engine = -1 /* auto */, a2a_ctas = 128, k2_push = -1 /* auto */;
+  int a2a_order = 1, k2_chunks = 0 /* auto */;
   bool ev_valid = false;
   bool uploaded = false;
   int64_t launches = 0, graph_launches = 12;
-  int k4_rows = 32, k4_ahead = 4;
+  int k4_rows = 32, k4_ahead = 4, k4_waves = 3;  // k4_waves: measured on 8 GPUs (profiles/r02_notes.md)
   int k1_prefetch = 0, k2_prefetch = 0, v_pieces = 1, cl_prefetch = -1 /* auto */;
   int use_graph = 1;
 #ifndef VMK_EMUL
@@ -664,6 +665,14 @@ int rowpair_units(const vmk_plan* p, int npairs, int g) {
   return (nblocks + g - 1) / g;
 }
 
+int launch_k6(vmk_plan* p, const K6Args& k) {
+  const int items = (k.nranks - 1) * ((k.rows + kK6Rows - 1) / kK6Rows) * ((k.ncols + kK6Threads - 1) / kK6Threads);
+  const int grid = items < p->a2a_ctas ? items : p->a2a_ctas;
+  VMK_TRY((be_launch<K6Push, K6Args, kK6Threads, 2>(grid < 1 ? 1 : grid, 0, k, p->st_copy)));
+  p->launches++;
+  return 0;
+}
+
 // K1 + the forward transpose of the distributed FFT.  On P > 1 GPUs the launch is split into `a2a_chunks` ranges
 // of row pairs; as soon as a range is done, its columns of the rows owned by the other ranks are copied into those
 // ranks' T buffers by the copy engines on a second stream (NJ/chunks*16-byte contiguous pieces over NVLink), while
@@ -709,20 +718,18 @@ int launch_k1(vmk_plan* p, const double* src) {
         }
       } else {  // SM push kernel
         K6Args k;
-        k.S = p->S;
-        for (int r = 0; r < kMaxPeers; r++) k.T.p[r] = r < P ? (void*)p->peer_T[r] : nullptr;
-        k.N = N;
-        k.NJ = p->NJ;
-        k.R = R;
-        k.j0 = p->j0;
-        k.col0 = 2 * pair0;
+        k.src = p->S;
+        for (int r = 0; r < kMaxPeers; r++) k.dst.p[r] = r < P ? (void*)p->peer_T[r] : nullptr;
+        k.src_hstride = (long long)R * p->NJ;
+        k.src_off = 2 * pair0;
+        k.dst_off = (long long)p->rank * R * p->NJ + 2 * pair0;
+        k.pitch = p->NJ;
+        k.rows = R;
         k.ncols = 2 * np;
         k.rank = p->rank;
         k.nranks = P;
-        const int items = (P - 1) * R;
-        const int grid = items < p->a2a_ctas ? items : p->a2a_ctas;
-        VMK_TRY((be_launch<K6Push, K6Args, kK6Threads, 4>(grid, 0, k, p->st_copy)));
-        p->launches++;
+        k.order = p->a2a_order;
+        VMK_TRY(launch_k6(p, k));
       }
     }
   }
@@ -741,8 +748,12 @@ int launch_k1(vmk_plan* p, const double* src) {
 // next launch transforms the following rows.
 int launch_k2(vmk_plan* p, double sign) {
   const int P = p->nranks, R = (p->N / 2) / P;
-  const int push = p->k2_push >= 0 ? p->k2_push : 1;  // measured: direct NVLink stores beat staged engine copies
-  int chunks = (P > 1 && !push) ? (p->a2a_chunks > 0 ? p->a2a_chunks : 4) : 1;
+  // k2_push 1: K2 stores foreign columns straight into the peers' V (its warps stall on the NVLink store queue);
+  // 0: staged in S and moved by the copy engines; 2: staged in S and moved by the SM push kernel on a second stream
+  // while K2 transforms the next row chunk
+  const int mode = p->k2_push >= 0 ? p->k2_push : 1;
+  const int push = mode == 1;
+  int chunks = (P > 1 && !push) ? (p->k2_chunks > 0 ? p->k2_chunks : 4) : 1;
   while (chunks > 1 && (R % chunks || R / chunks < 1)) chunks--;
   Timed t(p, KI_K2);
   for (int c = 0; c < chunks; c++) {
@@ -775,11 +786,27 @@ int launch_k2(vmk_plan* p, double sign) {
       VMK_TRY(be_event_record(p->ev_chunk[c], p->st));
       VMK_TRY(be_stream_wait(p->st_copy, p->ev_chunk[c]));
       VMK_TRY(be_stream_wait(p->st_copy2, p->ev_chunk[c]));
-      const size_t bytes = sizeof(double2) * (size_t)nr * p->NJ;
-      for (int q = 0; q + 1 < P; q++) {
-        const int h = (p->rank + 1 + q) % P;
-        VMK_TRY(be_d2d(p->peer_V[h] + (size_t)(p->rank * R + rloc0) * p->NJ, p->S + ((size_t)h * R + rloc0) * p->NJ, bytes,
-                       (q & 1) ? p->st_copy2 : p->st_copy));
+      if (mode == 2) {
+        K6Args k;
+        k.src = p->S;
+        for (int r = 0; r < kMaxPeers; r++) k.dst.p[r] = r < P ? (void*)p->peer_V[r] : nullptr;
+        k.src_hstride = (long long)R * p->NJ;
+        k.src_off = (long long)rloc0 * p->NJ;
+        k.dst_off = (long long)(p->rank * R + rloc0) * p->NJ;
+        k.pitch = p->NJ;
+        k.rows = nr;
+        k.ncols = p->NJ;
+        k.rank = p->rank;
+        k.nranks = P;
+        k.order = p->a2a_order;
+        VMK_TRY(launch_k6(p, k));
+      } else {
+        const size_t bytes = sizeof(double2) * (size_t)nr * p->NJ;
+        for (int q = 0; q + 1 < P; q++) {
+          const int h = (p->rank + 1 + q) % P;
+          VMK_TRY(be_d2d(p->peer_V[h] + (size_t)(p->rank * R + rloc0) * p->NJ, p->S + ((size_t)h * R + rloc0) * p->NJ,
+                         bytes, (q & 1) ? p->st_copy2 : p->st_copy));
+        }
       }
     }
   }
@@ -857,7 +884,7 @@ int launch_k4(vmk_plan* p, int mode, int win, int wn, int out, const StepParams&
   const int ctas_x = cols / tw;
   // small slabs: shorter row marches so that the grid is several waves of resident CTAs (3 per SM)
   while (a.rows_per_cta > 4 &&
-         ctas_x * ((p->NJ + groups * a.rows_per_cta - 1) / (groups * a.rows_per_cta)) < 6 * 3 * p->sms)
+         ctas_x * ((p->NJ + groups * a.rows_per_cta - 1) / (groups * a.rows_per_cta)) < p->k4_waves * 3 * p->sms)
     a.rows_per_cta /= 2;
   const int rows_per = groups * a.rows_per_cta;
   const int grid = ctas_x * ((p->NJ + rows_per - 1) / rows_per);
@@ -2073,9 +2100,10 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
               : k == "cl_prefetch" ? &p->cl_prefetch
               : k == "k4_ahead" ? &p->k4_ahead : k == "a2a_chunks" ? &p->a2a_chunks
               : k == "a2a_engine" ? &p->a2a_engine : k == "a2a_ctas" ? &p->a2a_ctas
-              : k == "k2_push" ? &p->k2_push : nullptr;
+              : k == "k2_push" ? &p->k2_push : k == "a2a_order" ? &p->a2a_order
+              : k == "k2_chunks" ? &p->k2_chunks : k == "k4_waves" ? &p->k4_waves : nullptr;
   if (knob) {
-    const int64_t hi = k == "a2a_ctas" ? 4096 : k == "a2a_chunks" ? 8 : 64;
+    const int64_t hi = k == "a2a_ctas" ? 4096 : (k == "a2a_chunks" || k == "k2_chunks") ? 8 : 64;
     const int64_t lo = (k == "a2a_ctas" || k.find("group") != std::string::npos) ? 1
                        : (k == "a2a_engine" || k == "k2_push" || k == "cl_prefetch") ? -1 : 0;
     if (value < lo || value > hi) return fail(VMK_EARG, "option value out of range");

@@ -666,36 +666,43 @@ VMK_HD void k4_body(const Ctx& c, const K4Args& a) {
 }
 
 // ======================================== K6 ====================================================
-// Forward transpose of the distributed FFT as an SM copy: rows of S owned by rank h (R rows of NJ complex, columns
-// [col0, col0+ncols) of this launch) are stored into T_h[row][j0 + col0 ...] with coalesced 16-byte lanes -- NVLink
-// stores in runs of ncols*16 bytes.  Runs on a second stream next to the K1 launch that produces the next columns.
+// The transposes of the distributed FFT as an SM copy from a local staging buffer into the peers' buffers (NVLink
+// stores, coalesced 16-byte lanes, runs of ncols*16 bytes).  Forward (K1 -> K2): rows of S owned by rank h -> block
+// `rank` of T_h, columns of the K1 launch that just finished.  Backward (K2 -> K3, k2_push = 2): block h of the staged
+// result rows -> rows of V_h.  Runs on a second stream beside the launch that produces the next chunk, so a stall on
+// the NVLink store queue never blocks a transform (K2's own push epilogue does: its warps wait at the stores).
 struct K6Args {
-  const double2* S;  // local K1 output [N/2][NJ]
-  PeerPtrs T;        // every rank's spectrum buffer [R][N]
-  int N, NJ, R, j0, col0, ncols, rank, nranks;
+  const double2* src;    // local staging buffer
+  PeerPtrs dst;          // every rank's destination buffer
+  long long src_hstride; // elements between the source blocks of consecutive destination ranks
+  long long src_off;     // first element of the launch's rows / columns inside a source block
+  long long dst_off;     // ... and inside a destination buffer (the same in every peer)
+  int pitch;             // row pitch of both, elements
+  int rows, ncols;       // rows per destination, elements per row
+  int rank, nranks;
+  int order;             // 0: work items destination-major (all CTAs feed one peer at a time), 1: destinations interleaved
 };
-constexpr int kK6Threads = 128;
+constexpr int kK6Threads = 256;
+constexpr int kK6Rows = 8;  // rows per work item = independent 16-byte loads in flight per thread
 
 VMK_HD void k6_push_body(const Ctx& c, const K6Args& a) {
-  const int items = (a.nranks - 1) * a.R;
+  const int rgroups = (a.rows + kK6Rows - 1) / kK6Rows, ctiles = (a.ncols + kK6Threads - 1) / kK6Threads;
+  const int per_dst = rgroups * ctiles, items = (a.nranks - 1) * per_dst;
   for (int it = c.bid; it < items; it += c.nblk) {
-    const int q = it / a.R, row = it % a.R;
+    const int q = a.order ? it % (a.nranks - 1) : it / per_dst;
+    const int w = a.order ? it / (a.nranks - 1) : it % per_dst;
     const int h = (a.rank + 1 + q) % a.nranks;  // neighbour first: the ranks do not all hit one peer at a time
-    const double2* src = a.S + (size_t)(h * a.R + row) * a.NJ + a.col0;
-    double2* dst = reinterpret_cast<double2*>(a.T.p[h]) + ((size_t)a.rank * a.R + row) * a.NJ + a.col0;
-    // 8 independent 16-byte loads in flight per thread before the (remote) stores
-    for (int i0 = 0; i0 < a.ncols; i0 += 8 * kK6Threads) {
-      double2 v[8];
+    const int row0 = (w / ctiles) * kK6Rows, col = (w % ctiles) * kK6Threads + c.tid;
+    const double2* src = a.src + (size_t)h * a.src_hstride + a.src_off + (size_t)row0 * a.pitch + col;
+    double2* dst = reinterpret_cast<double2*>(a.dst.p[h]) + a.dst_off + (size_t)row0 * a.pitch + col;
+    if (col < a.ncols) {
+      double2 v[kK6Rows];
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int i = i0 + c.tid + u * kK6Threads;
-        if (i < a.ncols) v[u] = ld_stream2(src + i);
-      }
+      for (int u = 0; u < kK6Rows; u++)
+        if (row0 + u < a.rows) v[u] = ld_stream2(src + (size_t)u * a.pitch);
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int i = i0 + c.tid + u * kK6Threads;
-        if (i < a.ncols) st_stream2(dst + i, v[u]);
-      }
+      for (int u = 0; u < kK6Rows; u++)
+        if (row0 + u < a.rows) st_stream2(dst + (size_t)u * a.pitch, v[u]);
     }
   }
 }

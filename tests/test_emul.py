@@ -325,11 +325,25 @@ def test_slab_decomposition(emul, oracle_c, n, nranks):
     _slab_run(emul, oracle_c, n, nranks)
 
 
-def _slab_run(emul, oracle_c, n, nranks):
+@pytest.mark.parametrize("n,nranks,opts", [
+    (128, 4, {"a2a_engine": 0, "a2a_chunks": 4, "a2a_order": 1}),   # column-chunked K1, SM push with interleaved peers
+    (128, 8, {"k2_push": 2, "k2_chunks": 4, "a2a_chunks": 2}),      # K2 staged + SM push of row chunks
+    (256, 2, {"k2_push": 2, "a2a_engine": 0, "a2a_order": 1, "a2a_ctas": 3}),
+    (64, 4, {"k2_push": 0}),                                       # K2 staged + copy engines
+])
+def test_slab_transpose_options(emul, oracle_c, n, nranks, opts):
+    """every way the two transposes of the distributed FFT can be scheduled (vmk_set_option) gives the same fields"""
+    _slab_run(emul, oracle_c, n, nranks, opts)
+
+
+def _slab_run(emul, oracle_c, n, nranks, opts=None):
     from cfd_julia_b200.common import Plan
     from cfd_julia_b200._lib import BARRIER_FN
     lib = emul.lib
     plans = [Plan(lib, n, n, r, nranks) for r in range(nranks)]
+    for p in plans:
+        for k, v in (opts or {}).items():
+            p.set_option(k, v)
     arr = (C.c_void_p * nranks)(*[p.handle for p in plans])
     for p in plans:
         lib.check(lib.peer_attach_local(p.handle, arr))
