@@ -100,6 +100,9 @@ struct SizeOps {
   int (*k1)(int grid, const K1Args&, Stream&);
   int (*k2)(int grid, const K2Args&, Stream&);
   int (*k3)(int grid, const K3Args&, Stream&);
+  // fused device-resident loop for small grids (ks_body): one cluster of `q` CTAs; null where it does not apply
+  int (*ks_configure)(int q);
+  int (*ks)(int q, const KSArgs&, Stream&);
   // hybrid RK3/CN solver (vmk_hybrid.cuh); null for the cluster sizes
   int (*kh_configure)(int* res);
   int (*kh)(int grid, const KHArgs&, Stream&);
@@ -127,6 +130,10 @@ struct K2Body {
 template <class C, bool PIECES = false>
 struct K3Body {
   VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, PIECES>(c, a); }
+};
+template <class C>
+struct KSBody {
+  VMK_HD static void run(const Ctx& c, const KSArgs& a) { ks_body<C>(c, a); }
 };
 template <class C>
 struct KHBody {
@@ -300,6 +307,8 @@ SizeOps make_cluster_ops() {
     return a.pieces ? be_launch_cluster<K3CBody<C, Q, true>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s)
                     : be_launch_cluster<K3CBody<C, Q>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
   };
+  o.ks_configure = nullptr;
+  o.ks = nullptr;
   o.kh_configure = nullptr;
   o.kh = nullptr;
   o.fill_ksqperm = nullptr;
@@ -344,6 +353,17 @@ SizeOps make_ops() {
     return a.pieces ? be_launch<K3Body<C, true>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s)
                     : be_launch<K3Body<C>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
   };
+  o.ks_configure = nullptr;
+  o.ks = nullptr;
+  if constexpr (!C::SPLIT && M <= 8) {
+    o.ks_configure = [](int q) -> int {
+      int r = 0;
+      return be_configure_cluster<KSBody<C>, KSArgs, C::CT, 1>(q, C::SMEM_BYTES, &r);
+    };
+    o.ks = [](int q, const KSArgs& a, Stream& s) -> int {
+      return be_launch_cluster<KSBody<C>, KSArgs, C::CT, 1>(q, q, C::SMEM_BYTES, a, s);
+    };
+  }
   if constexpr (C::SPLIT) {  // (measurement / test configurations with the split exchange buffer)
     o.kh_configure = nullptr;
     o.kh = nullptr;
@@ -384,6 +404,8 @@ SizeOps make_ops() {
 bool ops_for(int M, SizeOps* o) {
   switch (M) {
 #ifdef VMK_DEV_SIZES  // kernel-tuning builds only (tools/devbuild.sh): two sizes instead of thirteen, ~2 min of ptxas
+    case 7: *o = make_ops<7>(); return true;
+    case 8: *o = make_ops<8>(); return true;
     case 10: *o = make_ops<10>(); return true;
     case 13: *o = make_ops<13>(); return true;
     default: return false;
@@ -504,6 +526,9 @@ struct vmk_plan {
   int k4_rows = 32, k4_ahead = 4, k4_waves = 3;  // k4_waves: measured on 8 GPUs (profiles/r02_notes.md)
   int k1_prefetch = 0, k2_prefetch = 0, v_pieces = 1, cl_prefetch = -1 /* auto */;
   int use_graph = 1;
+  // small grids: the step loop as one cluster launch (ks_body); ks_q = CTAs of the cluster.  Opt-in: measured SLOWER than
+  // the CUDA graph of 12 launches (128^2: 67.5 against 51.2 us per step, profiles/r02_notes.md section 5)
+  int fuse_small = 0, ks_q = 0;
 #ifndef VMK_EMUL
   std::map<StepParams, cudaGraphExec_t> graphs;
 #endif
@@ -861,8 +886,7 @@ int launch_k3(vmk_plan* p) {
 }
 
 // mode 0: out = r; 1..3: RK3 stages.  win/wn/out index p->w[]
-int launch_k4(vmk_plan* p, int mode, int win, int wn, int out, const StepParams& sp) {
-  K4Args a;
+int make_k4(vmk_plan* p, int win, int wn, int out, const StepParams& sp, K4Args& a) {
   a.w = p->w[win];
   a.psi = p->psi;
   a.wn = p->w[wn];
@@ -887,7 +911,12 @@ int launch_k4(vmk_plan* p, int mode, int win, int wn, int out, const StepParams&
          ctas_x * ((p->NJ + groups * a.rows_per_cta - 1) / (groups * a.rows_per_cta)) < p->k4_waves * 3 * p->sms)
     a.rows_per_cta /= 2;
   const int rows_per = groups * a.rows_per_cta;
-  const int grid = ctas_x * ((p->NJ + rows_per - 1) / rows_per);
+  return ctas_x * ((p->NJ + rows_per - 1) / rows_per);
+}
+
+int launch_k4(vmk_plan* p, int mode, int win, int wn, int out, const StepParams& sp) {
+  K4Args a;
+  const int grid = make_k4(p, win, wn, out, sp, a);
   Timed t(p, KI_K4);
   int rc = 0;
   switch (mode) {
@@ -939,6 +968,67 @@ int enqueue_step(vmk_plan* p, const StepParams& sp) {
   VMK_TRY(enqueue_poisson(p, p->w[2], -1.0));
   VMK_TRY(cross_rank_barrier(p));
   VMK_TRY(launch_k4(p, 3, 2, 0, 0, sp));
+  return 0;
+}
+
+// Small grids on one GPU: `nsteps` steps as one launch of one cluster (ks_body).  Same buffers, tables and per-body
+// work decomposition as enqueue_step.
+bool small_fused_on(const vmk_plan* p) {
+  return p->nranks == 1 && p->ops.ks && p->fuse_small != 0 && p->v_pieces && !p->profiling && !p->barrier_fn &&
+         p->ks_q > 0;
+}
+
+int enqueue_small(vmk_plan* p, const StepParams& sp, int64_t nsteps) {
+  KSArgs a;
+  const int N = p->N;
+  const int src_of[3] = {0, 1, 2}, out_of[3] = {1, 2, 0};
+  for (int s = 0; s < 3; s++) {
+    K1Args& k = a.k1[s];
+    k.w = p->w[src_of[s]];
+    k.S = nullptr;
+    k.Tloc = p->T;
+    k.tw = p->tw;
+    k.NJ = p->NJ;
+    k.npairs = p->NJ / 2;
+    k.k_own0 = 0;
+    k.k_own1 = N / 2;
+    k.prefetch = 0;
+    a.k4_grid[s] = make_k4(p, src_of[s], 0, out_of[s], sp, a.k4[s]);
+  }
+  K2Args& k2 = a.k2;
+  k2.T = p->T;
+  k2.V = p->V;
+  k2.S = nullptr;
+  for (int r = 0; r < kMaxPeers; r++) k2.Vpeer.p[r] = nullptr;
+  k2.push = 0;
+  k2.pieces = 1;
+  k2.tw = p->tw;
+  k2.bbcos = p->bbcos;
+  k2.cccos = p->cccos;
+  k2.ccperm = p->ccperm;
+  k2.aa = p->div_aa;
+  k2.scale = -1.0 / (2.0 * (double)N * (double)N);
+  k2.NJ = p->NJ;
+  k2.log2NJ = p->log2NJ;
+  k2.nrows = N / 2;
+  k2.row0 = 0;
+  k2.R = N / 2;
+  k2.rloc0 = 0;
+  k2.rank = 0;
+  k2.prefetch = 0;
+  K3Args& k3 = a.k3;
+  k3.T = p->V;
+  k3.pieces = 1;
+  k3.prefetch = 0;
+  k3.tw = p->tw;
+  k3.psi = p->psi;
+  k3.lo_dst = p->psi + (size_t)(p->NJ + 1) * N;
+  k3.hi_dst = p->psi;
+  k3.NJ = p->NJ;
+  k3.npairs = p->NJ / 2;
+  a.nsteps = nsteps;
+  VMK_TRY(p->ops.ks(p->ks_q, a, p->st));
+  p->launches++;
   return 0;
 }
 
@@ -1517,6 +1607,13 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
       if (rc) break;
     }
     if ((rc = ops.configure(&p->res_k1, &p->res_k2, &p->res_k3))) break;
+    if (ops.ks && nranks == 1) {
+      // one CTA per block of FPC row pairs, at most 8 (the portable cluster size); 0 = the cluster does not fit
+      const int blocks = ((p->N / 2) + ops.fpc - 1) / ops.fpc;
+      int q = blocks < 8 ? blocks : 8;
+      while (q > 1 && ops.ks_configure(q)) q--;
+      p->ks_q = (q >= 1 && ops.ks_configure(q) == 0) ? q : 0;
+    }
     const size_t sb = sizeof(double) * slab_elems(p);
     for (int b = 0; b < 3 && !rc; b++) rc = dev_alloc(p, (void**)&p->w[b], sb);
     if (rc) break;
@@ -1753,6 +1850,12 @@ int vmk_step(vmk_plan* p, double dx, double dy, double dt, double re, int64_t ns
   VMK_TRY(ensure_divisor(p, dx, dy, 1.e-6));
   const StepParams sp{dx, dy, dt, re};
   VMK_TRY(be_event_record(p->ev0, p->st));
+  if (small_fused_on(p) && nsteps > 0) {
+    VMK_TRY(enqueue_small(p, sp, nsteps));
+    VMK_TRY(be_event_record(p->ev1, p->st));
+    p->ev_valid = true;
+    return VMK_OK;
+  }
 #ifndef VMK_EMUL
   if (p->use_graph && !p->barrier_fn && !p->profiling && nsteps > 0) {
     auto it = p->graphs.find(sp);
@@ -2117,6 +2220,8 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
     if (p->child) p->child->profiling = p->profiling;
   } else if (k == "graph") {
     p->use_graph = value != 0;
+  } else if (k == "fuse_small") {
+    p->fuse_small = value != 0;
   } else if (k == "k4_rows") {
     if (value < 1 || value > 8192) return fail(VMK_EARG, "k4_rows out of range");
     p->k4_rows = (int)value;

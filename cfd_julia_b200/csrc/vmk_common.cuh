@@ -27,6 +27,7 @@ struct Ctx {
   unsigned char* smem;  // dynamic shared memory base (16-byte aligned)
   void* hbar;           // host emulation barrier (unused on device)
   double* hscratch;     // host emulation: two doubles per thread for warp-shuffle emulation (unused on device)
+  bool tables_resident = false;  // the FFT twiddle tables are already in shared memory (fused small-grid step, ks_body)
   int crank;            // rank of the CTA in its thread-block cluster (0 for plain launches)
   int csize;            // CTAs per cluster (1 for plain launches)
   unsigned char* const* hcsmem;  // host emulation: shared-memory bases of the cluster's CTAs (unused on device)

@@ -425,6 +425,7 @@ struct Fft {
 
   // cooperative copy of the twiddle tables into shared memory (all CT threads)
   VMK_HD static void load_tables(const Ctx& c, double2* tw_sm, const double2* tw_g) {
+    if (c.tables_resident) return;
     for (int i = c.tid; i < C::TWN; i += C::CT) tw_sm[i] = tw_g[i];
   }
 };

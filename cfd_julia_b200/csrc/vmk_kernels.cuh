@@ -665,6 +665,56 @@ VMK_HD void k4_body(const Ctx& c, const K4Args& a) {
   }
 }
 
+// ======================================== KS ====================================================
+// Small grids (N <= 256): the whole device-resident loop of `numerical` (vm.jl:24-76) as ONE launch of one thread-block
+// cluster.  At vm.jl's own size (128^2) a step is 12 dependent kernels of ~4.5 us launch latency each and less than a
+// microsecond of work (profiles/r01_notes.md, "Small grids"); here the same kernel bodies run back to back, separated
+// by a hardware cluster barrier (release/acquire at cluster scope orders the global-memory traffic between the CTAs;
+// everything stays in L2), and the twiddle tables are loaded once.  Results are bit-identical to the 12-launch path
+// (same bodies, same work decomposition per body).
+struct KSArgs {
+  K1Args k1[3];  // per RK3 stage: the field that is transformed (wn, wtA, wtB)
+  K2Args k2;
+  K3Args k3;
+  K4Args k4[3];
+  int k4_grid[3];  // CTAs the stand-alone K4 launch would use (its work decomposition is by CTA index)
+  long long nsteps;
+};
+
+template <class C>
+VMK_HD void ks_body(const Ctx& c0, const KSArgs& a) {
+  using F = Fft<C>;
+  Ctx c = c0;
+  F::load_tables(c, F::tables(c.smem), a.k1[0].tw);
+  c.sync();
+  c.tables_resident = true;
+  auto k4_all = [&](auto mode_, const K4Args& k, int grid) {
+    constexpr int MODE = decltype(mode_)::value;
+    for (int vb = c.bid; vb < grid; vb += c.nblk) {
+      Ctx cv = c;
+      cv.bid = vb;
+      cv.nblk = grid;
+      k4_body<MODE>(cv, k);
+    }
+  };
+  for (long long step = 0; step < a.nsteps; step++) {
+    static_for<0, 3>([&](auto s_) {
+      constexpr int s = decltype(s_)::value;
+      k1_body<C>(c, a.k1[s]);
+      c.sync();  // the CTA's shared memory changes hands between the bodies
+      c.cluster_sync();
+      k2_body<C, true>(c, a.k2);
+      c.sync();
+      c.cluster_sync();
+      k3_body<C, true>(c, a.k3);
+      c.sync();
+      c.cluster_sync();
+      k4_all(std::integral_constant<int, s + 1>{}, a.k4[s], a.k4_grid[s]);
+      c.cluster_sync();
+    });
+  }
+}
+
 // ======================================== K6 ====================================================
 // The transposes of the distributed FFT as an SM copy from a local staging buffer into the peers' buffers (NVLink
 // stores, coalesced 16-byte lanes, runs of ncols*16 bytes).  Forward (K1 -> K2): rows of S owned by rank h -> block

@@ -390,3 +390,30 @@ def _slab_run(emul, oracle_c, n, nranks, opts=None):
 def test_ref_py_fixtures(emul, tag):
     """vectors computed by the reference's own Python twins of script 19 (tests/golden/make_ref_fixtures.py)"""
     pc.check_ref_py_lib(emul, tag)
+
+
+@pytest.mark.parametrize("n,nt", [(32, 7), (64, 5), (128, 4), (256, 3)])
+def test_fused_small_grid_step(emul, oracle_c, n, nt):
+    """N <= 256: the whole step loop as one cluster launch (ks_body) is bit-identical to the 12-launch path"""
+    dx, dy, _, _ = grid(n)
+    w0 = vm_field(n) + 0.1 * noise_field(n, 9)
+    dt = stable_dt(n, 1000.)
+    outs = []
+    for fused in (1, 0):
+        emul.clear_plans()
+        p = emul.plan(n, n)
+        p.set_option("fuse_small", fused)
+        p.set_option("k4_rows", 5 if n == 64 else 32)
+        p.upload(w0)
+        l0 = p.launch_count
+        p.step(dx, dy, dt, 1000., nt - 1)
+        p.step(dx, dy, dt, 1000., 1)
+        assert p.launch_count - l0 == (2 if fused else 12 * nt)
+        wn, psi = np.zeros_like(w0), np.zeros_like(w0)
+        p.download(wn, psi)
+        outs.append((wn, psi))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    ref = w0.copy(order="F")
+    _, s = oracle_c.numerical(n, n, nt, dx, dy, dt, 1000., ref)
+    assert rel_l2(outs[0][0], ref) < 1e-12 and rel_l2(outs[0][1], s) < 1e-12
+    emul.clear_plans()
