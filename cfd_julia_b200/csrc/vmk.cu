@@ -62,6 +62,7 @@
 #include "vmk_kernels.cuh"
 #include "vmk_pseudo.cuh"
 #include "vmk_pseudo32.cuh"
+#include "vmk_tri.cuh"
 
 using namespace vmk;
 
@@ -100,6 +101,10 @@ struct SizeOps {
   int (*k1)(int grid, const K1Args&, Stream&);
   int (*k2)(int grid, const K2Args&, Stream&);
   int (*k3)(int grid, const K3Args&, Stream&);
+  // natural-layout variants for the recurrence form of the solve along j (vmk_tri.cuh); null where it does not apply
+  int (*k1n)(int grid, const K1Args&, Stream&);
+  int (*k3n)(int grid, const K3Args&, Stream&);
+  int (*slot_k)(int s);  // kx held in slot s of a natural-layout spectrum row
   // fused device-resident loop for small grids (ks_body): one cluster of `q` CTAs; null where it does not apply
   int (*ks_configure)(int q);
   int (*ks)(int q, const KSArgs&, Stream&);
@@ -119,9 +124,9 @@ struct SizeOps {
   int (*kxf)(int grid, const KXSArgs&, Stream&);
 };
 
-template <class C>
+template <class C, bool NAT = false>
 struct K1Body {
-  VMK_HD static void run(const Ctx& c, const K1Args& a) { k1_body<C>(c, a); }
+  VMK_HD static void run(const Ctx& c, const K1Args& a) { k1_body<C, NAT>(c, a); }
 };
 template <class C, bool PIECES = false>
 struct K2Body {
@@ -129,7 +134,21 @@ struct K2Body {
 };
 template <class C, bool PIECES = false>
 struct K3Body {
-  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, PIECES>(c, a); }
+  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, PIECES ? 1 : 0>(c, a); }
+};
+template <class C>
+struct K3NBody {
+  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, 2>(c, a); }
+};
+struct KTTotals {
+  VMK_HD static void run(const Ctx& c, const KTArgs& a) { kt_totals_body(c, a); }
+};
+template <int PHASE>
+struct KTScan {
+  VMK_HD static void run(const Ctx& c, const KTArgs& a) { kt_scan_body<PHASE>(c, a); }
+};
+struct KTSolve {
+  VMK_HD static void run(const Ctx& c, const KTArgs& a) { kt_solve_body(c, a); }
 };
 template <class C>
 struct KSBody {
@@ -307,6 +326,9 @@ SizeOps make_cluster_ops() {
     return a.pieces ? be_launch_cluster<K3CBody<C, Q, true>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s)
                     : be_launch_cluster<K3CBody<C, Q>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
   };
+  o.k1n = nullptr;
+  o.k3n = nullptr;
+  o.slot_k = nullptr;
   o.ks_configure = nullptr;
   o.ks = nullptr;
   o.kh_configure = nullptr;
@@ -322,6 +344,10 @@ SizeOps make_cluster_ops() {
   o.kxf = nullptr;
   return o;
 }
+
+// sizes with a natural-layout K1 / K3 (the recurrence form of the solve along j, vmk_tri.cuh)
+template <class C>
+constexpr bool kTriSize = !C::SPLIT && C::M >= 6;
 
 template <int M>
 SizeOps make_ops() {
@@ -340,8 +366,24 @@ SizeOps make_ops() {
     int dummy = 0;
     VMK_TRY((be_configure<K2Body<C, true>, K2Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
     VMK_TRY((be_configure<K3Body<C, true>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
+    if constexpr (kTriSize<C>) {
+      VMK_TRY((be_configure<K1Body<C, true>, K1Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
+      VMK_TRY((be_configure<K3NBody<C>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, &dummy)));
+    }
     return 0;
   };
+  o.k1n = nullptr;
+  o.k3n = nullptr;
+  o.slot_k = nullptr;
+  if constexpr (kTriSize<C>) {
+    o.k1n = [](int grid, const K1Args& a, Stream& s) -> int {
+      return be_launch<K1Body<C, true>, K1Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    };
+    o.k3n = [](int grid, const K3Args& a, Stream& s) -> int {
+      return be_launch<K3NBody<C>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    };
+    o.slot_k = [](int s) -> int { return own_half_k<C>(s % C::T, s / C::T); };
+  }
   o.k1 = [](int grid, const K1Args& a, Stream& s) -> int {
     return be_launch<K1Body<C>, K1Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
   };
@@ -444,6 +486,8 @@ int ilog2_exact(int64_t n) {
 }
 
 enum { KI_K1 = 0, KI_K2, KI_K3, KI_K4, KI_COUNT };
+constexpr int kTriMaxK0 = 64;    // rows kx < K0 keep the FFT form along j (vmk_tri.cuh, tests/models/tri_model.py)
+constexpr int kTriAutoN = 1024;  // smallest grid for which the recurrence form is the default
 
 }  // namespace
 
@@ -529,6 +573,17 @@ struct vmk_plan {
   // small grids: the step loop as one cluster launch (ks_body); ks_q = CTAs of the cluster.  Opt-in: measured SLOWER than
   // the CUDA graph of 12 launches (128^2: 67.5 against 51.2 us per step, profiles/r02_notes.md section 5)
   int fuse_small = 0, ks_q = 0;
+  // solve along j as a cyclic tridiagonal solve by two-sided recurrences (vmk_tri.cuh) instead of K2's FFT pair
+  int fps_mode = -1 /* auto: recurrences where the buffers exist and N >= kTriAutoN */, tri_k0 = 0 /* auto */;
+  int tri_nch = 0, tri_k0_tab = -1;
+  double* tri_tab = nullptr;   // [kTriTab][N/2]
+  int* tri_low = nullptr;      // [N/2]
+  double2* tri_tot = nullptr;  // [3][nch][N/2]
+  double2* tri_cin = nullptr;  // [2 nch + 1][N/2]
+  double2* tri_G = nullptr;    // [P][3][N/2]   (peers write their own block)
+  double2* tri_L = nullptr;    // [kTriMaxK0][N] (peers write their own columns)
+  double2* peer_G[kMaxPeers];
+  double2* peer_L[kMaxPeers];
 #ifndef VMK_EMUL
   std::map<StepParams, cudaGraphExec_t> graphs;
 #endif
@@ -563,6 +618,60 @@ int ensure_staging(vmk_plan* p) {
   return dev_alloc(p, (void**)&p->staging, sizeof(double) * (size_t)(p->NJ + 2) * (p->N + 2));
 }
 
+bool tri_on(const vmk_plan* p) {
+  // (the cavity solver's divisor tables, div_kind 1, have no slot tables: it keeps the FFT form)
+  return p->tri_tab && p->div_kind == 0 && (p->fps_mode == 1 || (p->fps_mode < 0 && p->N >= kTriAutoN));
+}
+int tri_k0(const vmk_plan* p) {
+  const int cap = p->N / 4 < kTriMaxK0 ? p->N / 4 : kTriMaxK0;
+  int k0 = p->tri_k0 > 0 ? p->tri_k0 : (p->N / 16 < kTriMaxK0 ? p->N / 16 : kTriMaxK0);
+  if (k0 > cap) k0 = cap;
+  return k0 < 1 ? 1 : k0;
+}
+
+// Per-slot constants of the recurrence form (vmk_tri.cuh; derivation in tests/models/tri_model.py).  The row constant
+// is the reference's own FP64 value  ab = fl(aa + fl(bb cos kx))  (Common.jl:120, what K2 adds cc cos(ky) to); the
+// rest is evaluated in long double and rounded once.
+int fill_tri_tables(vmk_plan* p, const double* bbcos, const double* cccos, double cc) {
+  typedef long double L;
+  const int H = p->N / 2, k0 = tri_k0(p);
+  const double aa = p->div_aa;
+  std::vector<double> tab((size_t)kTriTab * H, 0.0);
+  std::vector<int> low(H, -1);
+  const L a = (L)cc / 2;
+  for (int s = 0; s < H; s++) {
+    const int k = p->ops.slot_k(s);
+    if (k < k0) {  // keeps the FFT form; neutral constants (its totals are computed but never used)
+      low[s] = k;
+      tab[(size_t)3 * H + s] = 1.0;
+      continue;
+    }
+    const double ab = aa + bbcos[k];
+    L delta = -((L)ab / a) - 2;
+    if (delta < 0) delta = 0;
+    const L r = 2 / (2 + delta + sqrtl(delta * (delta + 4)));
+    const L R = powl(r, (L)kTriCH), RJ = powl(r, (L)p->NJ), RN = powl(r, (L)p->N);
+    const L d_tri0 = (L)ab + (L)cc;
+    const L d_ref0 = (L)(double)(ab + cccos[0]);  // fl(ab + fl(cc cos eps)): ky[1] = eps, Common.jl:112-113
+    tab[s] = (double)r;
+    tab[(size_t)H + s] = (double)R;
+    tab[(size_t)2 * H + s] = (double)RJ;
+    tab[(size_t)3 * H + s] = (double)(1 / (1 - RN));
+    tab[(size_t)4 * H + s] = (double)(r * (1 - R * R) / (1 - r * r));
+    tab[(size_t)5 * H + s] = (double)(r * (1 - RJ * RJ) / (1 - r * r));
+    tab[(size_t)6 * H + s] = (double)(-r / ((L)cc * (L)p->N));
+    tab[(size_t)7 * H + s] = (double)((1 / d_ref0 - 1 / d_tri0) / (L)p->N / (2 * (L)p->N));
+    const L Rg = powl(r, (L)(kTriCH * (p->tri_nch / tri_scan_groups(p->tri_nch))));
+    tab[(size_t)8 * H + s] = (double)Rg;
+    tab[(size_t)9 * H + s] = (double)(r * (1 - Rg * Rg) / (1 - r * r));
+  }
+  VMK_TRY(be_h2d(p->tri_tab, tab.data(), sizeof(double) * tab.size(), p->st));
+  VMK_TRY(be_h2d(p->tri_low, low.data(), sizeof(int) * low.size(), p->st));
+  VMK_TRY(be_sync(p->st));
+  p->tri_k0_tab = k0;
+  return 0;
+}
+
 // bb*cos(kx[i]) and cc*cos(ky[j]) exactly as Common.jl:101-113,120 evaluates them (kx[1] = eps, ky = kx).
 // 2N cos() evaluations on the host per (dx,dy,eps); the 2 N^2 per call of the reference disappear.
 int ensure_divisor(vmk_plan* p, double dx, double dy, double eps) {
@@ -590,6 +699,7 @@ int ensure_divisor(vmk_plan* p, double dx, double dy, double eps) {
   VMK_TRY(be_h2d(p->ccperm, cp.data(), sizeof(double) * n, p->st));
   VMK_TRY(be_sync(p->st));
   p->div_aa = -2.0 / (dx * dx) - 2.0 / (dy * dy);  // :101
+  if (p->tri_tab) VMK_TRY(fill_tri_tables(p, b.data(), c.data(), cc));
   p->div_dx = dx;
   p->div_dy = dy;
   p->div_eps = eps;
@@ -946,8 +1056,125 @@ int launch_k5(vmk_plan* p, const double* src, double* dst, size_t total) {
   return 0;
 }
 
+template <class Body>
+int launch_kt(vmk_plan* p, const KTArgs& a) {
+  const int tiles = (a.H + kTriThreads - 1) / kTriThreads;
+  const int items = a.nch * tiles, cap = p->sms * 3 * 4;
+  VMK_TRY((be_launch<Body, KTArgs, kTriThreads, 3>(items < cap ? items : cap, 0, a, p->st)));
+  p->launches++;
+  return 0;
+}
+template <int PHASE>
+int launch_kt_scan(vmk_plan* p, const KTArgs& a) {
+  const int grid = (a.H + kTriScanSlots - 1) / kTriScanSlots;
+  VMK_TRY((be_launch<KTScan<PHASE>, KTArgs, kTriScanThreads, 1>(grid, kTriScanSmem, a, p->st)));
+  p->launches++;
+  return 0;
+}
+
+// The same solve with the j direction in its tridiagonal form (vmk_tri.cuh): K1 (natural rows) -> chunk totals ->
+// rank totals -> [one cross-rank barrier] -> carries, the rows kx < K0 by K2 -> solve in place -> K3 (natural rows).
+// No transpose, on any number of GPUs.
+int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
+  const int N = p->N, H = N / 2, P = p->nranks, k0 = p->tri_k0_tab;
+  {
+    K1Args a;
+    a.w = src;
+    a.S = nullptr;
+    a.Tloc = nullptr;
+    a.X = p->T;
+    a.tw = p->tw;
+    a.NJ = p->NJ;
+    a.npairs = p->NJ / 2;
+    a.k_own0 = 0;
+    a.k_own1 = 0;
+    a.prefetch = p->k1_prefetch;
+    const int work = rowpair_units(p, a.npairs, 1);
+    Timed t(p, KI_K1);
+    VMK_TRY(p->ops.k1n(work < p->res_k1 ? work : p->res_k1, a, p->st));
+    t.done();
+    p->launches++;
+  }
+  KTArgs k;
+  k.X = p->T;
+  k.tab = p->tri_tab;
+  k.lowrow = p->tri_low;
+  k.tot = p->tri_tot;
+  k.cin = p->tri_cin;
+  k.G = p->tri_G;
+  k.L = p->tri_L;
+  for (int r = 0; r < kMaxPeers; r++) {
+    k.Gpeer.p[r] = r < P ? (void*)p->peer_G[r] : nullptr;
+    k.Lpeer.p[r] = r < P ? (void*)p->peer_L[r] : nullptr;
+  }
+  k.H = H;
+  k.NJ = p->NJ;
+  k.nch = p->tri_nch;
+  k.N = N;
+  k.j0 = p->j0;
+  k.rank = p->rank;
+  k.nranks = P;
+  k.sign = sign;
+  Timed t(p, KI_K2);
+  VMK_TRY(launch_kt<KTTotals>(p, k));
+  if (P > 1) VMK_TRY(launch_kt_scan<0>(p, k));
+  VMK_TRY(cross_rank_barrier(p));  // every rank's totals and low-row columns have landed
+  {
+    K2Args a;
+    a.T = p->tri_L;
+    a.V = p->tri_L;
+    a.S = nullptr;
+    for (int r = 0; r < kMaxPeers; r++) a.Vpeer.p[r] = nullptr;
+    a.push = 0;
+    a.pieces = 0;
+    a.tw = p->tw;
+    a.bbcos = p->bbcos;
+    a.cccos = p->cccos;
+    a.ccperm = p->ccperm;
+    a.aa = p->div_aa;
+    a.scale = sign / (2.0 * (double)N * (double)N);
+    a.NJ = N;
+    a.log2NJ = p->M;
+    a.nrows = k0;
+    a.row0 = 0;
+    a.R = k0;
+    a.rloc0 = 0;
+    a.rank = 0;
+    a.prefetch = 0;
+    const int work = (k0 + p->ops.fpc - 1) / p->ops.fpc;
+    VMK_TRY(p->ops.k2(work < p->res_k2 ? work : p->res_k2, a, p->st));
+    p->launches++;
+  }
+  if (P > 1)
+    VMK_TRY(launch_kt_scan<1>(p, k));
+  else
+    VMK_TRY(launch_kt_scan<2>(p, k));
+  VMK_TRY(launch_kt<KTSolve>(p, k));
+  t.done();
+  {
+    K3Args a;
+    a.T = p->T;
+    a.pieces = 0;
+    a.prefetch = 0;
+    a.tw = p->tw;
+    a.psi = p->psi;
+    const int prev = (p->rank + P - 1) % P, next = (p->rank + 1) % P;
+    a.lo_dst = p->peer_psi[prev] + (size_t)(p->NJ + 1) * N;
+    a.hi_dst = p->peer_psi[next];
+    a.NJ = p->NJ;
+    a.npairs = p->NJ / 2;
+    const int work = rowpair_units(p, a.npairs, 1);
+    Timed t3(p, KI_K3);
+    VMK_TRY(p->ops.k3n(work < p->res_k3 ? work : p->res_k3, a, p->st));
+    t3.done();
+    p->launches++;
+  }
+  return 0;
+}
+
 // psi = solve(sign * src): K1 -> K2 -> K3.  Common.jl:115-123
 int enqueue_poisson(vmk_plan* p, const double* src, double sign) {
+  if (tri_on(p)) return enqueue_poisson_tri(p, src, sign);
   VMK_TRY(launch_k1(p, src));
   VMK_TRY(cross_rank_barrier(p));  // every rank's spectrum is written before any rank transforms along j
   VMK_TRY(launch_k2(p, sign));
@@ -1621,6 +1848,21 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     if ((rc = dev_alloc(p, (void**)&p->T, sizeof(double2) * (size_t)(p->N / 2) * p->NJ))) break;
     if ((rc = dev_alloc(p, (void**)&p->V, sizeof(double2) * (size_t)(p->N / 2) * p->NJ))) break;
     if (nranks > 1 && (rc = dev_alloc(p, (void**)&p->S, sizeof(double2) * (size_t)(p->N / 2) * p->NJ))) break;
+    {
+      // buffers of the recurrence form (vmk_tri.cuh); G and L always exist (tiny when unused) because peers map them
+      const bool tri = ops.k1n && (p->NJ % kTriCH) == 0;
+      const size_t H = (size_t)p->N / 2;
+      p->tri_nch = tri ? p->NJ / kTriCH : 0;
+      if (tri) {
+        if ((rc = dev_alloc(p, (void**)&p->tri_tab, sizeof(double) * kTriTab * H))) break;
+        if ((rc = dev_alloc(p, (void**)&p->tri_low, sizeof(int) * H))) break;
+        if ((rc = dev_alloc(p, (void**)&p->tri_tot, sizeof(double2) * 3 * p->tri_nch * H))) break;
+        if ((rc = dev_alloc(p, (void**)&p->tri_cin, sizeof(double2) * (2 * (size_t)p->tri_nch + 1) * H))) break;
+      }
+      if ((rc = dev_alloc(p, (void**)&p->tri_G, tri ? sizeof(double2) * 3 * H * nranks : 16))) break;
+      const size_t lrows = H < (size_t)kTriMaxK0 ? H : (size_t)kTriMaxK0;
+      if ((rc = dev_alloc(p, (void**)&p->tri_L, tri ? sizeof(double2) * lrows * p->N : 16))) break;
+    }
     if ((rc = dev_alloc(p, (void**)&p->tw, sizeof(double2) * (ops.twn ? ops.twn : 1)))) break;
     if ((rc = dev_alloc(p, (void**)&p->flags, sizeof(unsigned long long) * (kMaxPeers + 2)))) break;
 #ifndef VMK_EMUL
@@ -1646,7 +1888,11 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     p->peer_T[r] = nullptr;
     p->peer_V[r] = nullptr;
     p->peer_flags[r] = nullptr;
+    p->peer_G[r] = nullptr;
+    p->peer_L[r] = nullptr;
   }
+  p->peer_G[rank] = p->tri_G;
+  p->peer_L[rank] = p->tri_L;
   for (int b = 0; b < 3; b++) p->peer_w[b][rank] = p->w[b];
   p->peer_psi[rank] = p->psi;
   p->peer_T[rank] = p->T;
@@ -1680,6 +1926,12 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_free(p->bbcos);
   be_free(p->cccos);
   be_free(p->ccperm);
+  be_free(p->tri_tab);
+  be_free(p->tri_low);
+  be_free(p->tri_tot);
+  be_free(p->tri_cin);
+  be_free(p->tri_G);
+  be_free(p->tri_L);
   be_free(p->staging);
   be_free(p->hW);
   be_free(p->hJ);
@@ -1718,7 +1970,7 @@ int vmk_plan_destroy(vmk_plan* p) {
 
 // ---- slab decomposition: peer buffer exchange ------------------------------------------------------
 // A blob carries the handles of one rank's seven exchange buffers (w[0..2], psi, T, V, barrier flags).
-constexpr int kPeerBufs = 7;
+constexpr int kPeerBufs = 9;
 struct PeerBlob {
   IpcHandle h[kPeerBufs];
 };
@@ -1729,7 +1981,7 @@ int vmk_peer_export(vmk_plan* p, void* blob) {
   VMK_GUARD(p);
   if (!p || !blob) return fail(VMK_EARG, "NULL argument");
   PeerBlob* b = static_cast<PeerBlob*>(blob);
-  void* ptrs[kPeerBufs] = {p->w[0], p->w[1], p->w[2], p->psi, p->T, p->V, p->flags};
+  void* ptrs[kPeerBufs] = {p->w[0], p->w[1], p->w[2], p->psi, p->T, p->V, p->flags, p->tri_G, p->tri_L};
   for (int i = 0; i < kPeerBufs; i++) VMK_TRY(be_ipc_export(ptrs[i], &b->h[i]));
   return VMK_OK;
 }
@@ -1751,6 +2003,8 @@ int vmk_peer_import(vmk_plan* p, const void* blobs) {
     p->peer_T[r] = (double2*)ptrs[4];
     p->peer_V[r] = (double2*)ptrs[5];
     p->peer_flags[r] = (unsigned long long*)ptrs[6];
+    p->peer_G[r] = (double2*)ptrs[7];
+    p->peer_L[r] = (double2*)ptrs[8];
   }
   p->peers_ready = true;
   return VMK_OK;
@@ -1771,6 +2025,8 @@ int vmk_peer_attach_local(vmk_plan* p, vmk_plan* const* plans) {
     p->peer_T[r] = plans[r]->T;
     p->peer_V[r] = plans[r]->V;
     p->peer_flags[r] = plans[r]->flags;
+    p->peer_G[r] = plans[r]->tri_G;
+    p->peer_L[r] = plans[r]->tri_L;
   }
   p->peers_ready = true;
   return VMK_OK;
@@ -2222,6 +2478,16 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
     p->use_graph = value != 0;
   } else if (k == "fuse_small") {
     p->fuse_small = value != 0;
+  } else if (k == "fps_mode") {  // 0: FFT along j (K2); 1: recurrences along j (vmk_tri.cuh); -1: by grid size
+    if (value > 0 && !p->tri_tab)
+      return fail(VMK_ESIZE, "the recurrence form needs 32 | rows per rank, N >= 64 and a row that fits one SM");
+    p->fps_mode = value < 0 ? -1 : (value != 0);
+    drop_graphs(p);
+  } else if (k == "tri_k0") {  // rows kx < K0 keep the FFT form (0: N/16, at most 64)
+    if (value < 0 || value > kTriMaxK0) return fail(VMK_EARG, "tri_k0 out of range");
+    p->tri_k0 = (int)value;
+    p->div_valid = false;  // the slot tables are rebuilt by the next call
+    drop_graphs(p);
   } else if (k == "k4_rows") {
     if (value < 1 || value > 8192) return fail(VMK_EARG, "k4_rows out of range");
     p->k4_rows = (int)value;

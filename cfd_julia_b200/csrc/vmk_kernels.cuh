@@ -61,14 +61,18 @@ struct K1Args {
   int npairs;         // row pairs handled by this launch (w, S and Tloc are offset to its first pair)
   int k_own0, k_own1; // spectrum rows [k_own0, k_own1) are owned by this rank
   int prefetch;       // 0 off, 1: bulk L2 prefetch of the rows of the pair after next
+  double2* X;         // NAT: spectrum rows [jl][N/2] in slot order (vmk_tri.cuh), offset to the launch's first row
 };
 
 // Per row pair: rows (already in the exchange buffer, put there asynchronously during the previous pair's store
 // phase) -> registers -> forward FFT -> spectrum to shared memory -> Z[k], Z[N-k] to registers -> start the
 // asynchronous copy of the next pair's rows -> unpack and transposed 32-byte stores.
-template <class C>
+// NAT: the half spectrum of row jl goes to X[jl][s], slot s = t + T i = the order in which the threads hold it
+// (coalesced 16-byte stores, nothing is transposed); the solve along j is then vmk_tri.cuh's.
+template <class C, bool NAT = false>
 VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
   using F = Fft<C>;
+  static_assert(!(NAT && C::SPLIT), "the slot order of the natural layout is the own-half order");
   constexpr int N = C::N, E = C::E, T = C::T, P = C::P, NI = N / 2 / T;
   double2* tw = F::tables(c.smem);
   F::load_tables(c, tw, a.tw);
@@ -170,9 +174,15 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
           o0 = mk2(zk[i].x + zm[i].x, zk[i].y - zm[i].y);  // 2 X_j[k]   = Z[k] + conj Z[N-k]
           o1 = mk2(zk[i].y + zm[i].y, zm[i].x - zk[i].x);  // 2 X_j+1[k] = -i (Z[k] - conj Z[N-k])
         }
-        double2* dst = ((k >= a.k_own0 && k < a.k_own1) ? a.Tloc + (size_t)(k - a.k_own0) * a.NJ
-                                                        : a.S + (size_t)k * a.NJ) + jl;
-        st_stream4(dst, o0, o1);
+        if constexpr (NAT) {
+          double2* xr = a.X + (size_t)jl * (N / 2) + t + T * i;
+          st_stream2(xr, o0);
+          st_stream2(xr + N / 2, o1);
+        } else {
+          double2* dst = ((k >= a.k_own0 && k < a.k_own1) ? a.Tloc + (size_t)(k - a.k_own0) * a.NJ
+                                                          : a.S + (size_t)k * a.NJ) + jl;
+          st_stream4(dst, o0, o1);
+        }
       });
     }
   }
@@ -381,9 +391,13 @@ struct K3Args {
   int prefetch;       // cluster kernels: bulk L2 prefetch of the next pair's pieces
 };
 
-template <class C, bool PIECES>
+// LAYOUT of the solution spectrum: 0 = rows [kx][NJ] (32-byte pieces gathered from N/2 rows), 1 = PIECES,
+// 2 = natural rows [jl][N/2] in K1's slot order (vmk_tri.cuh): two contiguous 8N-byte rows per pair
+template <class C, int LAYOUT>
 VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
   using F = Fft<C>;
+  constexpr bool PIECES = LAYOUT == 1, NAT = LAYOUT == 2;
+  static_assert(!(NAT && C::SPLIT), "the slot order of the natural layout is the own-half order");
   constexpr int N = C::N, E = C::E, T = C::T, P = C::P, NI = N / 2 / T;
   double2* tw = F::tables(c.smem);
   F::load_tables(c, tw, a.tw);
@@ -459,9 +473,9 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
       c.sync();
       F::template load_part<P - 1, 1>(v, sd, t);
     } else {
-      if constexpr (PIECES) {
-        // the pair's N/2 pieces are one contiguous 16N-byte block in consumption order; the next pair's block is
-        // pulled into L2 by a single bulk prefetch while this pair is transformed
+      if constexpr (PIECES || NAT) {
+        // the pair's N/2 pieces (NAT: its two rows) are one contiguous 16N-byte block in consumption order; the next
+        // pair's block is pulled into L2 by a single bulk prefetch while this pair is transformed
         if (c.tid == 0 && pb + c.nblk < nblocks) {
           const int p0 = (pb + c.nblk) * C::FPC;
           const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
@@ -470,6 +484,7 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
       }
       // two half batches (loads of a half in flight together, then its repack) keep the register peak below the cap
       constexpr int NB = NI >= 8 ? 2 : 1, NH = NI / NB;
+      constexpr int bl_ = C::bits(P - 1), hl_ = 1 << (bl_ - 1);
       static_for<0, NB>([&](auto b_) {
         constexpr int b = decltype(b_)::value;
         double2 ua[NH], ub[NH];
@@ -477,9 +492,15 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
           static_for<0, NH>([&](auto i_) {
             constexpr int i = b * NH + decltype(i_)::value;
             const int idx = t + T * i;
-            const double2* src = PIECES ? a.T + (size_t)pair * N + 2 * idx
-                                        : a.T + (size_t)F::k_of_pos(halfspec_pos<C>(idx)) * a.NJ + jl;
-            ld_stream4(src, ua[i - b * NH], ub[i - b * NH]);
+            if constexpr (NAT) {
+              const double2* src = a.T + (size_t)jl * (N / 2) + idx;
+              ua[i - b * NH] = ld_stream2(src);
+              ub[i - b * NH] = ld_stream2(src + N / 2);
+            } else {
+              const double2* src = PIECES ? a.T + (size_t)pair * N + 2 * idx
+                                          : a.T + (size_t)F::k_of_pos(halfspec_pos<C>(idx)) * a.NJ + jl;
+              ld_stream4(src, ua[i - b * NH], ub[i - b * NH]);
+            }
           });
         }
         if constexpr (b == 0) c.sync();  // the previous pair's last exchange has been read everywhere
@@ -487,7 +508,8 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
         if (active) {
           static_for<0, NH>([&](auto i_) {
             constexpr int ii = decltype(i_)::value, i = b * NH + ii;
-            const int pos = halfspec_pos<C>(t + T * i);
+            // NAT: slot t + T i holds kx = own_half_k(t, i) (the position K1's thread t held it at)
+            const int pos = NAT ? (((t + T * (i / hl_)) << bl_) | (i % hl_)) : halfspec_pos<C>(t + T * i);
             const int k = F::k_of_pos(pos);
             if (k == 0) {
               sm[F::addr(0)] = mk2(ua[ii].x, ub[ii].x);                   // Z[0]   = u0_j + i u0_j+1
@@ -706,7 +728,7 @@ VMK_HD void ks_body(const Ctx& c0, const KSArgs& a) {
       k2_body<C, true>(c, a.k2);
       c.sync();
       c.cluster_sync();
-      k3_body<C, true>(c, a.k3);
+      k3_body<C, 1>(c, a.k3);
       c.sync();
       c.cluster_sync();
       k4_all(std::integral_constant<int, s + 1>{}, a.k4[s], a.k4_grid[s]);

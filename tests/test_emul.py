@@ -417,3 +417,49 @@ def test_fused_small_grid_step(emul, oracle_c, n, nt):
     _, s = oracle_c.numerical(n, n, nt, dx, dy, dt, 1000., ref)
     assert rel_l2(outs[0][0], ref) < 1e-12 and rel_l2(outs[0][1], s) < 1e-12
     emul.clear_plans()
+
+
+# ---- the solve along j as a cyclic tridiagonal solve by two-sided recurrences (csrc/vmk_tri.cuh) -----------------------
+@pytest.mark.parametrize("n,k0", [(64, 0), (128, 1), (256, 0), (512, 5), (1024, 0), (2048, 64)])
+def test_tri_fps(emul, oracle_c, n, k0):
+    """fps with fps_mode = 1 (FFT along i, recurrences along j, rows kx < K0 by K2) against the oracle's FFT x FFT"""
+    emul.clear_plans()
+    p = emul.plan(n, n)
+    p.set_option("fps_mode", 1)
+    p.set_option("tri_k0", k0)
+    pc.check_fps_noise(emul, oracle_c, n, seed=n)
+    emul.clear_plans()
+
+
+@pytest.mark.parametrize("n,nt", [(64, 10), (128, 6), (256, 4), (512, 3)])
+def test_tri_rhs_and_numerical(emul, oracle_c, n, nt):
+    emul.clear_plans()
+    emul.plan(n, n).set_option("fps_mode", 1)
+    pc.check_rhs(emul, oracle_c, noise_field(n, seed=n + 7))
+    pc.check_numerical(emul, oracle_c, vm_field(n), nt, stable_dt(n, 1000.), 1000.)
+    emul.clear_plans()
+
+
+def test_tri_default_by_size(emul, oracle_c):
+    """the recurrence form is the default from 1024^2 up: 6 launches per Poisson solve instead of 3"""
+    emul.clear_plans()
+    n = 1024
+    dx, dy, _, _ = grid(n)
+    p = emul.plan(n, n)
+    p.upload(vm_field(n))
+    l0 = p.launch_count
+    p.step(dx, dy, stable_dt(n, 1000.), 1000., 1)
+    assert p.launch_count - l0 == 3 * (6 + 1)
+    p.set_option("fps_mode", 0)
+    l0 = p.launch_count
+    p.step(dx, dy, stable_dt(n, 1000.), 1000., 1)
+    assert p.launch_count - l0 == 12
+    with pytest.raises(Exception):
+        emul.plan(32, 32).set_option("fps_mode", 1)
+    emul.clear_plans()
+
+
+@pytest.mark.parametrize("n,nranks,k0", [(64, 2, 0), (128, 4, 3), (256, 8, 0), (256, 2, 16), (512, 4, 0)])
+def test_tri_slab(emul, oracle_c, n, nranks, k0):
+    """slab decomposition without transposes: three complex numbers per kx and rank cross the ranks"""
+    _slab_run(emul, oracle_c, n, nranks, {"fps_mode": 1, "tri_k0": k0})
