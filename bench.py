@@ -41,7 +41,11 @@ def metric_name(n):
 UNIT = "grid-point-steps/s"
 BYTES_PER_POINT_STEP = 232.0
 # algorithmic bytes per grid point per launch: K1/K2/K3 read 8 + write 8; K4 reads w, psi (+wn) and writes
-KERNEL_BYTES = {"k1": 16.0, "k2": 16.0, "k3": 16.0, "k4": (24.0 + 32.0 + 32.0) / 3.0}
+KERNEL_BYTES = {"k1": 16.0, "k2": 16.0, "k3": 16.0, "k4": (24.0 + 32.0 + 32.0) / 3.0,
+                # recurrence form of the solve along j (csrc/vmk_tri.cuh): totals read the spectrum; the scan reads 3 and
+                # writes 2 complex numbers per chunk of 32 points; the solve reads and writes the spectrum; K2 transforms
+                # K0 = 64 of the N/2 spectrum rows (latency, not bandwidth: it runs beside the others)
+                "kt_totals": 8.0 + 48.0 / 32, "kt_scan": 80.0 / 32, "kt_solve": 16.0 + 32.0 / 32, "k2_low_rows": 0.25}
 RE, DT = 1000., 1e-4
 
 
@@ -336,6 +340,18 @@ def main():
     prof = plan.profile_steps(dx, dx, DT, RE, 3)
     pts = float(n) * (n // world)
     kern = {}
+    tri = plan.profile_tri()
+    fps_mode = "recurrences along j (csrc/vmk_tri.cuh)" if tri["kt_solve"]["launches"] else "FFT along j (K2)"
+    if tri["kt_solve"]["launches"]:
+        # the "k2" class of the recurrence form = chunk totals (reads the spectrum: 8 B/point) + scan (chunk totals and
+        # carries: 80 B per 32 points) + in-place solve (16 B/point) + K2 on the rows kx < K0 (beside them, on a
+        # second stream; timed in line here): list the three streaming kernels separately
+        rest = prof["k2"]["ms"] - sum(v["ms"] for v in tri.values())
+        nlow = prof["k2"]["launches"] - sum(v["launches"] for v in tri.values())
+        prof = dict(prof)
+        prof.pop("k2")
+        prof.update(tri)
+        prof["k2_low_rows"] = {"ms": rest, "launches": nlow}
     for k, v in prof.items():
         if v["launches"]:
             dur = v["ms"] / v["launches"]
@@ -346,9 +362,11 @@ def main():
     step_gbs = BYTES_PER_POINT_STEP * value / world / 1e9
     roofline = {"bound": "hbm", "kernel": top, "achieved": kern[top]["achieved_gbs"] if top else None, "peak": peak,
                 "unit": "GB/s", "frac": kern[top]["frac"] if top else None, "traffic": None, "peak_source": peak_src,
-                "kernels": kern,
+                "kernels": kern, "solve_along_j": fps_mode,
                 "step": {"achieved": step_gbs, "frac": step_gbs / peak, "frac_of_8TBs": step_gbs / 8000.,
-                         "bytes_per_point_step": BYTES_PER_POINT_STEP}}
+                         "bytes_per_point_step": BYTES_PER_POINT_STEP,
+                         "bytes_note": "232 = the FFT x FFT formulation's algorithmic traffic (SURVEY 8d), kept as the "
+                                       "common numerator; the recurrence form moves 8 B/point more per solve (256)"}}
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this command at 8192^2 on one
     # GPU (profiles/traffic.json, tools/ncu_summary.py); a capture exists for that configuration only
     roofline["kernel_times"] = ("CUDA events around every launch in a separate un-graphed pass (vmk_profile_steps); "
@@ -415,7 +433,12 @@ def main():
             "config": {**workload_config(n, DT),
                        "l2": f"working set {plan.device_bytes / 1e9:.1f} GB >> 126 MB L2, no flush needed",
                        "parallelism": f"slab{world}" if world > 1 else "single GPU",
-                       "exchange": "peer stores over NVLink inside K1/K2/K3/K4 + device-side flag barriers"
+                       "exchange": (("no transposes: per Poisson solve every rank stores 3 complex numbers per kx (rank "
+                                     "totals of the recurrences) and its columns of the K0 = 64 FFT-form rows into each "
+                                     "peer over NVLink, + halo rows of psi and w; "
+                                     if roofline.get("solve_along_j", "").startswith("rec") else
+                                     "all-to-all transposes as peer stores over NVLink inside K1/K2, halo rows; ")
+                                    + "device-side flag barriers, no NCCL call on the data path")
                        if world > 1 else None,
                        "cuda_graph": True},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,

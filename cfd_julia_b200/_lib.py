@@ -50,6 +50,7 @@ _PROTOS = {
     "step_elapsed_ms": (C.c_int, [_P, C.POINTER(_D)]),
     "profile_steps": (C.c_int, [_P, _D, _D, _D, _D, C.c_int64, C.POINTER(_D), C.POINTER(C.c_int64)]),
     "profile_read": (C.c_int, [_P, C.POINTER(_D), C.POINTER(C.c_int64)]),
+    "profile_tri": (C.c_int, [_P, C.POINTER(_D), C.POINTER(C.c_int64)]),
     "launch_count": (C.c_int64, [_P]),
     "set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "device_bytes": (C.c_int64, [_P]),

@@ -98,6 +98,13 @@ class Plan:
         self.lib.check(self.lib.profile_steps(self.handle, dx, dy, dt, re, nsteps, ms, n))
         return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(("k1", "k2", "k3", "k4"))}
 
+    def profile_tri(self):
+        """The recurrence kernels' part of the last profile_steps' "k2" class (csrc/vmk_tri.cuh); see vmk_profile_tri."""
+        ms = (C.c_double * 3)()
+        n = (C.c_int64 * 3)()
+        self.lib.check(self.lib.profile_tri(self.handle, ms, n))
+        return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(("kt_totals", "kt_scan", "kt_solve"))}
+
     def profile_read(self):
         """Per-class kernel time since the last read (after set_option("profile", 1)); see vmk_profile_read."""
         ms = (C.c_double * 4)()

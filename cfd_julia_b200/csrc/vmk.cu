@@ -36,6 +36,7 @@
 #define vmk_step_elapsed_ms vmke_step_elapsed_ms
 #define vmk_profile_steps vmke_profile_steps
 #define vmk_profile_read vmke_profile_read
+#define vmk_profile_tri vmke_profile_tri
 #define vmk_launch_count vmke_launch_count
 #define vmk_set_option vmke_set_option
 #define vmk_device_bytes vmke_device_bytes
@@ -257,9 +258,13 @@ void fill_ccperm(const double* cccos, double* out) {
 }
 
 // ---- rows spanning a thread-block cluster (vmk_cluster.cuh) ----------------------------------------------------
-template <class C, int Q>
+template <class C, int Q, bool NAT = false>
 struct K1CBody {
-  VMK_HD static void run(const Ctx& c, const K1Args& a) { k1c_body<C, Q>(c, a); }
+  VMK_HD static void run(const Ctx& c, const K1Args& a) { k1c_body<C, Q, NAT>(c, a); }
+};
+template <class C, int Q>
+struct K3CNBody {
+  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3c_body<C, Q, 2>(c, a); }
 };
 template <class C, int Q, bool PIECES = false>
 struct K2CBody {
@@ -267,7 +272,7 @@ struct K2CBody {
 };
 template <class C, int Q, bool PIECES = false>
 struct K3CBody {
-  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3c_body<C, Q, PIECES>(c, a); }
+  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3c_body<C, Q, PIECES ? 1 : 0>(c, a); }
 };
 
 template <class C, int Q>
@@ -313,6 +318,11 @@ SizeOps make_cluster_ops() {
     VMK_TRY((be_configure_cluster<K3CBody<C, Q, true>, K3Args, C::CT, 1>(Q, C::SMEM_BYTES, &d3)));
     if (d2 < *r2) *r2 = d2;
     if (d3 < *r3) *r3 = d3;
+    int d1 = 0;
+    VMK_TRY((be_configure_cluster<K1CBody<C, Q, true>, K1Args, C::CT, 1>(Q, C::SMEM_BYTES, &d1)));
+    VMK_TRY((be_configure_cluster<K3CNBody<C, Q>, K3Args, C::CT, 1>(Q, C::SMEM_BYTES, &d3)));
+    if (d1 < *r1) *r1 = d1;
+    if (d3 < *r3) *r3 = d3;
     return 0;
   };
   o.k1 = [](int grid, const K1Args& a, Stream& s) -> int {
@@ -326,9 +336,16 @@ SizeOps make_cluster_ops() {
     return a.pieces ? be_launch_cluster<K3CBody<C, Q, true>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s)
                     : be_launch_cluster<K3CBody<C, Q>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
   };
-  o.k1n = nullptr;
-  o.k3n = nullptr;
-  o.slot_k = nullptr;
+  o.k1n = [](int grid, const K1Args& a, Stream& s) -> int {
+    return be_launch_cluster<K1CBody<C, Q, true>, K1Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
+  };
+  o.k3n = [](int grid, const K3Args& a, Stream& s) -> int {
+    return be_launch_cluster<K3CNBody<C, Q>, K3Args, C::CT, 1>(grid, Q, C::SMEM_BYTES, a, s);
+  };
+  o.slot_k = [](int s) -> int {
+    constexpr int HP = C::N / 2;  // slots per CTA of the cluster
+    return Q * own_half_k<C>((s % HP) % C::T, (s % HP) / C::T) + s / HP;
+  };
   o.ks_configure = nullptr;
   o.ks = nullptr;
   o.kh_configure = nullptr;
@@ -485,7 +502,10 @@ int ilog2_exact(int64_t n) {
   return ((((int64_t)1) << m) == n) ? m : -1;
 }
 
-enum { KI_K1 = 0, KI_K2, KI_K3, KI_K4, KI_COUNT };
+// the first four are the classes of vmk_profile_steps / vmk_profile_read; KT1..KT3 (chunk totals, scan, solve of
+// vmk_tri.cuh) are folded into K2's class there and listed separately by vmk_profile_tri
+enum { KI_K1 = 0, KI_K2, KI_K3, KI_K4, KI_KT1, KI_KT2, KI_KT3, KI_COUNT };
+constexpr int KI_ABI = 4;
 constexpr int kTriMaxK0 = 64;    // rows kx < K0 keep the FFT form along j (vmk_tri.cuh, tests/models/tri_model.py)
 constexpr int kTriAutoN = 1024;  // smallest grid for which the recurrence form is the default
 
@@ -589,8 +609,10 @@ struct vmk_plan {
 #endif
   // per-kernel timing (vmk_profile_steps)
   bool profiling = false;
-  double prof_ms[KI_COUNT] = {0, 0, 0, 0};
-  int64_t prof_n[KI_COUNT] = {0, 0, 0, 0};
+  double prof_ms[KI_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  int64_t prof_n[KI_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  double tri_ms[3] = {0, 0, 0};  // last vmk_profile_steps: totals, scan, solve
+  int64_t tri_n[3] = {0, 0, 0};
   std::vector<std::pair<int, std::pair<Event, Event>>> prof_events;
 };
 
@@ -870,8 +892,7 @@ int launch_k1(vmk_plan* p, const double* src) {
   }
   if (P > 1) {
     VMK_TRY(be_event_record(p->ev_join, p->st_copy));
-    VMK_TRY(be_stream_wait(p->st, p->ev_join));
-    VMK_TRY(be_event_record(p->ev_join2, p->st_copy2));
+      VMK_TRY(be_event_record(p->ev_join2, p->st_copy2));
     VMK_TRY(be_stream_wait(p->st, p->ev_join2));
   }
   t.done();
@@ -947,8 +968,7 @@ int launch_k2(vmk_plan* p, double sign) {
   }
   if (P > 1 && !push) {
     VMK_TRY(be_event_record(p->ev_join, p->st_copy));
-    VMK_TRY(be_stream_wait(p->st, p->ev_join));
-    VMK_TRY(be_event_record(p->ev_join2, p->st_copy2));
+      VMK_TRY(be_event_record(p->ev_join2, p->st_copy2));
     VMK_TRY(be_stream_wait(p->st, p->ev_join2));
   }
   t.done();
@@ -1089,7 +1109,12 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
     a.k_own0 = 0;
     a.k_own1 = 0;
     a.prefetch = p->k1_prefetch;
-    const int work = rowpair_units(p, a.npairs, 1);
+    for (int r = 0; r < kMaxPeers; r++) a.Lpeer.p[r] = r < P ? (void*)p->peer_L[r] : nullptr;
+    a.k0 = k0;
+    a.jbase = p->j0;
+    a.nranks = P;
+    a.prefetch = p->ops.cluster > 1 ? (cl_prefetch_mask(p) & 1) : p->k1_prefetch;
+    const int work = rowpair_units(p, a.npairs, 1) * p->ops.cluster;
     Timed t(p, KI_K1);
     VMK_TRY(p->ops.k1n(work < p->res_k1 ? work : p->res_k1, a, p->st));
     t.done();
@@ -1103,10 +1128,7 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
   k.cin = p->tri_cin;
   k.G = p->tri_G;
   k.L = p->tri_L;
-  for (int r = 0; r < kMaxPeers; r++) {
-    k.Gpeer.p[r] = r < P ? (void*)p->peer_G[r] : nullptr;
-    k.Lpeer.p[r] = r < P ? (void*)p->peer_L[r] : nullptr;
-  }
+  for (int r = 0; r < kMaxPeers; r++) k.Gpeer.p[r] = r < P ? (void*)p->peer_G[r] : nullptr;
   k.H = H;
   k.NJ = p->NJ;
   k.nch = p->tri_nch;
@@ -1115,11 +1137,10 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
   k.rank = p->rank;
   k.nranks = P;
   k.sign = sign;
-  Timed t(p, KI_K2);
-  VMK_TRY(launch_kt<KTTotals>(p, k));
-  if (P > 1) VMK_TRY(launch_kt_scan<0>(p, k));
-  VMK_TRY(cross_rank_barrier(p));  // every rank's totals and low-row columns have landed
-  {
+  // the rows kx < K0 in L by K2's FFT pair, on the second stream beside the totals / the scan (on the plan's own
+  // stream while profiling, so that its events bracket it): L is complete after K1 on one rank, after the barrier on
+  // several
+  auto low_rows = [&]() -> int {
     K2Args a;
     a.T = p->tri_L;
     a.V = p->tri_L;
@@ -1141,18 +1162,44 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
     a.rloc0 = 0;
     a.rank = 0;
     a.prefetch = 0;
-    const int work = (k0 + p->ops.fpc - 1) / p->ops.fpc;
-    VMK_TRY(p->ops.k2(work < p->res_k2 ? work : p->res_k2, a, p->st));
+    const int work = (k0 + p->ops.fpc - 1) / p->ops.fpc * p->ops.cluster;
+    const int grid = work < p->res_k2 ? work : p->res_k2;
     p->launches++;
+    if (p->profiling) {
+      Timed t(p, KI_K2);
+      VMK_TRY(p->ops.k2(grid, a, p->st));
+      t.done();
+      return be_event_record(p->ev_join, p->st);
+    }
+    VMK_TRY(be_event_record(p->ev_chunk[0], p->st));
+    VMK_TRY(be_stream_wait(p->st_copy, p->ev_chunk[0]));
+    VMK_TRY(p->ops.k2(grid, a, p->st_copy));
+    return be_event_record(p->ev_join, p->st_copy);
+  };
+  auto timed = [&](int which, auto&& launch) -> int {
+    Timed t(p, which);
+    VMK_TRY(launch());
+    t.done();
+    return 0;
+  };
+  if (P == 1) {
+    VMK_TRY(low_rows());
+    VMK_TRY(timed(KI_KT1, [&] { return launch_kt<KTTotals>(p, k); }));
+    VMK_TRY(timed(KI_KT2, [&] { return launch_kt_scan<2>(p, k); }));
+  } else {
+    VMK_TRY(timed(KI_KT1, [&] { return launch_kt<KTTotals>(p, k); }));
+    VMK_TRY(timed(KI_KT2, [&] { return launch_kt_scan<0>(p, k); }));
+    VMK_TRY(cross_rank_barrier(p));  // every rank's totals and low-row columns have landed
+    VMK_TRY(low_rows());
+    VMK_TRY(timed(KI_KT2, [&] { return launch_kt_scan<1>(p, k); }));
   }
-  if (P > 1)
-    VMK_TRY(launch_kt_scan<1>(p, k));
-  else
-    VMK_TRY(launch_kt_scan<2>(p, k));
-  VMK_TRY(launch_kt<KTSolve>(p, k));
-  t.done();
+  VMK_TRY(timed(KI_KT3, [&] { return launch_kt<KTSolve>(p, k); }));
+  VMK_TRY(be_stream_wait(p->st, p->ev_join));  // K3 reads the rows kx < K0 from L
   {
     K3Args a;
+    a.L = p->tri_L;
+    a.k0 = k0;
+    a.jbase = p->j0;
     a.T = p->T;
     a.pieces = 0;
     a.prefetch = 0;
@@ -1163,7 +1210,8 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
     a.hi_dst = p->peer_psi[next];
     a.NJ = p->NJ;
     a.npairs = p->NJ / 2;
-    const int work = rowpair_units(p, a.npairs, 1);
+    a.prefetch = p->ops.cluster > 1 ? (cl_prefetch_mask(p) & 4) : 0;
+    const int work = rowpair_units(p, a.npairs, 1) * p->ops.cluster;
     Timed t3(p, KI_K3);
     VMK_TRY(p->ops.k3n(work < p->res_k3 ? work : p->res_k3, a, p->st));
     t3.done();
@@ -1827,11 +1875,12 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
     if ((rc = be_num_sms(&p->sms))) break;
     if ((rc = be_stream_create(p->st))) break;
     if ((rc = be_event_create(p->ev0)) || (rc = be_event_create(p->ev1))) break;
+    // second stream: the copies of the transposes (P > 1) / the FFT-form rows beside the recurrences (vmk_tri.cuh)
+    if ((rc = be_stream_create(p->st_copy)) || (rc = be_event_create(p->ev_join))) break;
+    for (int c = 0; c < 8 && !rc; c++) rc = be_event_create(p->ev_chunk[c]);
+    if (rc) break;
     if (nranks > 1) {
-      if ((rc = be_stream_create(p->st_copy)) || (rc = be_event_create(p->ev_join))) break;
       if ((rc = be_stream_create(p->st_copy2)) || (rc = be_event_create(p->ev_join2))) break;
-      for (int c = 0; c < 8 && !rc; c++) rc = be_event_create(p->ev_chunk[c]);
-      if (rc) break;
     }
     if ((rc = ops.configure(&p->res_k1, &p->res_k2, &p->res_k3))) break;
     if (ops.ks && nranks == 1) {
@@ -2049,6 +2098,9 @@ int vmk_fps(vmk_plan* p, double dx, double dy, const double* f, double* s, doubl
   // wtA is scratch between steps; the source needs no halo rows
   VMK_TRY(be_h2d(p->w[1] + p->N, f + (size_t)p->j0 * p->N, sizeof(double) * (size_t)p->N * p->NJ, p->st));
   VMK_TRY(enqueue_poisson(p, p->w[1], +1.0));
+  // recurrence form: a rank may not start its next solve (whose K1 stores into the peers' L and G) before every
+  // rank has consumed this one's
+  if (tri_on(p)) VMK_TRY(cross_rank_barrier(p));
   VMK_TRY(download_interior(p, p->psi, s));
   return be_sync(p->st);
 }
@@ -2063,6 +2115,7 @@ int vmk_ps_fft(vmk_plan* p, double dx, double dy, const double* f, double* u, do
   VMK_TRY(be_h2d_2d(p->w[1] + N, sizeof(double) * N, f + (size_t)p->j0 * (N + 1), sizeof(double) * (N + 1),
                     sizeof(double) * N, (size_t)p->NJ, p->st));
   VMK_TRY(enqueue_poisson(p, p->w[1], +1.0));
+  if (tri_on(p)) VMK_TRY(cross_rank_barrier(p));
   VMK_TRY(be_d2h(u + (size_t)p->j0 * N, p->psi + N, sizeof(double) * N * p->NJ, p->st));
   return be_sync(p->st);
 }
@@ -2424,9 +2477,25 @@ int vmk_profile_steps(vmk_plan* p, double dx, double dy, double dt, double re, i
   if (!rc) rc = collect_profile(p);
   p->profiling = was;
   VMK_TRY(rc);
-  for (int k = 0; k < KI_COUNT; k++) {
+  for (int k = 0; k < 3; k++) {
+    p->tri_ms[k] = p->prof_ms[KI_KT1 + k];
+    p->tri_n[k] = p->prof_n[KI_KT1 + k];
+    p->prof_ms[KI_K2] += p->prof_ms[KI_KT1 + k];
+    p->prof_n[KI_K2] += p->prof_n[KI_KT1 + k];
+  }
+  for (int k = 0; k < KI_ABI; k++) {
     if (ms) ms[k] = p->prof_ms[k];
     if (launches) launches[k] = p->prof_n[k];
+  }
+  return VMK_OK;
+}
+
+int vmk_profile_tri(vmk_plan* p, double* ms, int64_t* launches) {
+  VMK_GUARD(p);
+  VMK_TRY(check_plan(p));
+  for (int k = 0; k < 3; k++) {
+    if (ms) ms[k] = p->tri_ms[k];
+    if (launches) launches[k] = p->tri_n[k];
   }
   return VMK_OK;
 }
@@ -2436,7 +2505,16 @@ int vmk_profile_read(vmk_plan* p, double* ms, int64_t* launches) {
   VMK_TRY(check_plan(p));
   VMK_TRY(collect_profile(p));
   if (p->child) VMK_TRY(collect_profile(p->child));
-  for (int k = 0; k < KI_COUNT; k++) {
+  for (vmk_plan* q : {p, p->child}) {
+    if (!q) continue;
+    for (int k = KI_KT1; k < KI_COUNT; k++) {
+      q->prof_ms[KI_K2] += q->prof_ms[k];
+      q->prof_n[KI_K2] += q->prof_n[k];
+      q->prof_ms[k] = 0;
+      q->prof_n[k] = 0;
+    }
+  }
+  for (int k = 0; k < KI_ABI; k++) {
     if (ms) ms[k] = p->prof_ms[k] + (p->child ? p->child->prof_ms[k] : 0.0);
     if (launches) launches[k] = p->prof_n[k] + (p->child ? p->child->prof_n[k] : 0);
     p->prof_ms[k] = 0;
@@ -2480,7 +2558,7 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
     p->fuse_small = value != 0;
   } else if (k == "fps_mode") {  // 0: FFT along j (K2); 1: recurrences along j (vmk_tri.cuh); -1: by grid size
     if (value > 0 && !p->tri_tab)
-      return fail(VMK_ESIZE, "the recurrence form needs 32 | rows per rank, N >= 64 and a row that fits one SM");
+      return fail(VMK_ESIZE, "the recurrence form needs 32 | rows per rank and N >= 64");
     p->fps_mode = value < 0 ? -1 : (value != 0);
     drop_graphs(p);
   } else if (k == "tri_k0") {  // rows kx < K0 keep the FFT form (0: N/16, at most 64)

@@ -133,7 +133,9 @@ struct Cl {
 };
 
 // ======================================== K1 (cluster) ==========================================
-template <class C, int Q>
+// NAT (vmk_tri.cuh): CTA r stores its half spectrum to the slots [r N'/2, (r+1) N'/2) of the natural rows X[jl][N/2],
+// slot r N'/2 + t + T i  <->  kx = Q own_half_k(t, i) + r; the rows kx < k0 also go to every rank's L
+template <class C, int Q, bool NAT = false>
 VMK_HD void k1c_body(const Ctx& c, const K1Args& a) {
   using L = Cl<C, Q>;
   using F = Fft<C>;
@@ -212,9 +214,19 @@ VMK_HD void k1c_body(const Ctx& c, const K1Args& a) {
           o0 = mk2(zk.x + zm[i].x, zk.y - zm[i].y);  // 2 X_j[k]   = Z[k] + conj Z[N-k]
           o1 = mk2(zk.y + zm[i].y, zm[i].x - zk.x);  // 2 X_j+1[k] = -i (Z[k] - conj Z[N-k])
         }
-        double2* dst = ((k >= a.k_own0 && k < a.k_own1) ? a.Tloc + (size_t)(k - a.k_own0) * a.NJ
-                                                        : a.S + (size_t)k * a.NJ) + jl;
-        st_stream4(dst, o0, o1);
+        if constexpr (NAT) {
+          double2* xr = a.X + (size_t)jl * (N / 2) + (size_t)c.crank * (NP / 2) + t + T * i;
+          st_stream2(xr, o0);
+          st_stream2(xr + N / 2, o1);
+          if (k < a.k0) {
+            for (int q = 0; q < a.nranks; q++)
+              st_stream4(reinterpret_cast<double2*>(a.Lpeer.p[q]) + (size_t)k * N + a.jbase + jl, o0, o1);
+          }
+        } else {
+          double2* dst = ((k >= a.k_own0 && k < a.k_own1) ? a.Tloc + (size_t)(k - a.k_own0) * a.NJ
+                                                          : a.S + (size_t)k * a.NJ) + jl;
+          st_stream4(dst, o0, o1);
+        }
       });
     }
   }
@@ -360,16 +372,21 @@ VMK_HD void k2c_body(const Ctx& c, const K2Args& a) {
 }
 
 // ======================================== K3 (cluster) ==========================================
-template <class C, int Q, bool PIECES>
+// LAYOUT as in k3_body: 0 rows [kx][NJ], 1 PIECES, 2 natural rows [jl][N/2] in k1c_body's slot order (vmk_tri.cuh)
+template <class C, int Q, int LAYOUT>
 VMK_HD void k3c_body(const Ctx& c, const K3Args& a) {
   using L = Cl<C, Q>;
   using F = Fft<C>;
+  constexpr bool PIECES = LAYOUT == 1, NAT = LAYOUT == 2;
   constexpr int N = L::N, NP = L::NP, E = C::E, T = C::T, P = C::P, NI = L::NI, EQ = L::EQ;
+  constexpr int bl = L::bl, hl = L::hl;
   double2* tw = F::tables(c.smem);
   F::load_tables(c, tw, a.tw);
   c.sync();
   const double2* ctw = a.tw + C::TWN;
   const int g = c.tid / T, t = c.tid % T;
+  // position (last-pass layout) of the value a thread loads for its i-th half-spectrum register
+  auto load_pos = [&](int i) { return NAT ? (((t + T * (i / hl)) << bl) | (i % hl)) : halfspec_pos<C>(t + T * i); };
   double2* sm = F::xbuf(c.smem, g);
   double2* rsm[Q];
   L::remote_bases(c, sm, rsm);
@@ -384,6 +401,13 @@ VMK_HD void k3c_body(const Ctx& c, const K3Args& a) {
       if (a.prefetch && t == 0 && pair + ncl * C::FPC < a.npairs)
         prefetch_l2_bulk(a.T + (size_t)(pair + ncl * C::FPC) * N + (size_t)c.crank * NP, (unsigned)(NP * sizeof(double2)));
     }
+    if constexpr (NAT) {  // ... two contiguous 8 N' byte runs (rows jl and jl + 1)
+      if (a.prefetch && t == 0 && pair + ncl * C::FPC < a.npairs) {
+        const double2* nx = a.T + (size_t)(pair + ncl * C::FPC) * N + (size_t)c.crank * (NP / 2);
+        prefetch_l2_bulk(nx, (unsigned)(NP / 2 * sizeof(double2)));
+        prefetch_l2_bulk(nx + N / 2, (unsigned)(NP / 2 * sizeof(double2)));
+      }
+    }
     double2 v[E];
     {
       // the pieces (U[k][j], U[k][j+1]) of this CTA's k = Q k' + r, k' < N'/2
@@ -391,19 +415,28 @@ VMK_HD void k3c_body(const Ctx& c, const K3Args& a) {
       static_for<0, NI>([&](auto i_) {
         constexpr int i = decltype(i_)::value;
         const int idx = t + T * i;
-        const double2* src = PIECES ? a.T + (size_t)pair * N + 2 * ((size_t)c.crank * (NP / 2) + idx)
-                                    : a.T + (size_t)(Q * F::k_of_pos(halfspec_pos<C>(idx)) + c.crank) * a.NJ + jl;
-        if (active) {
-          ld_stream4(src, ua[i], ub[i]);
+        if constexpr (NAT) {
+          const int kk = Q * F::k_of_pos(load_pos(i)) + c.crank;
+          const bool low = kk < a.k0;
+          const double2* src = low ? a.L + (size_t)kk * N + a.jbase + jl
+                                   : a.T + (size_t)jl * (N / 2) + (size_t)c.crank * (NP / 2) + idx;
+          ua[i] = active ? ld_stream2(src) : mk2(0.0, 0.0);
+          ub[i] = active ? ld_stream2(src + (low ? 1 : N / 2)) : mk2(0.0, 0.0);
         } else {
-          ua[i] = ub[i] = mk2(0.0, 0.0);
+          const double2* src = PIECES ? a.T + (size_t)pair * N + 2 * ((size_t)c.crank * (NP / 2) + idx)
+                                      : a.T + (size_t)(Q * F::k_of_pos(halfspec_pos<C>(idx)) + c.crank) * a.NJ + jl;
+          if (active) {
+            ld_stream4(src, ua[i], ub[i]);
+          } else {
+            ua[i] = ub[i] = mk2(0.0, 0.0);
+          }
         }
       });
       c.cluster_sync_relaxed();  // the previous pair's gather_inverse has read every buffer (values consumed)
       // Z = U_j + i U_j+1: Z[k] into the own buffer, Z[N-k] (from the conjugates) into the partner's
       static_for<0, NI>([&](auto i_) {
         constexpr int i = decltype(i_)::value;
-        const int pos = halfspec_pos<C>(t + T * i);
+        const int pos = load_pos(i);
         const int kp = F::k_of_pos(pos);
         if (c.crank == 0 && kp == 0) {
           sm[F::addr(0)] = mk2(ua[i].x, ub[i].x);                    // Z[0]   = u0_j + i u0_j+1

@@ -61,7 +61,9 @@ struct K1Args {
   int npairs;         // row pairs handled by this launch (w, S and Tloc are offset to its first pair)
   int k_own0, k_own1; // spectrum rows [k_own0, k_own1) are owned by this rank
   int prefetch;       // 0 off, 1: bulk L2 prefetch of the rows of the pair after next
-  double2* X;         // NAT: spectrum rows [jl][N/2] in slot order (vmk_tri.cuh), offset to the launch's first row
+  double2* X = nullptr;  // NAT: spectrum rows [jl][N/2] in slot order (vmk_tri.cuh), offset to the launch's first row
+  PeerPtrs Lpeer = {};   // NAT: every rank's L[kx][j] (the rows kx < k0 keep the FFT form along j: K2 solves them there)
+  int k0 = 0, jbase = 0, nranks = 1;  // NAT: rows kx < k0 also go to L; global j of the launch's first row; ranks
 };
 
 // Per row pair: rows (already in the exchange buffer, put there asynchronously during the previous pair's store
@@ -178,6 +180,10 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
           double2* xr = a.X + (size_t)jl * (N / 2) + t + T * i;
           st_stream2(xr, o0);
           st_stream2(xr + N / 2, o1);
+          if (k < a.k0) {
+            for (int q = 0; q < a.nranks; q++)
+              st_stream4(reinterpret_cast<double2*>(a.Lpeer.p[q]) + (size_t)k * N + a.jbase + jl, o0, o1);
+          }
         } else {
           double2* dst = ((k >= a.k_own0 && k < a.k_own1) ? a.Tloc + (size_t)(k - a.k_own0) * a.NJ
                                                           : a.S + (size_t)k * a.NJ) + jl;
@@ -389,6 +395,8 @@ struct K3Args {
   int NJ, npairs;
   int pieces;         // 1: T is laid out [pair][idx][2] (see K2Args::pieces): contiguous, coalesced reads
   int prefetch;       // cluster kernels: bulk L2 prefetch of the next pair's pieces
+  const double2* L = nullptr;  // NAT: the rows kx < k0 are read from L[kx][jbase + jl] (solved there by K2, vmk_tri.cuh)
+  int k0 = 0, jbase = 0;
 };
 
 // LAYOUT of the solution spectrum: 0 = rows [kx][NJ] (32-byte pieces gathered from N/2 rows), 1 = PIECES,
@@ -493,9 +501,12 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
             constexpr int i = b * NH + decltype(i_)::value;
             const int idx = t + T * i;
             if constexpr (NAT) {
-              const double2* src = a.T + (size_t)jl * (N / 2) + idx;
+              // branch-free (a branch per load would serialise the batch): the rows kx < k0 come from L
+              const int kk = F::k_of_pos(((t + T * (i / hl_)) << bl_) | (i % hl_));
+              const bool low = kk < a.k0;
+              const double2* src = low ? a.L + (size_t)kk * N + a.jbase + jl : a.T + (size_t)jl * (N / 2) + idx;
               ua[i - b * NH] = ld_stream2(src);
-              ub[i - b * NH] = ld_stream2(src + N / 2);
+              ub[i - b * NH] = ld_stream2(src + (low ? 1 : N / 2));
             } else {
               const double2* src = PIECES ? a.T + (size_t)pair * N + 2 * idx
                                           : a.T + (size_t)F::k_of_pos(halfspec_pos<C>(idx)) * a.NJ + jl;

@@ -18,18 +18,18 @@
 //   * the FP64 evaluation of the divisor carries ~|aa| 1e-16 of rounding noise, visible where |d| is small; b is taken
 //     as the reference's own FP64 row constant, and the rows kx < K0 (with the packed kx = 0 / N/2 row: e[1,1] = 0,
 //     near-singular kx = eps operator) keep the FFT form with the literal divisor: the slots of those rows are copied
-//     into L[kx][j] by kt_totals_body, solved by k2_body and copied back by kt_solve_body.
+//     into L[kx][j] by k1_body (every rank's L), solved there by k2_body beside the kernels of this file, and read from there by k3_body.
 //
 // Layout: X[jl][s], jl = local row, s = slot in [0, H = N/2): the order in which K1's threads hold the half spectrum
 // (s = t + T i  <->  kx = own_half_k(t, i)); consecutive threads <-> consecutive 16-byte slots in every kernel here.
 //
 //   kt_totals_body   per (chunk of 32 rows, slot): u0 (zero carry-in) in registers -> tp = u0 at the chunk's last row,
-//                    al = sum r^m u0_m, xs = sum x_m; low slots: x -> L of every rank
+//                    al = sum r^m u0_m, xs = sum x_m
 //   kt_scan_body<0>  per slot: the rank's totals (TP, AL, X0) from its chunks' -> G of every rank
 //   [cross-rank barrier]
 //   kt_scan_body<1>  per slot: carries into the rank from all ranks' totals (cyclic closure), then into every chunk
 //   (one rank: kt_scan_body<2> does both in one launch)
-//   kt_solve_body    per (chunk, slot): u, v in registers (in place), scaled, + the eps correction; low slots <- L
+//   kt_solve_body    per (chunk, slot): u, v in registers (in place), scaled, + the eps correction
 #pragma once
 #include "vmk_common.cuh"
 
@@ -48,8 +48,7 @@ struct KTArgs {
   double2* cin;        // [2][nch][H]: carry into the chunk from the left (u) and from the right (v); then [H]: dc
   double2* G;          // [P][3][H]: TP, alpha, X0 of every rank (each rank writes its own block into every rank's G)
   PeerPtrs Gpeer;
-  double2* L;          // [K0][N]: low rows, all j
-  PeerPtrs Lpeer;
+  double2* L;          // [K0][N]: low rows, all j (filled by K1, solved in place by K2)
   int H, NJ, nch, N, j0, rank, nranks;
   double sign;         // +1: solve for f, -1: for -f (Common.jl:134)
 };
@@ -73,14 +72,6 @@ VMK_HD void kt_totals_body(const Ctx& c, const KTArgs& a) {
     double2 x[kTriCH];
 #pragma unroll
     for (int m = 0; m < kTriCH; m++) x[m] = ld_stream2(xp + (size_t)m * a.H);
-    const int lr = ld_roi(a.lowrow + s);
-    if (lr >= 0) {  // a row that keeps the FFT form: its values go to every rank's L (512-byte runs)
-      for (int q = 0; q < a.nranks; q++) {
-        double2* dst = reinterpret_cast<double2*>(a.Lpeer.p[q]) + (size_t)lr * a.N + a.j0 + ch * kTriCH;
-#pragma unroll
-        for (int m = 0; m < kTriCH; m++) st_stream2(dst + m, x[m]);
-      }
-    }
     const double r = ld_ro(a.tab + s);
     double2 xs = mk2(0.0, 0.0), u = mk2(0.0, 0.0);
 #pragma unroll
@@ -266,16 +257,8 @@ VMK_HD void kt_solve_body(const Ctx& c, const KTArgs& a) {
     const int ch = it / tiles, s = (it % tiles) * kTriThreads + c.tid;
     if (s >= a.H) continue;
     double2* xp = a.X + (size_t)ch * kTriCH * a.H + s;
-    const int lr = ld_roi(a.lowrow + s);
+    if (ld_roi(a.lowrow + s) >= 0) continue;  // solved by k2_body in L, where k3_body reads it
     double2 x[kTriCH];
-    if (lr >= 0) {  // solved by k2_body in L
-      const double2* src = a.L + (size_t)lr * a.N + a.j0 + ch * kTriCH;
-#pragma unroll
-      for (int m = 0; m < kTriCH; m++) x[m] = ld_stream2(src + m);
-#pragma unroll
-      for (int m = 0; m < kTriCH; m++) st_stream2(xp + (size_t)m * a.H, x[m]);
-      continue;
-    }
 #pragma unroll
     for (int m = 0; m < kTriCH; m++) x[m] = ld_stream2(xp + (size_t)m * a.H);
     const double r = ld_ro(a.tab + s), kv = ld_ro(a.tab + 6 * a.H + s) * a.sign;

@@ -162,6 +162,10 @@ int vmk_step_elapsed_ms(vmk_plan* plan, double* ms);
  * the launch counts */
 int vmk_profile_steps(vmk_plan* plan, double dx, double dy, double dt, double re, int64_t nsteps, double* ms,
                       int64_t* launches);
+/* after vmk_profile_steps on a plan that solves along j by recurrences (option "fps_mode", csrc/vmk_tri.cuh): the part of
+ * ms[1] / launches[1] spent in ms[0] chunk totals, ms[1] scan, ms[2] in-place solve (the rest of ms[1] is K2 on the rows
+ * kx < K0) */
+int vmk_profile_tri(vmk_plan* plan, double* ms, int64_t* launches);
 /* With the option "profile" set to 1, every kernel of the following calls on this plan (any solver) is bracketed by
  * CUDA events; vmk_profile_read sums them per class since the last read -- ms[0] row-forward transforms (K1), ms[1]
  * spectrum-row kernels (K2, KH, KP, the batched row FFT of the 3/2 rule), ms[2] row-inverse transforms (K3), ms[3]
@@ -174,6 +178,12 @@ int64_t vmk_launch_count(vmk_plan* plan);
  *   "ps32_fuse"   0      3/2 rule: 1 = the four derivative spectra are computed in the load stage of the inverse row
  *                        transform instead of being written and read back; 2 = and folded along i there, so that the
  *                        transform writes K3's input directly (both validated on the host emulator only so far)
+ *   "fps_mode"    -1=auto how fps / vm_rhs / the RK3 step solve along j (Common.jl:117-123): 0 = forward FFT, divide, inverse
+ *                        FFT (K2, with the two all-to-all transposes on several GPUs); 1 = the cyclic tridiagonal solve
+ *                        the divisor is the symbol of, by two-sided recurrences (csrc/vmk_tri.cuh: no transposes; needs
+ *                        32 | rows per rank, N in [64, 8192]); auto = 1 from 1024^2 up.  Same results to ~1e-15
+ *   "tri_k0"      0=auto fps_mode 1: the rows kx < K0 keep the FFT form (0: N/16, at most 64)
+ *   "fuse_small"  0      N <= 256, one GPU: the whole step loop as ONE cluster launch (measured slower than the graph)
  *   "profile"     0      1: bracket every kernel with events (see vmk_profile_read)
  *   "graph"       1      replay the step (kernels, copies, barriers) from a CUDA graph
  *   "k4_rows"     32     rows marched by one K4 thread column (shortened automatically on small slabs)

@@ -93,3 +93,28 @@ def test_spectral_solvers_refuse_cluster_sizes(emul_cl):
             fn(n, n, 1, dx, dy, .01, 1000., x, y, w, 1)
         assert e.value.code == 1 and "8192" in str(e.value)
     emul_cl.clear_plans()
+
+
+# ---- recurrence form of the solve along j (csrc/vmk_tri.cuh) on top of the cluster kernels' natural-layout K1 / K3 ----
+@pytest.mark.parametrize("n,k0", [(64, 0), (128, 3), (256, 0), (512, 0), (1024, 0)])
+def test_cluster_tri_fps(emul_cl, oracle_c, n, k0):
+    emul_cl.clear_plans()
+    p = emul_cl.plan(n, n)
+    p.set_option("fps_mode", 1)
+    p.set_option("tri_k0", k0)
+    pc.check_fps_noise(emul_cl, oracle_c, n, seed=n + 1)
+    emul_cl.clear_plans()
+
+
+@pytest.mark.parametrize("n,nt", [(64, 8), (256, 4), (512, 2)])
+def test_cluster_tri_numerical(emul_cl, oracle_c, n, nt):
+    emul_cl.clear_plans()
+    emul_cl.plan(n, n).set_option("fps_mode", 1)
+    pc.check_rhs(emul_cl, oracle_c, noise_field(n, seed=n + 3))
+    pc.check_numerical(emul_cl, oracle_c, vm_field(n), nt, stable_dt(n, 1000.), 1000.)
+    emul_cl.clear_plans()
+
+
+@pytest.mark.parametrize("n,nranks", [(128, 2), (256, 4), (512, 8)])
+def test_cluster_tri_slab(emul_cl, oracle_c, n, nranks):
+    _slab_run(emul_cl, oracle_c, n, nranks, {"fps_mode": 1})

@@ -97,6 +97,7 @@ def test_cluster_v_layouts_agree(cltest):
     res = []
     for pieces in (1, 0):
         p = cltest.plan(n, n)
+        p.set_option("fps_mode", 0)  # the layouts of V belong to the FFT form of the solve along j
         p.set_option("v_pieces", pieces)
         p.upload(w0)
         p.step(dx, dy, 1e-4, 1000., 2)
@@ -104,7 +105,20 @@ def test_cluster_v_layouts_agree(cltest):
         p.download(wn)
         res.append(wn)
     cltest.plan(n, n).set_option("v_pieces", 1)
+    cltest.plan(n, n).set_option("fps_mode", -1)
     assert rel_l2(res[0], res[1]) < 1e-14
+
+
+@pytest.mark.parametrize("n,mode", [(64, 1), (256, 1), (512, 1), (2048, 0), (8192, 0)])
+def test_cluster_both_forms_along_j(cltest, oracle_c, n, mode):
+    """the form of the solve along j that is NOT the default at this size: recurrences (csrc/vmk_tri.cuh) on top of
+    the cluster kernels' natural-layout K1 / K3 below 1024, K2's FFT pair from 1024 up"""
+    cltest.clear_plans()
+    cltest.plan(n, n).set_option("fps_mode", mode)
+    pc.check_fps_noise(cltest, oracle_c, n, seed=n + 2)
+    if n <= 2048:
+        pc.check_numerical(cltest, oracle_c, vm_field(n), 3, stable_dt(n, 1000.), 1000.)
+    cltest.clear_plans()
 
 
 # ---- the product library at 16384^2 and 32768^2 ----------------------------------------------------------------

@@ -197,6 +197,50 @@ def test_graph_and_plain_launch_agree(gpu):
     gpu.plan(n, n).set_option("graph", 1)
 
 
+# ---- the two forms of the solve along j (option "fps_mode"): K2's FFT pair, and the cyclic tridiagonal solve by
+# two-sided recurrences of csrc/vmk_tri.cuh (the default from 1024^2 up, so the sized tests above already run it) ----
+@pytest.mark.parametrize("n,k0", [(64, 0), (128, 1), (256, 0), (512, 7), (1024, 0), (2048, 64)])
+def test_tri_fps_small_sizes(gpu, oracle_c, n, k0):
+    gpu.clear_plans()
+    p = gpu.plan(n, n)
+    p.set_option("fps_mode", 1)
+    p.set_option("tri_k0", k0)
+    pc.check_fps_noise(gpu, oracle_c, n, seed=n)
+    gpu.clear_plans()
+
+
+@pytest.mark.parametrize("n,nt", [(64, 20), (256, 10), (512, 10)])
+def test_tri_rhs_and_numerical(gpu, oracle_c, n, nt):
+    gpu.clear_plans()
+    gpu.plan(n, n).set_option("fps_mode", 1)
+    pc.check_rhs(gpu, oracle_c, noise_field(n, seed=n + 7))
+    pc.check_numerical(gpu, oracle_c, vm_field(n), nt, stable_dt(n, 1000.), 1000.)
+    gpu.clear_plans()
+
+
+@pytest.mark.parametrize("n", [2048, 8192])
+def test_fft_form_along_j_still_served(gpu, oracle_c, n):
+    """fps_mode 0 (K1 -> K2 -> K3 with the transposed / PIECES layouts) against the oracle, and against fps_mode 1"""
+    gpu.clear_plans()
+    dx, dy, _, _ = grid(n)
+    f = np.asfortranarray(np.random.default_rng(n).uniform(-1, 1, (n, n)))
+    out = []
+    for mode in (0, 1):
+        p = gpu.plan(n, n)
+        p.set_option("fps_mode", mode)
+        s = np.zeros((n + 2, n + 2), order="F")
+        l0 = p.launch_count
+        gpu.fps(n, n, dx, dy, None, None, None, None, f, s)
+        assert p.launch_count - l0 == (6 if mode else 3)
+        out.append(s)
+    ref = np.zeros((n + 2, n + 2), order="F")
+    oracle_c.fps(n, n, dx, dy, f, ref)
+    for s in out:
+        assert rel_l2(s[1:n + 1, 1:n + 1], ref[1:n + 1, 1:n + 1]) < 1e-12
+    assert rel_l2(out[0], out[1]) < 1e-13
+    gpu.clear_plans()
+
+
 # ---- full-size (8192^2) properties: the oracle takes ~6 s per step there, so one step is compared directly
 # and longer runs are checked through size-independent properties ------------------------------------
 def test_full_size_two_steps_vs_oracle(gpu, oracle_c):
