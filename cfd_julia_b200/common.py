@@ -216,17 +216,26 @@ class Common:
         ut = np.zeros((nx + 1, ny + 1), order="F")
         rec = [0]
 
+        failed = []  # an exception cannot cross the C frames of the trampoline: keep the first, re-raise on return
+
         def _snap(k, _ptr, _user):
-            rec[0] += 1
-            if snapshot is not None:
-                snapshot(int(k), ut)
-            if outdir is not None:
-                write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut, lib=self.lib)
+            if failed:
+                return
+            try:
+                rec[0] += 1
+                if snapshot is not None:
+                    snapshot(int(k), ut)
+                if outdir is not None:
+                    write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut, lib=self.lib)
+            except BaseException as ex:  # noqa: BLE001
+                failed.append(ex)
 
         want = snapshot is not None or outdir is not None
         cb = SNAPSHOT_FN(_snap) if want else SNAPSHOT_FN()
         self.lib.check(entry(p.handle, int(nt), dx, dy, dt, re, _ptr(wn, (nx + 2, ny + 2), "wn"), ut.ctypes.data,
                              freq if want else 0, cb, None))
+        if failed:
+            raise failed[0]
         return ut
 
     # ---- 18_NS2D_Lid_Driven_Cavity/lid_driven_cavity.jl:59-117 -----------------------------------
@@ -246,18 +255,27 @@ class Common:
         out = np.zeros((nx + 1, ny + 1), order="F")
         rec = [0]
 
+        failed = []  # see above: the reference would abort at the failing open(); so does this, after the C call
+
         def _snap(k, ptr, _user):
-            rec[0] += 1
-            ut = wn[1:nx + 2, 1:ny + 2]
-            if snapshot is not None:
-                snapshot(int(k), ut)
-            if outdir is not None:
-                write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut, lib=self.lib)
+            if failed:
+                return
+            try:
+                rec[0] += 1
+                ut = wn[1:nx + 2, 1:ny + 2]
+                if snapshot is not None:
+                    snapshot(int(k), ut)
+                if outdir is not None:
+                    write_field(f"{outdir}/vm{rec[0]}.txt", x, y, ut, lib=self.lib)
+            except BaseException as ex:  # noqa: BLE001
+                failed.append(ex)
 
         want = freq > 0 and (snapshot is not None or outdir is not None)
         cb = SNAPSHOT_FN(_snap) if want else SNAPSHOT_FN()
         self.lib.check(self.lib.numerical(p.handle, int(nt), dx, dy, dt, re, _ptr(wn, g, "wn"), out.ctypes.data,
                                           freq if want else 0, cb, None))
+        if failed:
+            raise failed[0]
         return out
 
 

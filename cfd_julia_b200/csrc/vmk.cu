@@ -151,6 +151,9 @@ struct KTScan {
 struct KTSolve {
   VMK_HD static void run(const Ctx& c, const KTArgs& a) { kt_solve_body(c, a); }
 };
+struct KTLow {
+  VMK_HD static void run(const Ctx& c, const KTArgs& a) { kt_low_body(c, a); }
+};
 template <class C>
 struct KSBody {
   VMK_HD static void run(const Ctx& c, const KSArgs& a) { ks_body<C>(c, a); }
@@ -507,7 +510,8 @@ int ilog2_exact(int64_t n) {
 enum { KI_K1 = 0, KI_K2, KI_K3, KI_K4, KI_KT1, KI_KT2, KI_KT3, KI_COUNT };
 constexpr int KI_ABI = 4;
 constexpr int kTriMaxK0 = 64;    // rows kx < K0 keep the FFT form along j (vmk_tri.cuh, tests/models/tri_model.py)
-constexpr int kTriAutoN = 1024;  // smallest grid for which the recurrence form is the default
+constexpr int kTriAutoN = 2048;  // smallest grid for which the recurrence form is the default (measured on one B200:
+                                 // 1024^2 0.104 against 0.099 ms/step, 2048^2 0.279 / 0.289, 4096^2 0.893 / 0.930, 8192^2 3.50 / 3.87)
 
 }  // namespace
 
@@ -596,6 +600,7 @@ struct vmk_plan {
   // solve along j as a cyclic tridiagonal solve by two-sided recurrences (vmk_tri.cuh) instead of K2's FFT pair
   int fps_mode = -1 /* auto: recurrences where the buffers exist and N >= kTriAutoN */, tri_k0 = 0 /* auto */;
   int tri_nch = 0, tri_k0_tab = -1;
+  int zigzag = 0, zz = 0;  // consecutive streaming kernels alternate their row direction (K1Args::rev)
   double* tri_tab = nullptr;   // [kTriTab][N/2]
   int* tri_low = nullptr;      // [N/2]
   double2* tri_tot = nullptr;  // [3][nch][N/2]
@@ -659,12 +664,13 @@ int fill_tri_tables(vmk_plan* p, const double* bbcos, const double* cccos, doubl
   const int H = p->N / 2, k0 = tri_k0(p);
   const double aa = p->div_aa;
   std::vector<double> tab((size_t)kTriTab * H, 0.0);
-  std::vector<int> low(H, -1);
+  std::vector<int> low((size_t)H + kTriMaxK0, -1);  // lowrow[H], then lowslot[K0]
   const L a = (L)cc / 2;
   for (int s = 0; s < H; s++) {
     const int k = p->ops.slot_k(s);
     if (k < k0) {  // keeps the FFT form; neutral constants (its totals are computed but never used)
       low[s] = k;
+      low[(size_t)H + k] = s;
       tab[(size_t)3 * H + s] = 1.0;
       continue;
     }
@@ -1029,6 +1035,7 @@ int make_k4(vmk_plan* p, int win, int wn, int out, const StepParams& sp, K4Args&
   a.NJ = p->NJ;
   a.rows_per_cta = p->k4_rows;
   a.ahead = p->k4_ahead;
+  a.rev = (p->zigzag && tri_on(p)) ? (p->zz++ & 1) : 0;
   a.aa = 1.0 / (sp.re * (sp.dx * sp.dx));  // Common.jl:149
   a.bb = 1.0 / (sp.re * (sp.dy * sp.dy));  // :150
   a.gg = 1.0 / (4.0 * sp.dx * sp.dy);      // :151
@@ -1113,6 +1120,7 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
     a.k0 = k0;
     a.jbase = p->j0;
     a.nranks = P;
+    a.rev = p->zigzag ? (p->zz++ & 1) : 0;
     a.prefetch = p->ops.cluster > 1 ? (cl_prefetch_mask(p) & 1) : p->k1_prefetch;
     const int work = rowpair_units(p, a.npairs, 1) * p->ops.cluster;
     Timed t(p, KI_K1);
@@ -1137,6 +1145,9 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
   k.rank = p->rank;
   k.nranks = P;
   k.sign = sign;
+  k.lowslot = p->tri_low + H;
+  k.k0 = k0;
+  auto next_rev = [&]() { return p->zigzag ? (p->zz++ & 1) : 0; };
   // the rows kx < K0 in L by K2's FFT pair, on the second stream beside the totals / the scan (on the plan's own
   // stream while profiling, so that its events bracket it): L is complete after K1 on one rank, after the barrier on
   // several
@@ -1184,22 +1195,28 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
   };
   if (P == 1) {
     VMK_TRY(low_rows());
+    k.rev = next_rev();
     VMK_TRY(timed(KI_KT1, [&] { return launch_kt<KTTotals>(p, k); }));
     VMK_TRY(timed(KI_KT2, [&] { return launch_kt_scan<2>(p, k); }));
   } else {
+    k.rev = next_rev();
     VMK_TRY(timed(KI_KT1, [&] { return launch_kt<KTTotals>(p, k); }));
     VMK_TRY(timed(KI_KT2, [&] { return launch_kt_scan<0>(p, k); }));
     VMK_TRY(cross_rank_barrier(p));  // every rank's totals and low-row columns have landed
     VMK_TRY(low_rows());
     VMK_TRY(timed(KI_KT2, [&] { return launch_kt_scan<1>(p, k); }));
   }
+  k.rev = next_rev();
   VMK_TRY(timed(KI_KT3, [&] { return launch_kt<KTSolve>(p, k); }));
-  VMK_TRY(be_stream_wait(p->st, p->ev_join));  // K3 reads the rows kx < K0 from L
+  VMK_TRY(be_stream_wait(p->st, p->ev_join));  // the rows kx < K0 are solved: copy them into their slots
+  VMK_TRY(timed(KI_K2, [&] {
+    const int want = (k0 * p->NJ + kTriThreads - 1) / kTriThreads, cap = p->sms * 8;
+    p->launches++;
+    return be_launch<KTLow, KTArgs, kTriThreads, 3>(want < cap ? want : cap, 0, k, p->st);
+  }));
   {
     K3Args a;
-    a.L = p->tri_L;
-    a.k0 = k0;
-    a.jbase = p->j0;
+    a.rev = next_rev();
     a.T = p->T;
     a.pieces = 0;
     a.prefetch = 0;
@@ -1904,7 +1921,7 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
       p->tri_nch = tri ? p->NJ / kTriCH : 0;
       if (tri) {
         if ((rc = dev_alloc(p, (void**)&p->tri_tab, sizeof(double) * kTriTab * H))) break;
-        if ((rc = dev_alloc(p, (void**)&p->tri_low, sizeof(int) * H))) break;
+        if ((rc = dev_alloc(p, (void**)&p->tri_low, sizeof(int) * (H + kTriMaxK0)))) break;  // lowrow[H], lowslot[K0]
         if ((rc = dev_alloc(p, (void**)&p->tri_tot, sizeof(double2) * 3 * p->tri_nch * H))) break;
         if ((rc = dev_alloc(p, (void**)&p->tri_cin, sizeof(double2) * (2 * (size_t)p->tri_nch + 1) * H))) break;
       }
@@ -2102,7 +2119,7 @@ int vmk_fps(vmk_plan* p, double dx, double dy, const double* f, double* s, doubl
   // rank has consumed this one's
   if (tri_on(p)) VMK_TRY(cross_rank_barrier(p));
   VMK_TRY(download_interior(p, p->psi, s));
-  return be_sync(p->st);
+  return sync_and_check(p);  // slab plans: a barrier that timed out is an error, not VMK_OK with stale peer data
 }
 
 int vmk_ps_fft(vmk_plan* p, double dx, double dy, const double* f, double* u, double eps) {
@@ -2117,7 +2134,7 @@ int vmk_ps_fft(vmk_plan* p, double dx, double dy, const double* f, double* u, do
   VMK_TRY(enqueue_poisson(p, p->w[1], +1.0));
   if (tri_on(p)) VMK_TRY(cross_rank_barrier(p));
   VMK_TRY(be_d2h(u + (size_t)p->j0 * N, p->psi + N, sizeof(double) * N * p->NJ, p->st));
-  return be_sync(p->st);
+  return sync_and_check(p);  // slab plans: a barrier that timed out is an error, not VMK_OK with stale peer data
 }
 
 int vmk_rhs(vmk_plan* p, double dx, double dy, double re, const double* w, double* r, double* s, double* f) {
@@ -2138,7 +2155,7 @@ int vmk_rhs(vmk_plan* p, double dx, double dy, double re, const double* w, doubl
   VMK_TRY(launch_k4(p, 0, 1, 1, 2, sp));
   VMK_TRY(download_interior(p, p->w[2], r));
   VMK_TRY(download_ghosted(p, p->psi, s));
-  return be_sync(p->st);
+  return sync_and_check(p);  // slab plans: a barrier that timed out is an error, not VMK_OK with stale peer data
 }
 
 int vmk_upload(vmk_plan* p, const double* wn) {
@@ -2221,6 +2238,7 @@ int vmk_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, doub
   VMK_TRY(check_plan(p));
   if (!wn) return fail(VMK_EARG, "wn is NULL");
   if (nt < 0) return fail(VMK_EARG, "nt < 0");
+  if (out && p->nranks != 1) return fail(VMK_EARG, "out is only produced by single-GPU plans");
   VMK_TRY(vmk_upload(p, wn));
   if (snap && freq > 0) {
     for (int64_t k = 0; k < nt;) {
@@ -2237,7 +2255,6 @@ int vmk_numerical(vmk_plan* p, int64_t nt, double dx, double dy, double dt, doub
   }
   VMK_TRY(vmk_download(p, wn, nullptr));
   if (out) {
-    if (p->nranks != 1) return fail(VMK_EARG, "out is only produced by single-GPU plans");
     // wn[2:nx+2, 2:ny+2] (vm.jl:89): a strided view of the array that was just downloaded
     const size_t ld = (size_t)p->N + 2, n1 = (size_t)p->N + 1;
     for (size_t j = 0; j < n1; j++) memcpy(out + j * n1, wn + (j + 1) * ld + 1, sizeof(double) * n1);
@@ -2560,6 +2577,9 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
     if (value > 0 && !p->tri_tab)
       return fail(VMK_ESIZE, "the recurrence form needs 32 | rows per rank and N >= 64");
     p->fps_mode = value < 0 ? -1 : (value != 0);
+    drop_graphs(p);
+  } else if (k == "zigzag") {  // fps_mode 1: consecutive streaming kernels sweep the rows in alternating directions
+    p->zigzag = value != 0;
     drop_graphs(p);
   } else if (k == "tri_k0") {  // rows kx < K0 keep the FFT form (0: N/16, at most 64)
     if (value < 0 || value > kTriMaxK0) return fail(VMK_EARG, "tri_k0 out of range");

@@ -416,12 +416,9 @@ VMK_HD void k3c_body(const Ctx& c, const K3Args& a) {
         constexpr int i = decltype(i_)::value;
         const int idx = t + T * i;
         if constexpr (NAT) {
-          const int kk = Q * F::k_of_pos(load_pos(i)) + c.crank;
-          const bool low = kk < a.k0;
-          const double2* src = low ? a.L + (size_t)kk * N + a.jbase + jl
-                                   : a.T + (size_t)jl * (N / 2) + (size_t)c.crank * (NP / 2) + idx;
+          const double2* src = a.T + (size_t)jl * (N / 2) + (size_t)c.crank * (NP / 2) + idx;
           ua[i] = active ? ld_stream2(src) : mk2(0.0, 0.0);
-          ub[i] = active ? ld_stream2(src + (low ? 1 : N / 2)) : mk2(0.0, 0.0);
+          ub[i] = active ? ld_stream2(src + N / 2) : mk2(0.0, 0.0);
         } else {
           const double2* src = PIECES ? a.T + (size_t)pair * N + 2 * ((size_t)c.crank * (NP / 2) + idx)
                                       : a.T + (size_t)(Q * F::k_of_pos(halfspec_pos<C>(idx)) + c.crank) * a.NJ + jl;

@@ -64,6 +64,8 @@ struct K1Args {
   double2* X = nullptr;  // NAT: spectrum rows [jl][N/2] in slot order (vmk_tri.cuh), offset to the launch's first row
   PeerPtrs Lpeer = {};   // NAT: every rank's L[kx][j] (the rows kx < k0 keep the FFT form along j: K2 solves them there)
   int k0 = 0, jbase = 0, nranks = 1;  // NAT: rows kx < k0 also go to L; global j of the launch's first row; ranks
+  int rev = 0;  // 1: the row pairs are taken in descending order: consecutive streaming kernels alternate direction, so
+                // each starts on the ~100 MB its predecessor touched last, which are still in the 126 MB L2
 };
 
 // Per row pair: rows (already in the exchange buffer, put there asynchronously during the previous pair's store
@@ -83,9 +85,10 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
   double2* sm = F::xbuf(c.smem, g);
   double* rows = reinterpret_cast<double*>(F::landing(c.smem, g));  // the pair's two rows as [2][N] doubles
   const int nblocks = (a.npairs + C::FPC - 1) / C::FPC;
+  auto blk = [&](int pb) { return a.rev ? nblocks - 1 - pb : pb; };  // iteration index -> block of row pairs
   // the T threads of a transform copy its two rows (contiguous 2N doubles) as N 16-byte chunks
   auto issue_rows = [&](int pb) {
-    const int pair = pb * C::FPC + g;
+    const int pair = blk(pb) * C::FPC + g;
     if (pb < nblocks && pair < a.npairs) {
       const char* src = reinterpret_cast<const char*>(a.w + (size_t)(2 * pair + 1) * N);
       char* dst = reinterpret_cast<char*>(rows);
@@ -99,11 +102,11 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
   issue_rows(c.bid);
   for (int pb = c.bid; pb < nblocks; pb += c.nblk) {
     if (a.prefetch && c.tid == 0 && pb + 2 * c.nblk < nblocks) {
-      const int p0 = (pb + 2 * c.nblk) * C::FPC;
+      const int p0 = blk(pb + 2 * c.nblk) * C::FPC;
       const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
       prefetch_l2_bulk(a.w + (size_t)(2 * p0 + 1) * N, (unsigned)(np * 2 * N * sizeof(double)));
     }
-    const int pair = pb * C::FPC + g;
+    const int pair = blk(pb) * C::FPC + g;
     const bool active = pair < a.npairs;
     const int jl = 2 * pair;
     cp_async_wait_all();
@@ -395,8 +398,7 @@ struct K3Args {
   int NJ, npairs;
   int pieces;         // 1: T is laid out [pair][idx][2] (see K2Args::pieces): contiguous, coalesced reads
   int prefetch;       // cluster kernels: bulk L2 prefetch of the next pair's pieces
-  const double2* L = nullptr;  // NAT: the rows kx < k0 are read from L[kx][jbase + jl] (solved there by K2, vmk_tri.cuh)
-  int k0 = 0, jbase = 0;
+  int rev = 0;        // 1: the row pairs are taken in descending order (see K1Args::rev)
 };
 
 // LAYOUT of the solution spectrum: 0 = rows [kx][NJ] (32-byte pieces gathered from N/2 rows), 1 = PIECES,
@@ -414,12 +416,13 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
   double2* sm = F::xbuf(c.smem, g);
   double2* land = F::landing(c.smem, g);
   const int nblocks = (a.npairs + C::FPC - 1) / C::FPC;
+  auto blk = [&](int pb) { return a.rev ? nblocks - 1 - pb : pb; };  // iteration index -> block of row pairs
   // SPLIT: the 32-byte pieces (U[k][j], U[k][j+1]) of the NEXT pair are gathered asynchronously into the landing
   // buffer (first halves at [idx], second halves at [N/2 + idx]; a thread only touches its own idx = t + T*i) while
   // the current pair is transformed; otherwise the gather is synchronous (the exchange buffer is all there is).
   auto issue_gather = [&](int pb) {
     if constexpr (C::SPLIT) {
-      const int pair = pb * C::FPC + g;
+      const int pair = blk(pb) * C::FPC + g;
       if (pb < nblocks && pair < a.npairs) {
         static_for<0, NI>([&](auto i_) {
           constexpr int i = decltype(i_)::value;
@@ -435,7 +438,7 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
   };
   issue_gather(c.bid);
   for (int pb = c.bid; pb < nblocks; pb += c.nblk) {
-    const int pair = pb * C::FPC + g;
+    const int pair = blk(pb) * C::FPC + g;
     const bool active = pair < a.npairs;
     const int jl = 2 * pair;
     double2 v[E];
@@ -485,7 +488,7 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
         // the pair's N/2 pieces (NAT: its two rows) are one contiguous 16N-byte block in consumption order; the next
         // pair's block is pulled into L2 by a single bulk prefetch while this pair is transformed
         if (c.tid == 0 && pb + c.nblk < nblocks) {
-          const int p0 = (pb + c.nblk) * C::FPC;
+          const int p0 = blk(pb + c.nblk) * C::FPC;
           const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
           prefetch_l2_bulk(a.T + (size_t)p0 * N, (unsigned)(np * N * sizeof(double2)));
         }
@@ -501,12 +504,9 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
             constexpr int i = b * NH + decltype(i_)::value;
             const int idx = t + T * i;
             if constexpr (NAT) {
-              // branch-free (a branch per load would serialise the batch): the rows kx < k0 come from L
-              const int kk = F::k_of_pos(((t + T * (i / hl_)) << bl_) | (i % hl_));
-              const bool low = kk < a.k0;
-              const double2* src = low ? a.L + (size_t)kk * N + a.jbase + jl : a.T + (size_t)jl * (N / 2) + idx;
+              const double2* src = a.T + (size_t)jl * (N / 2) + idx;
               ua[i - b * NH] = ld_stream2(src);
-              ub[i - b * NH] = ld_stream2(src + (low ? 1 : N / 2));
+              ub[i - b * NH] = ld_stream2(src + N / 2);
             } else {
               const double2* src = PIECES ? a.T + (size_t)pair * N + 2 * idx
                                           : a.T + (size_t)F::k_of_pos(halfspec_pos<C>(idx)) * a.NJ + jl;
@@ -562,6 +562,7 @@ struct K4Args {
   double* lo_dst;     // mirror of interior row 0   (previous rank's top halo row of `out`)
   double* hi_dst;     // mirror of interior row NJ-1 (next rank's bottom halo row of `out`)
   int N, log2N, NJ;
+  int rev = 0;        // 1: row blocks in descending order (see K1Args::rev)
   int rows_per_cta;   // rows marched by one thread column
   int ahead;          // rows ahead of the march that are prefetched into L2 (0 = off)
   double aa, bb;      // 1/(re dx^2), 1/(re dy^2)     Common.jl:149-150
@@ -625,7 +626,7 @@ VMK_HD void k4_body(const Ctx& c, const K4Args& a) {
   const int tx = cols < kK4Threads ? cols : kK4Threads;  // threads across i
   const int groups = kK4Threads / tx;                    // row groups per CTA
   const int ctas_x = cols / tx;
-  const int bx = c.bid % ctas_x, by = c.bid / ctas_x;
+  const int bx = c.bid % ctas_x, by = a.rev ? c.nblk / ctas_x - 1 - c.bid / ctas_x : c.bid / ctas_x;
   const int i0 = kK4Cols * (bx * tx + c.tid % tx);
   const int grp = c.tid / tx;
   const int jbeg = (by * groups + grp) * a.rows_per_cta;

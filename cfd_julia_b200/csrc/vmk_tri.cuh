@@ -18,7 +18,8 @@
 //   * the FP64 evaluation of the divisor carries ~|aa| 1e-16 of rounding noise, visible where |d| is small; b is taken
 //     as the reference's own FP64 row constant, and the rows kx < K0 (with the packed kx = 0 / N/2 row: e[1,1] = 0,
 //     near-singular kx = eps operator) keep the FFT form with the literal divisor: the slots of those rows are copied
-//     into L[kx][j] by k1_body (every rank's L), solved there by k2_body beside the kernels of this file, and read from there by k3_body.
+//     into L[kx][j] by k1_body (every rank's L), solved there by k2_body beside the kernels of this file, and copied back by kt_low_body (k3_body with a
+//     per-load choice of the source was 0.05 ms slower at 8192^2).
 //
 // Layout: X[jl][s], jl = local row, s = slot in [0, H = N/2): the order in which K1's threads hold the half spectrum
 // (s = t + T i  <->  kx = own_half_k(t, i)); consecutive threads <-> consecutive 16-byte slots in every kernel here.
@@ -30,6 +31,7 @@
 //   kt_scan_body<1>  per slot: carries into the rank from all ranks' totals (cyclic closure), then into every chunk
 //   (one rank: kt_scan_body<2> does both in one launch)
 //   kt_solve_body    per (chunk, slot): u, v in registers (in place), scaled, + the eps correction
+//   kt_low_body      X[.][slots of kx < K0] <- L
 #pragma once
 #include "vmk_common.cuh"
 
@@ -51,6 +53,9 @@ struct KTArgs {
   double2* L;          // [K0][N]: low rows, all j (filled by K1, solved in place by K2)
   int H, NJ, nch, N, j0, rank, nranks;
   double sign;         // +1: solve for f, -1: for -f (Common.jl:134)
+  int rev = 0;         // 1: totals / solve take the chunks in descending order (see K1Args::rev)
+  const int* lowslot = nullptr;  // [k0]: slot of kx
+  int k0 = 0;
 };
 
 VMK_HD int ld_roi(const int* p) {
@@ -65,7 +70,8 @@ VMK_HD double2 cfma(double2 y, double r, double2 x) { return mk2(fma_(y.x, r, x.
 VMK_HD void kt_totals_body(const Ctx& c, const KTArgs& a) {
   const int tiles = (a.H + kTriThreads - 1) / kTriThreads;
   const int items = a.nch * tiles;
-  for (int it = c.bid; it < items; it += c.nblk) {
+  for (int it0 = c.bid; it0 < items; it0 += c.nblk) {
+    const int it = a.rev ? items - 1 - it0 : it0;
     const int ch = it / tiles, s = (it % tiles) * kTriThreads + c.tid;
     if (s >= a.H) continue;
     const double2* xp = a.X + (size_t)ch * kTriCH * a.H + s;
@@ -253,11 +259,12 @@ VMK_HD void kt_solve_body(const Ctx& c, const KTArgs& a) {
   const int tiles = (a.H + kTriThreads - 1) / kTriThreads;
   const int items = a.nch * tiles;
   const size_t plane = (size_t)a.nch * a.H;
-  for (int it = c.bid; it < items; it += c.nblk) {
+  for (int it0 = c.bid; it0 < items; it0 += c.nblk) {
+    const int it = a.rev ? items - 1 - it0 : it0;
     const int ch = it / tiles, s = (it % tiles) * kTriThreads + c.tid;
     if (s >= a.H) continue;
     double2* xp = a.X + (size_t)ch * kTriCH * a.H + s;
-    if (ld_roi(a.lowrow + s) >= 0) continue;  // solved by k2_body in L, where k3_body reads it
+    if (ld_roi(a.lowrow + s) >= 0) continue;  // solved by k2_body in L and copied back by kt_low_body
     double2 x[kTriCH];
 #pragma unroll
     for (int m = 0; m < kTriCH; m++) x[m] = ld_stream2(xp + (size_t)m * a.H);
@@ -275,6 +282,15 @@ VMK_HD void kt_solve_body(const Ctx& c, const KTArgs& a) {
       y = cfma(y, r, x[m]);
       st_stream2(xp + (size_t)m * a.H, mk2(fma_(y.x, kv, dc.x), fma_(y.y, kv, dc.y)));
     }
+  }
+}
+
+// the rows kx < k0, solved in L by K2: X[jl][slot(kx)] = L[kx][j0 + jl]   (k0 <= 64 slots x NJ rows: megabytes)
+VMK_HD void kt_low_body(const Ctx& c, const KTArgs& a) {
+  const int total = a.k0 * a.NJ;
+  for (int q = c.bid * kTriThreads + c.tid; q < total; q += c.nblk * kTriThreads) {
+    const int k = q / a.NJ, jl = q % a.NJ;  // consecutive threads read consecutive j of one row of L
+    a.X[(size_t)jl * a.H + ld_roi(a.lowslot + k)] = ld_stream2(a.L + (size_t)k * a.N + a.j0 + jl);
   }
 }
 

@@ -49,7 +49,7 @@ def main():
         rows = slice(rank * nj, (rank + 1) * nj + 2)  # this rank's ghosted rows j0 .. j0+NJ+1 (incl. neighbour halos)
         # the solve along j in its default form for this size, and (up to 1024^2) in the other one: 0 = K2's FFT pair with
         # the two all-to-all transposes, 1 = recurrences with three complex numbers per kx and rank (csrc/vmk_tri.cuh)
-        default_mode = 1 if n >= 1024 and (n // world) % 32 == 0 else 0
+        default_mode = 1 if n >= 2048 and (n // world) % 32 == 0 else 0
         modes = [default_mode] + ([1 - default_mode] if n <= 1024 and (n // world) % 32 == 0 else [])
         for mode in modes:
             p = Plan(lib, n, n, rank, world)

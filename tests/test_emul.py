@@ -441,15 +441,15 @@ def test_tri_rhs_and_numerical(emul, oracle_c, n, nt):
 
 
 def test_tri_default_by_size(emul, oracle_c):
-    """the recurrence form is the default from 1024^2 up: 6 launches per Poisson solve instead of 3"""
+    """the recurrence form is the default from 2048^2 up: 7 launches per Poisson solve instead of 3"""
     emul.clear_plans()
-    n = 1024
+    n = 2048
     dx, dy, _, _ = grid(n)
     p = emul.plan(n, n)
     p.upload(vm_field(n))
     l0 = p.launch_count
     p.step(dx, dy, stable_dt(n, 1000.), 1000., 1)
-    assert p.launch_count - l0 == 3 * (6 + 1)
+    assert p.launch_count - l0 == 3 * (7 + 1)
     p.set_option("fps_mode", 0)
     l0 = p.launch_count
     p.step(dx, dy, stable_dt(n, 1000.), 1000., 1)
@@ -463,3 +463,29 @@ def test_tri_default_by_size(emul, oracle_c):
 def test_tri_slab(emul, oracle_c, n, nranks, k0):
     """slab decomposition without transposes: three complex numbers per kx and rank cross the ranks"""
     _slab_run(emul, oracle_c, n, nranks, {"fps_mode": 1, "tri_k0": k0})
+
+
+@pytest.mark.parametrize("n,nt", [(128, 5), (512, 2)])
+def test_tri_zigzag_is_bit_identical(emul, n, nt):
+    """option "zigzag": consecutive streaming kernels sweep the rows in alternating directions (each starts on what
+    its predecessor left in L2); the arithmetic per point does not change"""
+    dx, dy, _, _ = grid(n)
+    w0 = vm_field(n) + 0.1 * noise_field(n, 4)
+    outs = []
+    for zz in (0, 1):
+        emul.clear_plans()
+        p = emul.plan(n, n)
+        p.set_option("fps_mode", 1)
+        p.set_option("zigzag", zz)
+        p.set_option("k4_rows", 8)
+        p.upload(w0)
+        p.step(dx, dy, stable_dt(n, 1000.), 1000., nt)
+        wn, psi = np.zeros_like(w0), np.zeros_like(w0)
+        p.download(wn, psi)
+        outs.append((wn, psi))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    emul.clear_plans()
+
+
+def test_tri_zigzag_slab(emul, oracle_c):
+    _slab_run(emul, oracle_c, 256, 4, {"fps_mode": 1, "zigzag": 1})

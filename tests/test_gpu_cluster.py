@@ -112,7 +112,7 @@ def test_cluster_v_layouts_agree(cltest):
 @pytest.mark.parametrize("n,mode", [(64, 1), (256, 1), (512, 1), (2048, 0), (8192, 0)])
 def test_cluster_both_forms_along_j(cltest, oracle_c, n, mode):
     """the form of the solve along j that is NOT the default at this size: recurrences (csrc/vmk_tri.cuh) on top of
-    the cluster kernels' natural-layout K1 / K3 below 1024, K2's FFT pair from 1024 up"""
+    the cluster kernels' natural-layout K1 / K3 below 2048, K2's FFT pair from 2048 up"""
     cltest.clear_plans()
     cltest.plan(n, n).set_option("fps_mode", mode)
     pc.check_fps_noise(cltest, oracle_c, n, seed=n + 2)

@@ -24,9 +24,10 @@ for n in sizes:
     nt = 2
     wr = w.copy(order="F")
     _, psir = oc.numerical(n, n, nt, dx, dx, dt, 1000., wr)
-    for mode in (0, 1):
+    for mode, zz in ((0, 0), (1, 0), (1, 1)):
         p = vm.plan(n, n)
         p.set_option("fps_mode", mode)
+        p.set_option("zigzag", zz)
         s = np.zeros((n + 2, n + 2), order="F")
         vm.fps(n, n, dx, dx, None, None, None, None, f, s)
         e_fps = rel_l2(s[1:n + 1, 1:n + 1], ref[1:n + 1, 1:n + 1])
@@ -43,5 +44,5 @@ for n in sizes:
         ms = p.step_elapsed_ms() / 20
         prof = p.profile_steps(dx, dx, dt, 1000., 3)
         per = {k: round(v["ms"] / 3, 4) for k, v in prof.items()}
-        print(f"n={n} fps_mode={mode}: fps rel-L2 {e_fps:.2e}  run({nt}) w {e_w:.2e} psi {e_p:.2e}  step {ms:.4f} ms  "
+        print(f"n={n} fps_mode={mode} zigzag={zz}: fps rel-L2 {e_fps:.2e}  run({nt}) w {e_w:.2e} psi {e_p:.2e}  step {ms:.4f} ms  "
               f"per-step class ms {per}", flush=True)
