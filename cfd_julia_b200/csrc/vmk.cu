@@ -106,6 +106,10 @@ struct SizeOps {
   int (*k1n)(int grid, const K1Args&, Stream&);
   int (*k3n)(int grid, const K3Args&, Stream&);
   int (*slot_k)(int s);  // kx held in slot s of a natural-layout spectrum row
+  // fused form (vmk_tri.cuh): the recurrences along j inside K1 / K3; null where it does not apply
+  int (*kf_configure)(int* res);
+  int (*k1f)(int grid, const K1Args&, Stream&);
+  int (*k3f)(int grid, const K3Args&, Stream&);
   // fused device-resident loop for small grids (ks_body): one cluster of `q` CTAs; null where it does not apply
   int (*ks_configure)(int q);
   int (*ks)(int q, const KSArgs&, Stream&);
@@ -140,6 +144,17 @@ struct K3Body {
 template <class C>
 struct K3NBody {
   VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, 2>(c, a); }
+};
+template <class C>
+struct K1FBody {
+  VMK_HD static void run(const Ctx& c, const K1Args& a) { k1_body<C, true, true>(c, a); }
+};
+template <class C>
+struct K3FBody {
+  VMK_HD static void run(const Ctx& c, const K3Args& a) { k3_body<C, 2, true>(c, a); }
+};
+struct KTScanF {
+  VMK_HD static void run(const Ctx& c, const KTArgs& a) { kt_scanf_body<0>(c, a); }
 };
 struct KTTotals {
   VMK_HD static void run(const Ctx& c, const KTArgs& a) { kt_totals_body(c, a); }
@@ -349,6 +364,9 @@ SizeOps make_cluster_ops() {
     constexpr int HP = C::N / 2;  // slots per CTA of the cluster
     return Q * own_half_k<C>((s % HP) % C::T, (s % HP) / C::T) + s / HP;
   };
+  o.kf_configure = nullptr;
+  o.k1f = nullptr;
+  o.k3f = nullptr;
   o.ks_configure = nullptr;
   o.ks = nullptr;
   o.kh_configure = nullptr;
@@ -368,6 +386,9 @@ SizeOps make_cluster_ops() {
 // sizes with a natural-layout K1 / K3 (the recurrence form of the solve along j, vmk_tri.cuh)
 template <class C>
 constexpr bool kTriSize = !C::SPLIT && C::M >= 6;
+// ... and with the fused form (whole warps per transform: the tensor-memory state is addressed per warp)
+template <class C>
+constexpr bool kFusedSize = kTriSize<C> && C::T >= 32;
 
 template <int M>
 SizeOps make_ops() {
@@ -395,6 +416,24 @@ SizeOps make_ops() {
   o.k1n = nullptr;
   o.k3n = nullptr;
   o.slot_k = nullptr;
+  o.kf_configure = nullptr;
+  o.k1f = nullptr;
+  o.k3f = nullptr;
+  if constexpr (kFusedSize<C>) {
+    o.kf_configure = [](int* r) -> int {
+      int r1 = 0, r3 = 0;
+      VMK_TRY((be_configure<K1FBody<C>, K1Args, C::CT, C::MINB>(C::SMEM_BYTES, &r1)));
+      VMK_TRY((be_configure<K3FBody<C>, K3Args, C::CT, C::MINB>(C::SMEM_BYTES, &r3)));
+      *r = r1 < r3 ? r1 : r3;
+      return 0;
+    };
+    o.k1f = [](int grid, const K1Args& a, Stream& s) -> int {
+      return be_launch<K1FBody<C>, K1Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    };
+    o.k3f = [](int grid, const K3Args& a, Stream& s) -> int {
+      return be_launch<K3FBody<C>, K3Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
+    };
+  }
   if constexpr (kTriSize<C>) {
     o.k1n = [](int grid, const K1Args& a, Stream& s) -> int {
       return be_launch<K1Body<C, true>, K1Args, C::CT, C::MINB>(grid, C::SMEM_BYTES, a, s);
@@ -510,6 +549,7 @@ int ilog2_exact(int64_t n) {
 enum { KI_K1 = 0, KI_K2, KI_K3, KI_K4, KI_KT1, KI_KT2, KI_KT3, KI_COUNT };
 constexpr int KI_ABI = 4;
 constexpr int kTriMaxK0 = 64;    // rows kx < K0 keep the FFT form along j (vmk_tri.cuh, tests/models/tri_model.py)
+constexpr int kFusedAutoN = 1 << 30;  // smallest grid for which the fused form is the default (none yet: not measured)
 constexpr int kTriAutoN = 2048;  // smallest grid for which the recurrence form is the default (measured on one B200:
                                  // 1024^2 0.104 against 0.099 ms/step, 2048^2 0.279 / 0.289, 4096^2 0.893 / 0.930, 8192^2 3.50 / 3.87)
 
@@ -601,6 +641,13 @@ struct vmk_plan {
   int fps_mode = -1 /* auto: recurrences where the buffers exist and N >= kTriAutoN */, tri_k0 = 0 /* auto */;
   int tri_nch = 0, tri_k0_tab = -1;
   int zigzag = 0, zz = 0;  // consecutive streaming kernels alternate their row direction (K1Args::rev)
+  // fused form (fps_mode 2): the recurrences inside K1 / K3; fz_grid CTAs = fz_grid * fpc units of row pairs
+  int fz_grid = 0;
+  double fz_kc = 0.0;          // psi = (r fz_kc sign) v + dc: the per-slot scale factor of kt_solve_body, tab[6] = r fz_kc
+  size_t fz_units_cap = 0;     // blocks the totals / carry buffers were sized for
+  bool fz_ok = false;          // tables valid and within the range of the (1/r)^M Horner form
+  double* tri_ftab = nullptr;  // [kTriFTab][N/2]
+  double2* tri_rr = nullptr;   // [N/2]: (r, 1/r)
   double* tri_tab = nullptr;   // [kTriTab][N/2]
   int* tri_low = nullptr;      // [N/2]
   double2* tri_tot = nullptr;  // [3][nch][N/2]
@@ -647,7 +694,12 @@ int ensure_staging(vmk_plan* p) {
 
 bool tri_on(const vmk_plan* p) {
   // (the cavity solver's divisor tables, div_kind 1, have no slot tables: it keeps the FFT form)
-  return p->tri_tab && p->div_kind == 0 && (p->fps_mode == 1 || (p->fps_mode < 0 && p->N >= kTriAutoN));
+  return p->tri_tab && p->div_kind == 0 && (p->fps_mode >= 1 || (p->fps_mode < 0 && p->N >= kTriAutoN));
+}
+// the fused form of the recurrences (one GPU): asked for, or by default where it was measured faster
+bool fz_on(const vmk_plan* p) {
+  return tri_on(p) && p->tri_ftab && p->fz_ok && p->nranks == 1 &&
+         (p->fps_mode == 2 || (p->fps_mode < 0 && p->N >= kFusedAutoN));
 }
 int tri_k0(const vmk_plan* p) {
   const int cap = p->N / 4 < kTriMaxK0 ? p->N / 4 : kTriMaxK0;
@@ -695,6 +747,37 @@ int fill_tri_tables(vmk_plan* p, const double* bbcos, const double* cccos, doubl
   }
   VMK_TRY(be_h2d(p->tri_tab, tab.data(), sizeof(double) * tab.size(), p->st));
   VMK_TRY(be_h2d(p->tri_low, low.data(), sizeof(int) * low.size(), p->st));
+  p->fz_ok = false;
+  if (p->tri_ftab) {
+    // fused form: blocks of 2 Lmin or 2 Lmin + 2 rows (the units of K1 / K3, fz_first)
+    const int units = p->fz_grid * p->ops.fpc, npairs = p->NJ / 2;
+    const int lmin = npairs / units;
+    std::vector<double> ft((size_t)kTriFTab * H, 0.0);
+    std::vector<double2> rr(H);
+    bool ok = true;
+    for (int s = 0; s < H; s++) {
+      rr[s].x = rr[s].y = 0.0;
+      if (low[s] >= 0) continue;  // r = 0: the slot passes through K3's recurrence unchanged
+      const L r = (L)tab[s];      // the rounded r the kernels multiply by
+      rr[s].x = (double)r;
+      rr[s].y = (double)(1 / r);
+      // (1/r)^M and r^M must stay far inside the FP64 range (K1's Horner sum A, K3's q)
+      if ((L)(2 * lmin + 2) * log10l(1 / r) > 200) ok = false;
+      ft[s] = (double)(r / (1 - r * r));
+      for (int cls = 0; cls < 2; cls++) {
+        const int M = 2 * (lmin + cls);
+        if (M == 0) continue;
+        const L R = powl(r, (L)M);
+        ft[(size_t)(1 + 3 * cls) * H + s] = (double)R;
+        ft[(size_t)(2 + 3 * cls) * H + s] = (double)(r * (1 - R * R) / (1 - r * r));
+        ft[(size_t)(3 + 3 * cls) * H + s] = (double)powl(r, (L)(M - 1));
+      }
+    }
+    p->fz_kc = (double)(-1 / ((L)cc * (L)p->N));
+    VMK_TRY(be_h2d(p->tri_ftab, ft.data(), sizeof(double) * ft.size(), p->st));
+    VMK_TRY(be_h2d(p->tri_rr, rr.data(), sizeof(double2) * rr.size(), p->st));
+    p->fz_ok = ok;
+  }
   VMK_TRY(be_sync(p->st));
   p->tri_k0_tab = k0;
   return 0;
@@ -1237,8 +1320,129 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
   return 0;
 }
 
+// The recurrence form with the recurrences INSIDE K1 and K3 (one GPU; vmk_tri.cuh "fused form"): K1 (forward
+// recurrence per unit, block totals) -> scan over the blocks (beside it: the rows kx < K0 by K2, stored straight into
+// their slots) -> K3 (backward recurrence, scaling, eps correction).  The spectrum crosses HBM twice instead of five times.
+int enqueue_poisson_fused(vmk_plan* p, const double* src, double sign) {
+  const int N = p->N, H = N / 2, k0 = p->tri_k0_tab;
+  const int units = p->fz_grid * p->ops.fpc;
+  {
+    K1Args a;
+    a.w = src;
+    a.S = nullptr;
+    a.Tloc = nullptr;
+    a.X = p->T;
+    a.tw = p->tw;
+    a.NJ = p->NJ;
+    a.npairs = p->NJ / 2;
+    a.k_own0 = 0;
+    a.k_own1 = 0;
+    a.prefetch = p->k1_prefetch;
+    for (int r = 0; r < kMaxPeers; r++) a.Lpeer.p[r] = r < 1 ? (void*)p->peer_L[r] : nullptr;
+    a.k0 = k0;
+    a.jbase = 0;
+    a.nranks = 1;
+    a.rr = p->tri_rr;
+    a.tot = p->tri_tot;
+    Timed t(p, KI_K1);
+    VMK_TRY(p->ops.k1f(p->fz_grid, a, p->st));
+    t.done();
+    p->launches++;
+  }
+  KTArgs k;
+  k.X = p->T;
+  k.tab = p->tri_tab;
+  k.lowrow = p->tri_low;
+  k.tot = p->tri_tot;
+  k.cin = p->tri_cin;
+  k.G = p->tri_G;
+  k.L = p->tri_L;
+  for (int r = 0; r < kMaxPeers; r++) k.Gpeer.p[r] = nullptr;
+  k.H = H;
+  k.NJ = p->NJ;
+  k.nch = p->tri_nch;
+  k.N = N;
+  k.j0 = 0;
+  k.rank = 0;
+  k.nranks = 1;
+  k.sign = sign;
+  k.lowslot = p->tri_low + H;
+  k.k0 = k0;
+  k.ftab = p->tri_ftab;
+  k.units = units;
+  k.npairs = p->NJ / 2;
+  {  // the rows kx < K0 in L by K2's FFT pair, on the second stream beside the scan
+    K2Args a;
+    a.T = p->tri_L;
+    a.V = p->tri_L;
+    a.S = nullptr;
+    for (int r = 0; r < kMaxPeers; r++) a.Vpeer.p[r] = nullptr;
+    a.push = 0;
+    a.pieces = 0;
+    a.tw = p->tw;
+    a.bbcos = p->bbcos;
+    a.cccos = p->cccos;
+    a.ccperm = p->ccperm;
+    a.aa = p->div_aa;
+    a.scale = sign / (2.0 * (double)N * (double)N);
+    a.NJ = N;
+    a.log2NJ = p->M;
+    a.nrows = k0;
+    a.row0 = 0;
+    a.R = k0;
+    a.rloc0 = 0;
+    a.rank = 0;
+    a.prefetch = 0;
+    a.Xnat = p->T;
+    a.lowslot = p->tri_low + H;
+    const int work = (k0 + p->ops.fpc - 1) / p->ops.fpc * p->ops.cluster;
+    const int grid = work < p->res_k2 ? work : p->res_k2;
+    p->launches++;
+    if (p->profiling) {
+      Timed t(p, KI_K2);
+      VMK_TRY(p->ops.k2(grid, a, p->st));
+      t.done();
+      VMK_TRY(be_event_record(p->ev_join, p->st));
+    } else {
+      VMK_TRY(be_event_record(p->ev_chunk[0], p->st));
+      VMK_TRY(be_stream_wait(p->st_copy, p->ev_chunk[0]));
+      VMK_TRY(p->ops.k2(grid, a, p->st_copy));
+      VMK_TRY(be_event_record(p->ev_join, p->st_copy));
+    }
+  }
+  {
+    Timed t(p, KI_KT2);
+    const int grid = (H + kTriScanSlots - 1) / kTriScanSlots;
+    VMK_TRY((be_launch<KTScanF, KTArgs, kTriScanThreads, 1>(grid, kTriScanFSmem, k, p->st)));
+    t.done();
+    p->launches++;
+  }
+  VMK_TRY(be_stream_wait(p->st, p->ev_join));  // the rows kx < K0 are solved and back in their slots
+  {
+    K3Args a;
+    a.T = p->T;
+    a.pieces = 0;
+    a.prefetch = 0;
+    a.tw = p->tw;
+    a.psi = p->psi;
+    a.lo_dst = p->peer_psi[0] + (size_t)(p->NJ + 1) * N;
+    a.hi_dst = p->peer_psi[0];
+    a.NJ = p->NJ;
+    a.npairs = p->NJ / 2;
+    a.rr = p->tri_rr;
+    a.cin = p->tri_cin;
+    a.kc = p->fz_kc * sign;
+    Timed t3(p, KI_K3);
+    VMK_TRY(p->ops.k3f(p->fz_grid, a, p->st));
+    t3.done();
+    p->launches++;
+  }
+  return 0;
+}
+
 // psi = solve(sign * src): K1 -> K2 -> K3.  Common.jl:115-123
 int enqueue_poisson(vmk_plan* p, const double* src, double sign) {
+  if (fz_on(p)) return enqueue_poisson_fused(p, src, sign);
   if (tri_on(p)) return enqueue_poisson_tri(p, src, sign);
   VMK_TRY(launch_k1(p, src));
   VMK_TRY(cross_rank_barrier(p));  // every rank's spectrum is written before any rank transforms along j
@@ -1920,10 +2124,24 @@ int vmk_plan_create_slab(int64_t nx, int64_t ny, int rank, int nranks, vmk_plan*
       const size_t H = (size_t)p->N / 2;
       p->tri_nch = tri ? p->NJ / kTriCH : 0;
       if (tri) {
+        // fused form (one GPU): K1 and K3 on the same grid, so that their units own the same blocks of row pairs
+        size_t blocks = (size_t)p->tri_nch;
+        if (ops.kf_configure && nranks == 1) {
+          int res = 0;
+          if ((rc = ops.kf_configure(&res))) break;
+          const int work = rowpair_units(p, p->NJ / 2, 1);
+          p->fz_grid = work < res ? work : res;
+          if ((size_t)p->fz_grid * ops.fpc > (size_t)kTriScanFMaxUnits) p->fz_grid = kTriScanFMaxUnits / ops.fpc;
+          const size_t units = (size_t)p->fz_grid * ops.fpc;
+          if (units > blocks) blocks = units;
+          p->fz_units_cap = blocks;
+          if ((rc = dev_alloc(p, (void**)&p->tri_ftab, sizeof(double) * kTriFTab * H))) break;
+          if ((rc = dev_alloc(p, (void**)&p->tri_rr, sizeof(double2) * H))) break;
+        }
         if ((rc = dev_alloc(p, (void**)&p->tri_tab, sizeof(double) * kTriTab * H))) break;
         if ((rc = dev_alloc(p, (void**)&p->tri_low, sizeof(int) * (H + kTriMaxK0)))) break;  // lowrow[H], lowslot[K0]
-        if ((rc = dev_alloc(p, (void**)&p->tri_tot, sizeof(double2) * 3 * p->tri_nch * H))) break;
-        if ((rc = dev_alloc(p, (void**)&p->tri_cin, sizeof(double2) * (2 * (size_t)p->tri_nch + 1) * H))) break;
+        if ((rc = dev_alloc(p, (void**)&p->tri_tot, sizeof(double2) * 3 * blocks * H))) break;
+        if ((rc = dev_alloc(p, (void**)&p->tri_cin, sizeof(double2) * (2 * blocks + 1) * H))) break;
       }
       if ((rc = dev_alloc(p, (void**)&p->tri_G, tri ? sizeof(double2) * 3 * H * nranks : 16))) break;
       const size_t lrows = H < (size_t)kTriMaxK0 ? H : (size_t)kTriMaxK0;
@@ -1996,6 +2214,8 @@ int vmk_plan_destroy(vmk_plan* p) {
   be_free(p->tri_low);
   be_free(p->tri_tot);
   be_free(p->tri_cin);
+  be_free(p->tri_ftab);
+  be_free(p->tri_rr);
   be_free(p->tri_G);
   be_free(p->tri_L);
   be_free(p->staging);
@@ -2573,10 +2793,21 @@ int vmk_set_option(vmk_plan* p, const char* key, int64_t value) {
     p->use_graph = value != 0;
   } else if (k == "fuse_small") {
     p->fuse_small = value != 0;
-  } else if (k == "fps_mode") {  // 0: FFT along j (K2); 1: recurrences along j (vmk_tri.cuh); -1: by grid size
+  } else if (k == "fps_mode") {  // 0: FFT along j (K2); 1: recurrences along j (vmk_tri.cuh); 2: ... inside K1 / K3
+                                 // (fused form, one GPU); -1: by grid size
     if (value > 0 && !p->tri_tab)
       return fail(VMK_ESIZE, "the recurrence form needs 32 | rows per rank and N >= 64");
-    p->fps_mode = value < 0 ? -1 : (value != 0);
+    if (value == 2 && (!p->tri_ftab || p->nranks != 1))
+      return fail(VMK_ESIZE, "the fused form needs one GPU and N in [512, 8192]");
+    p->fps_mode = value < 0 ? -1 : (value >= 2 ? 2 : (int)value);
+    drop_graphs(p);
+  } else if (k == "fz_grid") {  // fused form: CTAs of K1 / K3 (their units own blocks of row pairs); tuning / tests
+    if (!p->tri_ftab) return fail(VMK_ESIZE, "the fused form needs one GPU and N in [512, 8192]");
+    const int work = rowpair_units(p, p->NJ / 2, 1);
+    if (value < 1 || value > work || (size_t)value * p->ops.fpc > p->fz_units_cap)
+      return fail(VMK_EARG, "fz_grid out of range");
+    p->fz_grid = (int)value;
+    p->div_valid = false;  // the block-length tables follow the grid
     drop_graphs(p);
   } else if (k == "zigzag") {  // fps_mode 1: consecutive streaming kernels sweep the rows in alternating directions
     p->zigzag = value != 0;

@@ -124,6 +124,7 @@ VMK_HD double2 csqr(double2 a) {  // a^2: 4 FP64 instructions
   return mk2(fma_(a.x, a.x, -(a.y * a.y)), t + t);
 }
 VMK_HD double2 cconj(double2 a) { return mk2(a.x, -a.y); }
+VMK_HD double2 cfma(double2 y, double r, double2 x) { return mk2(fma_(y.x, r, x.x), fma_(y.y, r, x.y)); }  // y r + x
 VMK_HD double2 cscale(double2 a, double s) { return mk2(a.x * s, a.y * s); }
 
 // ---- global memory access with cache hints -------------------------------------------------
@@ -150,6 +151,14 @@ VMK_HD double ld_stream1(const double* p) {
 VMK_HD void st_stream2(double2* p, double2 v) {
 #ifdef __CUDA_ARCH__
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+#else
+  *p = v;
+#endif
+}
+// the same store without the "memory" clobber: for buffers the kernel never reads (later loads may be hoisted above it)
+VMK_HD void st_stream2_nc(double2* p, double2 v) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y));
 #else
   *p = v;
 #endif
@@ -214,6 +223,13 @@ VMK_HD double ld_ro(const double* p) {
   return *p;
 #endif
 }
+VMK_HD int ld_roi(const int* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
 VMK_HD double2 ld_ro2(const double2* p) {
 #ifdef __CUDA_ARCH__
   return __ldg(p);
@@ -263,6 +279,162 @@ VMK_HD double rcp_fast(double d) {
   return 1.0 / d;
 #endif
 }
+
+// ---- tensor memory as per-thread state ---------------------------------------------------------------------------------
+// The FP64 kernels have no use for the tensor cores, but the 256 KB of tensor memory next to them (128 lanes x 512
+// 32-bit columns per SM) is storage a thread can reach without the LSU: lane 32 (w % 4) + l belongs to lane l of warp w,
+// so a CTA of 8 warps has 128 doubles per thread of state that survives across loop iterations when the register
+// file is full (the fused forms of K1 / K3 keep the running values of the recurrences along j there, vmk_tri.cuh).
+// tcgen05.ld / .st are warp-wide (.sync.aligned): every call site is reached by whole warps.
+// The state is private to the thread and the instructions are volatile (kept in program order among themselves), so
+// they carry no "memory" clobber: the compiler stays free to move ordinary loads across them.
+// Emulator: a plain per-thread array.
+// columns a CTA of `ct` threads allocates for `nd` doubles per thread (power of two >= 32)
+VMK_HD constexpr int tm_cols(int nd, int ct) {
+  const int need = 2 * nd * ((ct + 127) / 128);
+  int c = 32;
+  while (c < need) c *= 2;
+  return c;
+}
+template <int ND>  // doubles per thread
+struct TmState {
+#ifdef __CUDA_ARCH__
+  unsigned base;  // tensor-memory address of this thread's first column: (lane base << 16) | column
+#else
+  double buf[ND];
+#endif
+  // COLS = columns allocated by the CTA (power of two >= 32, >= 2 ND x warps/4); all threads of the CTA call it
+  template <int COLS>
+  VMK_HD void open(const Ctx& c) {
+#ifdef __CUDA_ARCH__
+    __shared__ unsigned tm_base_slot;
+    if (c.tid < 32) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&tm_base_slot);
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned w = (unsigned)c.tid >> 5;
+    base = tm_base_slot + (((w & 3u) * 32u) << 16) + (w >> 2) * (unsigned)(2 * ND);
+#else
+    (void)c;
+    for (int i = 0; i < ND; i++) buf[i] = 0.0;
+#endif
+  }
+  template <int COLS>
+  VMK_HD void close(const Ctx& c) {
+#ifdef __CUDA_ARCH__
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (c.tid < 32) {
+      const unsigned w0 = base & 0xffffu;  // warp 0: lane base 0, column offset 0
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(w0), "r"(COLS) : "memory");
+    }
+#else
+    (void)c;
+#endif
+  }
+  // two / four / six consecutive doubles at offset OFF (in doubles); load and wait are one asm statement, so the
+  // registers are valid when it returns
+  template <int OFF>
+  VMK_HD void ld2(double& a, double& b) const {
+#ifdef __CUDA_ARCH__
+    unsigned r0, r1, r2, r3;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+        : "r"(base + 2u * OFF));
+    a = __hiloint2double((int)r1, (int)r0);
+    b = __hiloint2double((int)r3, (int)r2);
+#else
+    a = buf[OFF];
+    b = buf[OFF + 1];
+#endif
+  }
+  template <int OFF>
+  VMK_HD void ld4(double& a, double& b, double& d, double& e) const {
+#ifdef __CUDA_ARCH__
+    unsigned r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+        : "r"(base + 2u * OFF));
+    a = __hiloint2double((int)r1, (int)r0);
+    b = __hiloint2double((int)r3, (int)r2);
+    d = __hiloint2double((int)r5, (int)r4);
+    e = __hiloint2double((int)r7, (int)r6);
+#else
+    a = buf[OFF];
+    b = buf[OFF + 1];
+    d = buf[OFF + 2];
+    e = buf[OFF + 3];
+#endif
+  }
+  template <int OFF>
+  VMK_HD void ld6(double& a, double& b, double& d, double& e, double& f, double& g) const {
+#ifdef __CUDA_ARCH__
+    unsigned r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%12];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [%13];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7), "=r"(r8), "=r"(r9),
+          "=r"(r10), "=r"(r11)
+        : "r"(base + 2u * OFF), "r"(base + 2u * OFF + 8u));
+    a = __hiloint2double((int)r1, (int)r0);
+    b = __hiloint2double((int)r3, (int)r2);
+    d = __hiloint2double((int)r5, (int)r4);
+    e = __hiloint2double((int)r7, (int)r6);
+    f = __hiloint2double((int)r9, (int)r8);
+    g = __hiloint2double((int)r11, (int)r10);
+#else
+    a = buf[OFF];
+    b = buf[OFF + 1];
+    d = buf[OFF + 2];
+    e = buf[OFF + 3];
+    f = buf[OFF + 4];
+    g = buf[OFF + 5];
+#endif
+  }
+  template <int OFF>
+  VMK_HD void st2(double a, double b) {
+#ifdef __CUDA_ARCH__
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + 2u * OFF),
+                 "r"(__double2loint(a)), "r"(__double2hiint(a)), "r"(__double2loint(b)), "r"(__double2hiint(b)));
+#else
+    buf[OFF] = a;
+    buf[OFF + 1] = b;
+#endif
+  }
+  template <int OFF>
+  VMK_HD void st4(double a, double b, double d, double e) {
+#ifdef __CUDA_ARCH__
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(base + 2u * OFF),
+                 "r"(__double2loint(a)), "r"(__double2hiint(a)), "r"(__double2loint(b)), "r"(__double2hiint(b)),
+                 "r"(__double2loint(d)), "r"(__double2hiint(d)), "r"(__double2loint(e)), "r"(__double2hiint(e)));
+#else
+    buf[OFF] = a;
+    buf[OFF + 1] = b;
+    buf[OFF + 2] = d;
+    buf[OFF + 3] = e;
+#endif
+  }
+  // stores issued so far are complete (before the same columns are loaded again)
+  VMK_HD void fence_st() const {
+#ifdef __CUDA_ARCH__
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
+  }
+};
+
+// FUSED kernels: unit q = CTA * FPC + transform group owns the contiguous pairs [fz_first(q), fz_first(q + 1)) and
+// takes them in order (K1: ascending, K3: descending), so that the recurrences along j run inside the unit
+VMK_HD int fz_first(int q, int units, int npairs) { return (int)(((long long)q * npairs) / units); }
 
 constexpr int kMaxPeers = 8;
 struct PeerPtrs {

@@ -66,29 +66,43 @@ struct K1Args {
   int k0 = 0, jbase = 0, nranks = 1;  // NAT: rows kx < k0 also go to L; global j of the launch's first row; ranks
   int rev = 0;  // 1: the row pairs are taken in descending order: consecutive streaming kernels alternate direction, so
                 // each starts on the ~100 MB its predecessor touched last, which are still in the 126 MB L2
+  // FUSED (vmk_tri.cuh, "fused form"): the forward recurrence along j runs in K1's epilogue
+  const double2* rr = nullptr;  // [N/2]: (r, 1/r) per slot
+  double2* tot = nullptr;       // [3][units][N/2]: tp, A, S of every unit's block of rows
 };
+
 
 // Per row pair: rows (already in the exchange buffer, put there asynchronously during the previous pair's store
 // phase) -> registers -> forward FFT -> spectrum to shared memory -> Z[k], Z[N-k] to registers -> start the
 // asynchronous copy of the next pair's rows -> unpack and transposed 32-byte stores.
 // NAT: the half spectrum of row jl goes to X[jl][s], slot s = t + T i = the order in which the threads hold it
 // (coalesced 16-byte stores, nothing is transposed); the solve along j is then vmk_tri.cuh's.
-template <class C, bool NAT = false>
+template <class C, bool NAT = false, bool FUSED = false>
 VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
   using F = Fft<C>;
   static_assert(!(NAT && C::SPLIT), "the slot order of the natural layout is the own-half order");
+  static_assert(!FUSED || (NAT && C::T >= 32), "the fused form stores natural rows; its state is per warp");
   constexpr int N = C::N, E = C::E, T = C::T, P = C::P, NI = N / 2 / T;
+  constexpr int TMCOLS = tm_cols(6 * NI, C::CT);
+  TmState<6 * NI> tm;  // FUSED: per slot u (last row's recurrence value), A, S
+  if constexpr (FUSED) tm.template open<TMCOLS>(c);
   double2* tw = F::tables(c.smem);
   F::load_tables(c, tw, a.tw);
   c.sync();
   const int g = c.tid / T, t = c.tid % T;
   double2* sm = F::xbuf(c.smem, g);
   double* rows = reinterpret_cast<double*>(F::landing(c.smem, g));  // the pair's two rows as [2][N] doubles
-  const int nblocks = (a.npairs + C::FPC - 1) / C::FPC;
+  // FUSED: the loop counter pb is the position inside the unit's own block of pairs; otherwise the block of FPC pairs
+  const int units = c.nblk * C::FPC, unit = c.bid * C::FPC + g;
+  const int u_first = FUSED ? fz_first(unit, units, a.npairs) : 0;
+  const int u_len = FUSED ? fz_first(unit + 1, units, a.npairs) - u_first : 0;
+  const int nblocks = FUSED ? (a.npairs + units - 1) / units : (a.npairs + C::FPC - 1) / C::FPC;
+  const int pb_begin = FUSED ? 0 : c.bid, pb_step = FUSED ? 1 : c.nblk;
   auto blk = [&](int pb) { return a.rev ? nblocks - 1 - pb : pb; };  // iteration index -> block of row pairs
+  auto pair_of = [&](int pb) { return FUSED ? (pb < u_len ? u_first + pb : a.npairs) : blk(pb) * C::FPC + g; };
   // the T threads of a transform copy its two rows (contiguous 2N doubles) as N 16-byte chunks
   auto issue_rows = [&](int pb) {
-    const int pair = blk(pb) * C::FPC + g;
+    const int pair = pair_of(pb);
     if (pb < nblocks && pair < a.npairs) {
       const char* src = reinterpret_cast<const char*>(a.w + (size_t)(2 * pair + 1) * N);
       char* dst = reinterpret_cast<char*>(rows);
@@ -99,14 +113,25 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
     }
     cp_async_commit();
   };
-  issue_rows(c.bid);
-  for (int pb = c.bid; pb < nblocks; pb += c.nblk) {
-    if (a.prefetch && c.tid == 0 && pb + 2 * c.nblk < nblocks) {
+  issue_rows(pb_begin);
+  if constexpr (FUSED) {
+    static_for<0, NI>([&](auto i_) {
+      constexpr int i = decltype(i_)::value;
+      tm.template st4<6 * i>(0.0, 0.0, 0.0, 0.0);
+      tm.template st2<6 * i + 4>(0.0, 0.0);
+    });
+    tm.fence_st();
+  }
+  for (int pb = pb_begin; pb < nblocks; pb += pb_step) {
+    if constexpr (FUSED) {
+      if (a.prefetch && t == 0 && pb + 2 < u_len)
+        prefetch_l2_bulk(a.w + (size_t)(2 * (u_first + pb + 2) + 1) * N, (unsigned)(2 * N * sizeof(double)));
+    } else if (a.prefetch && c.tid == 0 && pb + 2 * c.nblk < nblocks) {
       const int p0 = blk(pb + 2 * c.nblk) * C::FPC;
       const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
       prefetch_l2_bulk(a.w + (size_t)(2 * p0 + 1) * N, (unsigned)(np * 2 * N * sizeof(double)));
     }
-    const int pair = blk(pb) * C::FPC + g;
+    const int pair = pair_of(pb);
     const bool active = pair < a.npairs;
     const int jl = 2 * pair;
     cp_async_wait_all();
@@ -124,7 +149,7 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
     c.sync();  // all rows are in registers
     // SPLIT: the landing buffer is a buffer of its own, so the next pair's rows start streaming in right away;
     // otherwise they share the exchange buffer and have to wait until the spectrum has been read back (below)
-    if constexpr (C::SPLIT) issue_rows(pb + c.nblk);
+    if constexpr (C::SPLIT) issue_rows(pb + pb_step);
     F::forward(c, v, sm, tw, t);
     double2 zk[NI], zm[NI];
     if constexpr (C::SPLIT) {
@@ -165,9 +190,47 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
         zm[i] = sm[F::addr(F::pos_of_k(k == 0 ? N / 2 : N - k))];  // k == 0: Z[N/2]
       });
       c.sync();  // the spectrum is in registers: the buffer is free for the next pair's rows
-      issue_rows(pb + c.nblk);
+      issue_rows(pb + pb_step);
     }
-    if (active) {
+    if constexpr (FUSED) {
+      if (active) {
+        // the half spectra of the two rows, in place (zk <- 2 X_j, zm <- 2 X_j+1); the rows kx < k0 also go to L
+        static_for<0, NI>([&](auto i_) {
+          constexpr int i = decltype(i_)::value;
+          const int k = own_half_k<C>(t, i);
+          double2 o0, o1;
+          if (k == 0) {
+            o0 = mk2(2.0 * zk[i].x, 2.0 * zm[i].x);
+            o1 = mk2(2.0 * zk[i].y, 2.0 * zm[i].y);
+          } else {
+            o0 = mk2(zk[i].x + zm[i].x, zk[i].y - zm[i].y);
+            o1 = mk2(zk[i].y + zm[i].y, zm[i].x - zk[i].x);
+          }
+          zk[i] = o0;
+          zm[i] = o1;
+          if (k < a.k0) st_stream4(reinterpret_cast<double2*>(a.Lpeer.p[0]) + (size_t)k * N + a.jbase + jl, o0, o1);
+        });
+        // forward recurrence u_j = x_j + r u_(j-1) from zero at the unit's first row, with the block's totals on the
+        // way: tp = u at its last row, A = sum_m (1/r)^(M-1-m) u_m (Horner; r^(M-1) A = v at its first row when
+        // nothing enters from the right), S = sum_m u_m.  State per slot in tensor memory.
+        static_for<0, NI>([&](auto i_) {
+          constexpr int i = decltype(i_)::value;
+          const double2 rq = ld_ro2(a.rr + t + T * i);
+          double2 u, A, S;
+          tm.template ld6<6 * i>(u.x, u.y, A.x, A.y, S.x, S.y);
+          const double2 u1 = cfma(u, rq.x, zk[i]);
+          const double2 u2 = cfma(u1, rq.x, zm[i]);
+          A = cfma(cfma(A, rq.y, u1), rq.y, u2);
+          S = cadd(S, cadd(u1, u2));
+          double2* xr = a.X + (size_t)jl * (N / 2) + t + T * i;
+          st_stream2_nc(xr, u1);
+          st_stream2_nc(xr + N / 2, u2);
+          tm.template st4<6 * i>(u2.x, u2.y, A.x, A.y);
+          tm.template st2<6 * i + 4>(S.x, S.y);
+        });
+        tm.fence_st();
+      }
+    } else if (active) {
       static_for<0, NI>([&](auto i_) {
         constexpr int i = decltype(i_)::value;
         const int k = C::SPLIT ? F::k_of_pos(halfspec_pos<C>(t + T * i)) : own_half_k<C>(t, i);
@@ -196,6 +259,21 @@ VMK_HD void k1_body(const Ctx& c, const K1Args& a) {
     }
   }
   cp_async_wait_all();
+  if constexpr (FUSED) {
+    if (u_len > 0) {  // the block's totals
+      const size_t plane = (size_t)units * (N / 2);
+      static_for<0, NI>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        double2 u, A, S;
+        tm.template ld6<6 * i>(u.x, u.y, A.x, A.y, S.x, S.y);
+        double2* tp = a.tot + (size_t)unit * (N / 2) + t + T * i;
+        tp[0] = u;
+        tp[plane] = A;
+        tp[2 * plane] = S;
+      });
+    }
+    tm.template close<TMCOLS>(c);
+  }
 }
 
 // ======================================== K2 ====================================================
@@ -220,6 +298,8 @@ struct K2Args {
   int row0, nrows;      // global kx of this launch's first row, rows in this launch
   int R, rloc0, rank;   // spectrum rows per rank, local index of the launch's first row, this rank
   int prefetch;         // 0 off, 1: bulk L2 prefetch of the next row (single rank only)
+  double2* Xnat = nullptr;       // non-null: store row kx as column lowslot[kx] of X[j][N/2] instead of V (vmk_tri.cuh,
+  const int* lowslot = nullptr;  // fused form: the rows kx < K0 solved here go back to their slots)
 };
 
 template <class C, bool PIECES>
@@ -310,17 +390,29 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
         static_for<0, E / rl>([&](auto u_) {
           constexpr int u = decltype(u_)::value;
           const int id = t + T * u;
-          static_for<0, rl>([&](auto p_) {
-            constexpr int p = decltype(p_)::value;
-            const int k = F::k_of_pos((id << bl) | p);
-            const double2 cmv = cm[u * rl + p];
-            const double2 ck = v[u * rl + p];
-            const double cc = ld_ro(a.cccos + k);
-            const double g0 = 0.5 * a.scale * rcp_rn(ab0 + cc), gn = 0.5 * a.scale * rcp_rn(abn + cc);
-            double2 pp = cscale(mk2(ck.x + cmv.x, ck.y - cmv.y), g0);  // A^' = (C + conj Cm)/2 * g
-            const double2 qq = cscale(mk2(ck.y + cmv.y, cmv.x - ck.x), gn);  // B^' = -i(C - conj Cm)/2 * g
-            if (k == 0) pp = mk2(0.0, 0.0);                              // e[1,1] = 0, Common.jl:118
-            v[u * rl + p] = mk2(pp.x - qq.y, pp.y + qq.x);               // A^' + i B^'
+          // the divisor's cc cos(ky) in batches of independent, coalesced loads (ccperm holds cccos in register order):
+          // one load -> two IEEE reciprocals -> next load serialised E L2 latencies on the one CTA that every solve of the
+          // recurrence form waits for (the rows kx < K0)
+          constexpr int CB = rl < 8 ? rl : 8;
+          static_for<0, rl / CB>([&](auto b_) {
+            constexpr int pb0 = decltype(b_)::value * CB;
+            double ccv[CB];
+            static_for<0, CB>([&](auto q_) {
+              constexpr int q = decltype(q_)::value;
+              ccv[q] = ld_ro(a.ccperm + (u * rl + pb0 + q) * T + t);
+            });
+            static_for<0, CB>([&](auto q_) {
+              constexpr int p = pb0 + decltype(q_)::value;
+              const int k = F::k_of_pos((id << bl) | p);
+              const double2 cmv = cm[u * rl + p];
+              const double2 ck = v[u * rl + p];
+              const double cc = ccv[p - pb0];
+              const double g0 = 0.5 * a.scale * rcp_rn(ab0 + cc), gn = 0.5 * a.scale * rcp_rn(abn + cc);
+              double2 pp = cscale(mk2(ck.x + cmv.x, ck.y - cmv.y), g0);  // A^' = (C + conj Cm)/2 * g
+              const double2 qq = cscale(mk2(ck.y + cmv.y, cmv.x - ck.x), gn);  // B^' = -i(C - conj Cm)/2 * g
+              if (k == 0) pp = mk2(0.0, 0.0);                              // e[1,1] = 0, Common.jl:118
+              v[u * rl + p] = mk2(pp.x - qq.y, pp.y + qq.x);               // A^' + i B^'
+            });
           });
         });
       } else {
@@ -372,6 +464,13 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
         if (active)
           st_stream4(a.V + (size_t)(j >> 1) * N + piece, odd ? send : keep, odd ? keep : send);
       });
+    } else if (active && a.Xnat) {
+      // fused form of the recurrences (one GPU): the solved row goes straight to its slot of the natural-layout rows
+      double2* col = a.Xnat + ld_roi(a.lowslot + kx);
+      static_for<0, E>([&](auto e_) {
+        constexpr int e = decltype(e_)::value;
+        st_stream2(col + (size_t)F::template own_pos<e>(t) * (N / 2), v[e]);
+      });
     } else if (active) {
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
@@ -399,24 +498,42 @@ struct K3Args {
   int pieces;         // 1: T is laid out [pair][idx][2] (see K2Args::pieces): contiguous, coalesced reads
   int prefetch;       // cluster kernels: bulk L2 prefetch of the next pair's pieces
   int rev = 0;        // 1: the row pairs are taken in descending order (see K1Args::rev)
+  // FUSED (vmk_tri.cuh, "fused form"): T holds the forward recurrence values; the backward recurrence, the scaling
+  // and the eps correction run in K3's load stage
+  const double2* rr = nullptr;   // [N/2]: (r, 1/r) per slot
+  const double2* cin = nullptr;  // [2][units][N/2]: q at the block's last row, carry from the right; then [N/2]: dc
+  double kc = 0.0;               // scale factor per slot = r kc (slots that keep the FFT form, r = 0, pass through)
 };
 
 // LAYOUT of the solution spectrum: 0 = rows [kx][NJ] (32-byte pieces gathered from N/2 rows), 1 = PIECES,
 // 2 = natural rows [jl][N/2] in K1's slot order (vmk_tri.cuh): two contiguous 8N-byte rows per pair
-template <class C, int LAYOUT>
+template <class C, int LAYOUT, bool FUSED = false>
 VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
   using F = Fft<C>;
   constexpr bool PIECES = LAYOUT == 1, NAT = LAYOUT == 2;
   static_assert(!(NAT && C::SPLIT), "the slot order of the natural layout is the own-half order");
+  static_assert(!FUSED || (NAT && C::T >= 32), "the fused form reads natural rows; its state is per warp");
   constexpr int N = C::N, E = C::E, T = C::T, P = C::P, NI = N / 2 / T;
+  constexpr int TMCOLS = tm_cols(4 * NI, C::CT);
+  TmState<4 * NI> tm;  // FUSED: per slot y (the backward recurrence value of the row above), q (what the carry from the
+                       // left still contributes at the current row)
+  if constexpr (FUSED) tm.template open<TMCOLS>(c);
   double2* tw = F::tables(c.smem);
   F::load_tables(c, tw, a.tw);
   c.sync();
   const int g = c.tid / T, t = c.tid % T;
   double2* sm = F::xbuf(c.smem, g);
   double2* land = F::landing(c.smem, g);
-  const int nblocks = (a.npairs + C::FPC - 1) / C::FPC;
+  // FUSED: the loop counter pb counts DOWN the unit's own block of pairs (see fz_first)
+  const int units = c.nblk * C::FPC, unit = c.bid * C::FPC + g;
+  const int u_first = FUSED ? fz_first(unit, units, a.npairs) : 0;
+  const int u_len = FUSED ? fz_first(unit + 1, units, a.npairs) - u_first : 0;
+  const int nblocks = FUSED ? (a.npairs + units - 1) / units : (a.npairs + C::FPC - 1) / C::FPC;
+  const int pb_begin = FUSED ? 0 : c.bid, pb_step = FUSED ? 1 : c.nblk;
   auto blk = [&](int pb) { return a.rev ? nblocks - 1 - pb : pb; };  // iteration index -> block of row pairs
+  auto pair_of = [&](int pb) {
+    return FUSED ? (pb < u_len ? u_first + u_len - 1 - pb : a.npairs) : blk(pb) * C::FPC + g;
+  };
   // SPLIT: the 32-byte pieces (U[k][j], U[k][j+1]) of the NEXT pair are gathered asynchronously into the landing
   // buffer (first halves at [idx], second halves at [N/2 + idx]; a thread only touches its own idx = t + T*i) while
   // the current pair is transformed; otherwise the gather is synchronous (the exchange buffer is all there is).
@@ -437,8 +554,20 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
     }
   };
   issue_gather(c.bid);
-  for (int pb = c.bid; pb < nblocks; pb += c.nblk) {
-    const int pair = blk(pb) * C::FPC + g;
+  if constexpr (FUSED) {
+    // state at the block's last row, from the scan: y = the carry from the right, q = r^M cu
+    if (u_len > 0) {
+      static_for<0, NI>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        const size_t o = (size_t)unit * (N / 2) + t + T * i;
+        const double2 q = a.cin[o], y = a.cin[(size_t)units * (N / 2) + o];
+        tm.template st4<4 * i>(y.x, y.y, q.x, q.y);
+      });
+      tm.fence_st();
+    }
+  }
+  for (int pb = pb_begin; pb < nblocks; pb += pb_step) {
+    const int pair = pair_of(pb);
     const bool active = pair < a.npairs;
     const int jl = 2 * pair;
     double2 v[E];
@@ -487,7 +616,10 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
       if constexpr (PIECES || NAT) {
         // the pair's N/2 pieces (NAT: its two rows) are one contiguous 16N-byte block in consumption order; the next
         // pair's block is pulled into L2 by a single bulk prefetch while this pair is transformed
-        if (c.tid == 0 && pb + c.nblk < nblocks) {
+        if constexpr (FUSED) {
+          if (t == 0 && pb + 1 < u_len)
+            prefetch_l2_bulk(a.T + (size_t)(pair - 1) * N, (unsigned)(N * sizeof(double2)));
+        } else if (c.tid == 0 && pb + c.nblk < nblocks) {
           const int p0 = blk(pb + c.nblk) * C::FPC;
           const int np = (a.npairs - p0) < C::FPC ? (a.npairs - p0) : C::FPC;
           prefetch_l2_bulk(a.T + (size_t)p0 * N, (unsigned)(np * N * sizeof(double2)));
@@ -513,6 +645,33 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
               ld_stream4(src, ua[i - b * NH], ub[i - b * NH]);
             }
           });
+          if constexpr (FUSED) {
+            // backward recurrence over the unit's block, last row first: with u0 the forward values K1 left (zero
+            // carry into the block) and q_m = r^(m+1) cu what the true carry cu adds at row m,
+            //   v_m = u0_m + q_m + r v_(m+1),   q_(m-1) = q_m / r,   psi_m = kv v_m + dc;
+            // q and v at the block's last row come from the scan (state_init).  Slots that keep the FFT form along j
+            // (r = 0) hold final values already: they pass through.  The constants are loaded together with the rows.
+            double2 rq[NH], dc[NH];
+            static_for<0, NH>([&](auto i_) {
+              constexpr int ii = decltype(i_)::value, i = b * NH + ii;
+              rq[ii] = ld_ro2(a.rr + t + T * i);
+              dc[ii] = ld_stream2(a.cin + 2 * (size_t)units * (N / 2) + t + T * i);
+            });
+            static_for<0, NH>([&](auto i_) {
+              constexpr int ii = decltype(i_)::value, i = b * NH + ii;
+              const double kv = rq[ii].x == 0.0 ? 1.0 : rq[ii].x * a.kc;  // -r sign / (cc N)
+              double2 y, q;
+              tm.template ld4<4 * i>(y.x, y.y, q.x, q.y);
+              const double2 v1 = cfma(y, rq[ii].x, cadd(ub[ii], q));
+              q = cscale(q, rq[ii].y);
+              const double2 v0 = cfma(v1, rq[ii].x, cadd(ua[ii], q));
+              q = cscale(q, rq[ii].y);
+              tm.template st4<4 * i>(v0.x, v0.y, q.x, q.y);
+              ub[ii] = mk2(fma_(v1.x, kv, dc[ii].x), fma_(v1.y, kv, dc[ii].y));
+              ua[ii] = mk2(fma_(v0.x, kv, dc[ii].x), fma_(v0.y, kv, dc[ii].y));
+            });
+            tm.fence_st();
+          }
         }
         if constexpr (b == 0) c.sync();  // the previous pair's last exchange has been read everywhere
         // Z = U_j + i U_j+1 in position order (Z[N-k] from the conjugates), straight into the last-pass layout
@@ -551,6 +710,7 @@ VMK_HD void k3_body(const Ctx& c, const K3Args& a) {
     }
   }
   cp_async_wait_all();
+  if constexpr (FUSED) tm.template close<TMCOLS>(c);
 }
 
 // ======================================== K4 ====================================================

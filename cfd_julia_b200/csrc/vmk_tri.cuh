@@ -39,6 +39,8 @@ namespace vmk {
 
 constexpr int kTriCH = 32;        // rows per register-resident chunk
 constexpr int kTriThreads = 128;  // slots per CTA
+constexpr int kTriFTab = 7;       // fused form, doubles per slot: g0 = r / (1 - r^2), then (R, Gam(R), r^(M-1)) of a block of
+                                  // M = 2 Lmin rows and of a block of M = 2 Lmin + 2 rows, Lmin = npairs / units
 constexpr int kTriTab = 10;       // doubles per slot: r, R = r^CH, RJ = r^NJ, W = 1/(1 - r^N), Gam(R), Gam(RJ), Kv, Qs,
                                   // Rg = R^cpg, Gam(Rg) -- Gam(x) = r (1 - x^2) / (1 - r^2)
 
@@ -56,16 +58,11 @@ struct KTArgs {
   int rev = 0;         // 1: totals / solve take the chunks in descending order (see K1Args::rev)
   const int* lowslot = nullptr;  // [k0]: slot of kx
   int k0 = 0;
+  // fused form (kt_scanf_body): blocks of rows = the units of the fused K1 / K3 (fz_first), two possible lengths
+  const double* ftab = nullptr;  // [kTriFTab][H]
+  int units = 0, npairs = 0;
 };
 
-VMK_HD int ld_roi(const int* p) {
-#ifdef __CUDA_ARCH__
-  return __ldg(p);
-#else
-  return *p;
-#endif
-}
-VMK_HD double2 cfma(double2 y, double r, double2 x) { return mk2(fma_(y.x, r, x.x), fma_(y.y, r, x.y)); }  // y r + x
 
 VMK_HD void kt_totals_body(const Ctx& c, const KTArgs& a) {
   const int tiles = (a.H + kTriThreads - 1) / kTriThreads;
@@ -109,6 +106,8 @@ VMK_HD void kt_totals_body(const Ctx& c, const KTArgs& a) {
 // dependent L2 round trip per chunk took 0.2 ms at 8192^2).
 constexpr int kTriScanSlots = 32, kTriScanGroups = 16, kTriScanThreads = kTriScanSlots * kTriScanGroups;
 constexpr int kTriScanSmem = kTriScanThreads * 5 * (int)sizeof(double2);
+constexpr int kTriScanFMaxUnits = 3072;  // blocks of row pairs kt_scanf_body keeps the lengths of
+constexpr int kTriScanFSmem = kTriScanThreads * 4 * (int)sizeof(double2) + kTriScanFMaxUnits * (int)sizeof(int);
 
 VMK_HD int tri_scan_groups(int nch) { return nch >= 8 * kTriScanGroups ? kTriScanGroups : (nch >= 8 ? nch / 8 : 1); }
 
@@ -249,6 +248,144 @@ VMK_HD void kt_scan_body(const Ctx& c, const KTArgs& a) {
         if (cl >= 0) {
           a.cin[plane + (size_t)(ch0 + cl) * H + s] = cv;
           cv = cfma(cv, R, cfma(cuv[i], gam, t1[i]));
+        }
+      }
+    }
+  }
+}
+
+// ---- the fused form: K1 runs the forward recurrence, K3 the backward one (vmk_kernels.cuh, FUSED) ---------------------
+// The spectrum then crosses HBM twice per solve (K1's store, K3's load) instead of five times.  K1's unit q (a CTA's
+// transform group) owns a contiguous block of row pairs, starts the forward recurrence from zero at its first row and
+// leaves, per slot, tp = u at the block's last row, A = sum_m (1/r)^(M-1-m) u_m (so al = r^(M-1) A) and S = sum_m u_m
+// (the block's sum of x is (1 - r) S + r tp).  This kernel is kt_scan_body<2> for those blocks: the same two-line
+// composition, with R and Gam per block (two possible lengths) from tables and per group of blocks on the fly
+// (Gam(R) = g0 (1 - R^2)).  It leaves what K3's unit starts from at the block's LAST row:
+//   cin[0][q] = r^M cu_q (what the carry from the left still adds there),  cin[1][q] = cv_q,  cin[2] = dc.
+template <int DUMMY = 0>
+VMK_HD void kt_scanf_body(const Ctx& c, const KTArgs& a) {
+  const int H = a.H, U = a.units;
+  const int cpg = (U + kTriScanGroups - 1) / kTriScanGroups;
+  const int lx = c.tid % kTriScanSlots, g = c.tid / kTriScanSlots;
+  const int s = c.bid * kTriScanSlots + lx;
+  const bool on = s < H;
+  // [4][groups][slots]: tp, al, xs -> cu, (Rg, -), with cv taking tp's place on the way down; then the blocks' lengths
+  double2* sm = reinterpret_cast<double2*>(c.smem);
+  int* lens = reinterpret_cast<int*>(sm + 4 * kTriScanThreads);
+  auto at = [&](int q, int gg) -> double2& { return sm[(q * kTriScanGroups + gg) * kTriScanSlots + lx]; };
+  const size_t plane = (size_t)U * H;
+  const int lmin = a.npairs / U;
+  for (int q = c.tid; q < U; q += kTriScanThreads) lens[q] = fz_first(q + 1, U, a.npairs) - fz_first(q, U, a.npairs);
+  c.sync();
+  const double r = on ? ld_ro(a.tab + s) : 0.0, g0 = on ? ld_ro(a.ftab + s) : 0.0;
+  const double Ra = on ? ld_ro(a.ftab + H + s) : 0.0, Ga = on ? ld_ro(a.ftab + 2 * H + s) : 0.0;
+  const double Pa = on ? ld_ro(a.ftab + 3 * H + s) : 0.0;
+  const double Rb = on ? ld_ro(a.ftab + 4 * H + s) : 0.0, Gb = on ? ld_ro(a.ftab + 5 * H + s) : 0.0;
+  const double Pb = on ? ld_ro(a.ftab + 6 * H + s) : 0.0;
+  const int ch0 = g * cpg, ch1 = ch0 + cpg < U ? ch0 + cpg : U;
+  // upwards: the group's (tp, al, xs) and R
+  {
+    double2 lp = mk2(0.0, 0.0), al = mk2(0.0, 0.0), xs = mk2(0.0, 0.0);
+    double rp = 1.0;
+    if (on) {
+      for (int b0 = ch0; b0 < ch1; b0 += 8) {
+        double2 t0[8], t1[8], t2[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (b0 + i < ch1 && lens[b0 + i] > 0) {
+            const double2* t = a.tot + (size_t)(b0 + i) * H + s;
+            t0[i] = t[0];
+            t1[i] = t[plane];
+            t2[i] = t[2 * plane];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (b0 + i < ch1 && lens[b0 + i] > 0) {
+            const bool lg = lens[b0 + i] > lmin;
+            const double R = lg ? Rb : Ra, gam = lg ? Gb : Ga, pw = lg ? Pb : Pa;
+            const double2 z = cfma(lp, gam, cscale(t1[i], pw));
+            al = mk2(fma_(z.x, rp, al.x), fma_(z.y, rp, al.y));
+            rp *= R;
+            lp = cfma(lp, R, t0[i]);
+            // the block's sum of x = (1 - r) S + r tp
+            xs = mk2(xs.x + fma_(t2[i].x, 1.0 - r, r * t0[i].x), xs.y + fma_(t2[i].y, 1.0 - r, r * t0[i].y));
+          }
+        }
+      }
+    }
+    at(0, g) = lp;
+    at(1, g) = al;
+    at(2, g) = xs;
+    at(3, g) = mk2(rp, 0.0);
+  }
+  c.sync();
+  if (on && g == 0) {
+    double2 lp = mk2(0.0, 0.0), al = mk2(0.0, 0.0), xs = mk2(0.0, 0.0);
+    double rp = 1.0;
+    for (int gg = 0; gg < kTriScanGroups; gg++) {
+      const double Rg = at(3, gg).x, Gg = g0 * (1.0 - Rg * Rg);
+      const double2 z = cfma(lp, Gg, at(1, gg));
+      al = mk2(fma_(z.x, rp, al.x), fma_(z.y, rp, al.y));
+      rp *= Rg;
+      lp = cfma(lp, Rg, at(0, gg));
+      xs = cadd(xs, at(2, gg));
+    }
+    // cyclic closure over the whole domain (one rank: NJ = N): W = 1 / (1 - r^N), GJ = Gam(r^N)
+    const double W = ld_ro(a.tab + 3 * H + s), GJ = ld_ro(a.tab + 5 * H + s), qs = ld_ro(a.tab + 7 * H + s) * a.sign;
+    const double2 cu_own = cscale(lp, W);
+    const double2 cv = cscale(cfma(cu_own, GJ, al), W);
+    a.cin[2 * plane + s] = mk2(xs.x * qs, xs.y * qs);  // the eps correction, already scaled and signed
+    double2 acc = cu_own;
+    for (int gg = 0; gg < kTriScanGroups; gg++) {  // carry from the left into every group (takes xs's place)
+      const double Rg = at(3, gg).x;
+      at(2, gg) = acc;
+      acc = cfma(acc, Rg, at(0, gg));
+    }
+    acc = cv;
+    for (int gg = kTriScanGroups - 1; gg >= 0; gg--) {  // carry from the right (takes tp's place)
+      const double Rg = at(3, gg).x, Gg = g0 * (1.0 - Rg * Rg);
+      const double2 cug = at(2, gg);
+      at(0, gg) = acc;
+      acc = cfma(acc, Rg, cfma(cug, Gg, at(1, gg)));
+    }
+  }
+  c.sync();
+  if (on) {
+    // carries into the group's blocks: u carries ascending, then v carries descending
+    double2 cu = at(2, g), cv = at(0, g);
+    for (int b0 = ch0; b0 < ch1; b0 += 8) {
+      double2 t0[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (b0 + i < ch1 && lens[b0 + i] > 0) t0[i] = a.tot[(size_t)(b0 + i) * H + s];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (b0 + i < ch1) {
+          a.cin[(size_t)(b0 + i) * H + s] = cu;
+          if (lens[b0 + i] > 0) cu = cfma(cu, lens[b0 + i] > lmin ? Rb : Ra, t0[i]);
+        }
+      }
+    }
+    for (int b0 = ch1; b0 > ch0; b0 -= 8) {
+      double2 t1[8], cuv[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int q = b0 - 1 - i;
+        if (q >= ch0) {
+          cuv[i] = a.cin[(size_t)q * H + s];
+          if (lens[q] > 0) t1[i] = a.tot[plane + (size_t)q * H + s];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int q = b0 - 1 - i;
+        if (q >= ch0) {
+          const bool lg = lens[q] > lmin;
+          const double R = lg ? Rb : Ra, gam = lg ? Gb : Ga, pw = lg ? Pb : Pa;
+          a.cin[plane + (size_t)q * H + s] = cv;
+          a.cin[(size_t)q * H + s] = cscale(cuv[i], R);  // q at the block's last row: r^M cu
+          if (lens[q] > 0) cv = cfma(cv, R, cfma(cuv[i], gam, cscale(t1[i], pw)));
         }
       }
     }

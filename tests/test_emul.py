@@ -489,3 +489,40 @@ def test_tri_zigzag_is_bit_identical(emul, n, nt):
 
 def test_tri_zigzag_slab(emul, oracle_c):
     _slab_run(emul, oracle_c, 256, 4, {"fps_mode": 1, "zigzag": 1})
+
+
+# ---- the fused form of the recurrences (fps_mode 2): forward recurrence in K1's epilogue, backward in K3's load stage,
+# per-slot state in tensor memory on the GPU (a per-thread array here) ----
+@pytest.mark.parametrize("n,k0,grid_ctas", [(512, 0, 0), (512, 3, 5), (1024, 0, 0), (1024, 64, 7), (2048, 0, 0)])
+def test_fused_fps(emul, oracle_c, n, k0, grid_ctas):
+    """fps with fps_mode = 2 against the oracle's FFT x FFT; grid_ctas != 0: ragged blocks of row pairs per unit"""
+    emul.clear_plans()
+    p = emul.plan(n, n)
+    p.set_option("fps_mode", 2)
+    p.set_option("tri_k0", k0)
+    if grid_ctas:
+        p.set_option("fz_grid", grid_ctas)
+    l0 = p.launch_count
+    pc.check_fps_noise(emul, oracle_c, n, seed=n + 1)
+    assert p.launch_count - l0 == 4  # K1, K2 on the rows kx < K0, scan, K3
+    emul.clear_plans()
+
+
+@pytest.mark.parametrize("n,nt,grid_ctas", [(512, 3, 0), (512, 2, 3), (1024, 2, 0)])
+def test_fused_rhs_and_numerical(emul, oracle_c, n, nt, grid_ctas):
+    emul.clear_plans()
+    p = emul.plan(n, n)
+    p.set_option("fps_mode", 2)
+    if grid_ctas:
+        p.set_option("fz_grid", grid_ctas)
+    pc.check_rhs(emul, oracle_c, noise_field(n, seed=n + 9))
+    pc.check_numerical(emul, oracle_c, vm_field(n), nt, stable_dt(n, 1000.), 1000.)
+    emul.clear_plans()
+
+
+def test_fused_form_refused_where_it_does_not_apply(emul):
+    emul.clear_plans()
+    p = emul.plan(256, 256)  # fewer than 32 threads per transform: the per-warp state does not apply
+    with pytest.raises(Exception):
+        p.set_option("fps_mode", 2)
+    emul.clear_plans()
