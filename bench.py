@@ -215,7 +215,7 @@ def workload_config(n, dt):
                            "(BASELINE configs[4])" if n == 32768 else "(not the headline size)")}
 
 
-def parity_probe(lib, Plan, n, world, rank, gather, steps=3):
+def parity_probe(lib, Plan, n, world, rank, gather, steps=3, fps_mode=None):
     """Outside the timed region: `steps` RK3 steps of an n x n vortex merger on the SAME rank layout as the benchmark,
     compared with the C oracle on every rank's slab -- so that the scaling runs carry multi-GPU correctness."""
     from oracle import oracle_c as oc
@@ -226,6 +226,8 @@ def parity_probe(lib, Plan, n, world, rank, gather, steps=3):
     plan = Plan(lib, n, n, rank, world)
     if world > 1:
         plan.attach_peers(gather)
+    if fps_mode is not None:
+        plan.set_option("fps_mode", fps_mode)
     plan.upload(w0)
     plan.step(dx, dx, dt, RE, steps)
     plan.sync()
@@ -341,8 +343,10 @@ def main():
     pts = float(n) * (n // world)
     kern = {}
     tri = plan.profile_tri()
-    fps_mode = "recurrences along j (csrc/vmk_tri.cuh)" if tri["kt_solve"]["launches"] else "FFT along j (K2)"
-    if tri["kt_solve"]["launches"]:
+    fused = tri["kt_scan"]["launches"] and not tri["kt_solve"]["launches"]
+    fps_mode = ("recurrences along j inside K1 / K3, per-slot state in tensor memory (csrc/vmk_tri.cuh, fused form)" if fused
+                else "recurrences along j (csrc/vmk_tri.cuh)" if tri["kt_solve"]["launches"] else "FFT along j (K2)")
+    if tri["kt_scan"]["launches"]:
         # the "k2" class of the recurrence form = chunk totals (reads the spectrum: 8 B/point) + scan (chunk totals and
         # carries: 80 B per 32 points) + in-place solve (16 B/point) + K2 on the rows kx < K0 (beside them, on a
         # second stream; timed in line here): list the three streaming kernels separately
@@ -350,12 +354,15 @@ def main():
         nlow = prof["k2"]["launches"] - sum(v["launches"] for v in tri.values())
         prof = dict(prof)
         prof.pop("k2")
-        prof.update(tri)
+        prof.update({k: v for k, v in tri.items() if v["launches"]})
         prof["k2_low_rows"] = {"ms": rest, "launches": nlow}
     for k, v in prof.items():
         if v["launches"]:
             dur = v["ms"] / v["launches"]
-            ach = KERNEL_BYTES[k] * pts / (dur * 1e-3) / 1e9
+            kb = KERNEL_BYTES[k]
+            if fused and k == "kt_scan":  # 3 complex totals read, 2 carries written per block of rows (one per CTA) and kx
+                kb = 80.0 * (tri["kt_scan"].get("units") or 148) / (2.0 * n)
+            ach = kb * pts / (dur * 1e-3) / 1e9
             kern[k] = {"ms_per_launch": dur, "achieved_gbs": ach, "frac": ach / peak,
                        "share": v["ms"] / sum(q["ms"] for q in prof.values())}
     top = max(kern, key=lambda k: kern[k]["ms_per_launch"]) if kern else None
@@ -366,7 +373,8 @@ def main():
                 "step": {"achieved": step_gbs, "frac": step_gbs / peak, "frac_of_8TBs": step_gbs / 8000.,
                          "bytes_per_point_step": BYTES_PER_POINT_STEP,
                          "bytes_note": "232 = the FFT x FFT formulation's algorithmic traffic (SURVEY 8d), kept as the "
-                                       "common numerator; the recurrence form moves 8 B/point more per solve (256)"}}
+                                       "common numerator; the recurrence form as separate kernels moves 8 B/point more "
+                                       "per solve (256 per step), the fused form 16 B/point less (184 per step)"}}
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this command at 8192^2 on one
     # GPU (profiles/traffic.json, tools/ncu_summary.py); a capture exists for that configuration only
     roofline["kernel_times"] = ("CUDA events around every launch in a separate un-graphed pass (vmk_profile_steps); "
@@ -407,7 +415,10 @@ def main():
             dist.all_gather_object(out, b)
             return out
         pn = min(n, 2048)  # the smallest grid that takes the same default code path as the benchmarked one
-        pplan, parity = parity_probe(lib, Plan, pn, world, rank, _gather2 if dist is not None else None)
+        # (the fused form of the recurrences is the default at 8192^2 on one GPU only: ask for it at the probe's size)
+        pmode = 2 if (world == 1 and pn >= 512 and "fused form" in roofline.get("solve_along_j", "")) else None
+        pplan, parity = parity_probe(lib, Plan, pn, world, rank, _gather2 if dist is not None else None, fps_mode=pmode)
+        parity["solve_along_j"] = roofline.get("solve_along_j")
         if dist is not None:
             t = torch.tensor([parity["rel_l2_w"], parity["rel_l2_psi"]], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -181,7 +181,11 @@ int64_t vmk_launch_count(vmk_plan* plan);
  *   "fps_mode"    -1=auto how fps / vm_rhs / the RK3 step solve along j (Common.jl:117-123): 0 = forward FFT, divide, inverse
  *                        FFT (K2, with the two all-to-all transposes on several GPUs); 1 = the cyclic tridiagonal solve
  *                        the divisor is the symbol of, by two-sided recurrences (csrc/vmk_tri.cuh: no transposes; needs
- *                        32 | rows per rank, N in [64, 8192]); auto = 1 from 2048^2 up.  Same results to ~1e-15
+ *                        32 | rows per rank, N in [64, 8192]); 2 = the same recurrences INSIDE K1 / K3 (fused form, one
+ *                        GPU, N in [512, 8192]: the spectrum crosses HBM twice per solve instead of five times, the
+ *                        per-slot running values live in tensor memory); auto = 1 from 2048^2 up, 2 at 8192^2 on one
+ *                        GPU.  Same results to ~1e-15
+ *   "fz_grid"            fps_mode 2: CTAs of K1 / K3 (each owns contiguous blocks of row pairs); tuning / tests
  *   "tri_k0"      0=auto fps_mode 1: the rows kx < K0 keep the FFT form (0: N/16, at most 64)
  *   "fuse_small"  0      N <= 256, one GPU: the whole step loop as ONE cluster launch (measured slower than the graph)
  *   "profile"     0      1: bracket every kernel with events (see vmk_profile_read)

@@ -241,6 +241,54 @@ def test_fft_form_along_j_still_served(gpu, oracle_c, n):
     gpu.clear_plans()
 
 
+# ---- the fused form of the recurrences (fps_mode 2, one GPU; the default at 8192^2): forward recurrence in K1's
+# epilogue, backward recurrence in K3's load stage, per-slot state in tensor memory (tcgen05.ld / .st) ----
+@pytest.mark.parametrize("n,k0,grid_ctas", [(512, 0, 0), (512, 3, 37), (1024, 0, 0), (1024, 64, 101), (2048, 0, 0),
+                                            (4096, 0, 0), (4096, 16, 123)])
+def test_fused_fps_sizes(gpu, oracle_c, n, k0, grid_ctas):
+    gpu.clear_plans()
+    p = gpu.plan(n, n)
+    p.set_option("fps_mode", 2)
+    p.set_option("tri_k0", k0)
+    if grid_ctas:  # ragged blocks of row pairs per unit
+        p.set_option("fz_grid", grid_ctas)
+    l0 = p.launch_count
+    pc.check_fps_noise(gpu, oracle_c, n, seed=n + 1)
+    assert p.launch_count - l0 == 4  # K1, K2 on the rows kx < K0, scan, K3
+    gpu.clear_plans()
+
+
+@pytest.mark.parametrize("n,nt", [(512, 10), (1024, 5), (2048, 3)])
+def test_fused_rhs_and_numerical(gpu, oracle_c, n, nt):
+    gpu.clear_plans()
+    gpu.plan(n, n).set_option("fps_mode", 2)
+    pc.check_rhs(gpu, oracle_c, noise_field(n, seed=n + 9))
+    pc.check_numerical(gpu, oracle_c, vm_field(n), nt, stable_dt(n, 1000.), 1000.)
+    gpu.clear_plans()
+
+
+def test_fused_is_the_default_at_8192_and_agrees_with_the_other_forms(gpu, oracle_c):
+    n = 8192
+    gpu.clear_plans()
+    dx, dy, _, _ = grid(n)
+    f = np.asfortranarray(np.random.default_rng(n + 3).uniform(-1, 1, (n, n)))
+    out = {}
+    for mode in (-1, 1, 2):
+        p = gpu.plan(n, n)
+        p.set_option("fps_mode", mode)
+        s = np.zeros((n + 2, n + 2), order="F")
+        l0 = p.launch_count
+        gpu.fps(n, n, dx, dy, None, None, None, None, f, s)
+        assert p.launch_count - l0 == (7 if mode == 1 else 4)
+        out[mode] = s
+    ref = np.zeros((n + 2, n + 2), order="F")
+    oracle_c.fps(n, n, dx, dy, f, ref)
+    for s in out.values():
+        assert rel_l2(s[1:n + 1, 1:n + 1], ref[1:n + 1, 1:n + 1]) < 1e-12
+    assert np.array_equal(out[-1], out[2]) and rel_l2(out[1], out[2]) < 1e-13
+    gpu.clear_plans()
+
+
 # ---- full-size (8192^2) properties: the oracle takes ~6 s per step there, so one step is compared directly
 # and longer runs are checked through size-independent properties ------------------------------------
 def test_full_size_two_steps_vs_oracle(gpu, oracle_c):
@@ -303,7 +351,8 @@ def test_bench_contract_line(tmp_path):
         assert k in d, k
     # 3 steps x 3 stages x (K1, K2, K3, K4), or x (K1, totals, scan, K2 on the low rows, solve, copy of the low rows, K3, K4) with the
     # recurrence form of the solve along j (the default from 2048^2 up)
-    per_stage = 8 if d["roofline"]["solve_along_j"].startswith("recurrences") else 4
+    form = d["roofline"]["solve_along_j"]
+    per_stage = 5 if "fused form" in form else 8 if form.startswith("recurrences") else 4
     assert d["value"] > 0 and d["gpu_launches"] == 9 * per_stage and d["dtype"] == "f64" and d["vs_baseline"] is None
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
     rf = d["roofline"]
