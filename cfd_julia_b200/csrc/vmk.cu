@@ -1258,6 +1258,12 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
     a.rloc0 = 0;
     a.rank = 0;
     a.prefetch = 0;
+    if (p->ops.cluster == 1) {  // (the cluster K2 keeps V = L; kt_low_body copies)
+      a.Xnat = p->T;
+      a.lowslot = p->tri_low + H;
+      a.xnat_j0 = p->j0;
+      a.xnat_nj = p->NJ;
+    }
     const int work = (k0 + p->ops.fpc - 1) / p->ops.fpc * p->ops.cluster;
     const int grid = work < p->res_k2 ? work : p->res_k2;
     p->launches++;
@@ -1293,12 +1299,15 @@ int enqueue_poisson_tri(vmk_plan* p, const double* src, double sign) {
   }
   k.rev = next_rev();
   VMK_TRY(timed(KI_KT3, [&] { return launch_kt<KTSolve>(p, k); }));
-  VMK_TRY(be_stream_wait(p->st, p->ev_join));  // the rows kx < K0 are solved: copy them into their slots
-  VMK_TRY(timed(KI_K2, [&] {
-    const int want = (k0 * p->NJ + kTriThreads - 1) / kTriThreads, cap = p->sms * 8;
-    p->launches++;
-    return be_launch<KTLow, KTArgs, kTriThreads, 3>(want < cap ? want : cap, 0, k, p->st);
-  }));
+  VMK_TRY(be_stream_wait(p->st, p->ev_join));  // the rows kx < K0 are solved and (one SM per row: K2 stored them
+                                               // there itself) back in their slots; cluster sizes: copy them
+  if (p->ops.cluster > 1) {
+    VMK_TRY(timed(KI_K2, [&] {
+      const int want = (k0 * p->NJ + kTriThreads - 1) / kTriThreads, cap = p->sms * 8;
+      p->launches++;
+      return be_launch<KTLow, KTArgs, kTriThreads, 3>(want < cap ? want : cap, 0, k, p->st);
+    }));
+  }
   {
     K3Args a;
     a.rev = next_rev();
@@ -1397,6 +1406,8 @@ int enqueue_poisson_fused(vmk_plan* p, const double* src, double sign) {
     a.prefetch = 0;
     a.Xnat = p->T;
     a.lowslot = p->tri_low + H;
+    a.xnat_j0 = 0;
+    a.xnat_nj = N;
     const int work = (k0 + p->ops.fpc - 1) / p->ops.fpc * p->ops.cluster;
     const int grid = work < p->res_k2 ? work : p->res_k2;
     p->launches++;

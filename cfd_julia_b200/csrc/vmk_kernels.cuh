@@ -298,8 +298,9 @@ struct K2Args {
   int row0, nrows;      // global kx of this launch's first row, rows in this launch
   int R, rloc0, rank;   // spectrum rows per rank, local index of the launch's first row, this rank
   int prefetch;         // 0 off, 1: bulk L2 prefetch of the next row (single rank only)
-  double2* Xnat = nullptr;       // non-null: store row kx as column lowslot[kx] of X[j][N/2] instead of V (vmk_tri.cuh,
-  const int* lowslot = nullptr;  // fused form: the rows kx < K0 solved here go back to their slots)
+  double2* Xnat = nullptr;       // non-null: store row kx as column lowslot[kx] of the natural-layout rows X[jl][N/2]
+  const int* lowslot = nullptr;  // instead of V (vmk_tri.cuh: the rows kx < K0 solved here go straight back to their slots);
+  int xnat_j0 = 0, xnat_nj = 0;  // only the columns j0 <= j < j0 + nj (the rank's own rows of X)
 };
 
 template <class C, bool PIECES>
@@ -465,11 +466,12 @@ VMK_HD void k2_body(const Ctx& c, const K2Args& a) {
           st_stream4(a.V + (size_t)(j >> 1) * N + piece, odd ? send : keep, odd ? keep : send);
       });
     } else if (active && a.Xnat) {
-      // fused form of the recurrences (one GPU): the solved row goes straight to its slot of the natural-layout rows
+      // recurrence form: the solved row goes straight to its slot of the natural-layout rows (this rank's columns of it)
       double2* col = a.Xnat + ld_roi(a.lowslot + kx);
       static_for<0, E>([&](auto e_) {
         constexpr int e = decltype(e_)::value;
-        st_stream2(col + (size_t)F::template own_pos<e>(t) * (N / 2), v[e]);
+        const int jl = F::template own_pos<e>(t) - a.xnat_j0;
+        if ((unsigned)jl < (unsigned)a.xnat_nj) st_stream2(col + (size_t)jl * (N / 2), v[e]);
       });
     } else if (active) {
       static_for<0, E>([&](auto e_) {

@@ -68,9 +68,23 @@ vm_rhs(nx, ny, Δx, Δy, re, w::Matrix{Float64}, u, e, data, data1, r::Matrix{Fl
 end
 
 # snapshot trampoline: the C side brings wn to the host and calls back with the step number
+# An exception must not unwind through the C frames of the library (undefined behaviour for ccall): the first one is
+# kept, later callbacks do nothing, and it is rethrown after the call has returned (same contract as common.py's _snap).
+const SNAP_ERROR = Ref{Any}(nothing)
 function snap_trampoline(k::Int64, wn::Ptr{Cdouble}, user::Ptr{Cvoid})::Cvoid
+  SNAP_ERROR[] === nothing || return
   f = unsafe_pointer_to_objref(user)::Base.RefValue{Function}
-  f[](k)
+  try
+    f[](k)
+  catch err
+    SNAP_ERROR[] = err
+  end
+  return
+end
+function rethrow_snapshot_error()
+  err = SNAP_ERROR[]
+  SNAP_ERROR[] = nothing
+  err === nothing || throw(err)
   return
 end
 
@@ -93,6 +107,7 @@ numerical(nx, ny, nt, Δx, Δy, Δt, re, x, y, wn::Matrix{Float64}, ns) = begin
                 vmk_plan(nx, ny).handle, nt, Δx, Δy, Δt, re, wn, out, freq,
                 @cfunction(snap_trampoline, Cvoid, (Int64, Ptr{Cdouble}, Ptr{Cvoid})), pointer_from_objref(cb)))
   end
+  rethrow_snapshot_error()
   return out
 end
 
@@ -131,6 +146,7 @@ for (jlname, csym) in ((:numerical_hybrid, :vmk_hybrid_numerical), (:numerical_p
                   vmk_plan(nx, ny).handle, nt, Δx, Δy, Δt, re, wn, ut, freq,
                   @cfunction(snap_trampoline, Cvoid, (Int64, Ptr{Cdouble}, Ptr{Cvoid})), pointer_from_objref(cb)))
     end
+    rethrow_snapshot_error()
     return ut
   end
 end

@@ -231,7 +231,7 @@ def test_fft_form_along_j_still_served(gpu, oracle_c, n):
         s = np.zeros((n + 2, n + 2), order="F")
         l0 = p.launch_count
         gpu.fps(n, n, dx, dy, None, None, None, None, f, s)
-        assert p.launch_count - l0 == (7 if mode else 3)
+        assert p.launch_count - l0 == (6 if mode else 3)
         out.append(s)
     ref = np.zeros((n + 2, n + 2), order="F")
     oracle_c.fps(n, n, dx, dy, f, ref)
@@ -279,7 +279,7 @@ def test_fused_is_the_default_at_8192_and_agrees_with_the_other_forms(gpu, oracl
         s = np.zeros((n + 2, n + 2), order="F")
         l0 = p.launch_count
         gpu.fps(n, n, dx, dy, None, None, None, None, f, s)
-        assert p.launch_count - l0 == (7 if mode == 1 else 4)
+        assert p.launch_count - l0 == (6 if mode == 1 else 4)
         out[mode] = s
     ref = np.zeros((n + 2, n + 2), order="F")
     oracle_c.fps(n, n, dx, dy, f, ref)
@@ -349,10 +349,10 @@ def test_bench_contract_line(tmp_path):
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
-    # 3 steps x 3 stages x (K1, K2, K3, K4), or x (K1, totals, scan, K2 on the low rows, solve, copy of the low rows, K3, K4) with the
-    # recurrence form of the solve along j (the default from 2048^2 up)
+    # 3 steps x 3 stages x (K1, K2, K3, K4), or x (K1, totals, scan, K2 on the low rows, solve, K3, K4) with the
+    # recurrence form of the solve along j (the default from 2048^2 up), or x (K1, K2 on the low rows, scan, K3, K4) fused
     form = d["roofline"]["solve_along_j"]
-    per_stage = 5 if "fused form" in form else 8 if form.startswith("recurrences") else 4
+    per_stage = 5 if "fused form" in form else 7 if form.startswith("recurrences") else 4
     assert d["value"] > 0 and d["gpu_launches"] == 9 * per_stage and d["dtype"] == "f64" and d["vs_baseline"] is None
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
     rf = d["roofline"]
