@@ -123,7 +123,114 @@ def poisson_tri(n, dx, dy, f, K0=64, chunk=32):
     return np.fft.irfft(out, n=n, axis=0)
 
 
+def solve_rows_fused(x, r, q0, cc, units):
+    """The fused form (csrc/vmk_kernels.cuh, k1_body / k3_body with FUSED; kt_scanf_body), same blocking and the same
+    FP64 operations per value: unit q owns the row pairs [q npairs / U, (q+1) npairs / U).
+      K1: u0_m = x_m + r u0_(m-1) from zero at the block's first row; tp = u0 at its last row,
+          A = Horner in 1/r of u0 (al = r^(M-1) A), S = sum u0 (sum of x = (1 - r) S + r tp)
+      scan: blocks compose as (tp, al, R = r^M, Gam = r (1 - R^2) / (1 - r^2)); cyclic closure W = 1 / (1 - r^N)
+      K3: last row first, v_m = u0_m + q_m + r v_(m+1), q_(m-1) = q_m / r from q = r^M cu, psi_m = -(2 r / cc) v_m + dc
+    x: [rows, n] complex, one row per kx; r: long double per row."""
+    rows, n = x.shape
+    npairs = n // 2
+    first = [(q * npairs) // units for q in range(units + 1)]
+    r64 = r.astype(np.float64)
+    rinv = (1 / r).astype(np.float64)
+    L = np.longdouble
+    rl = r64.astype(L)  # the tables are powers of the rounded r
+    u0 = np.empty_like(x)
+    tp = np.zeros((rows, units), complex)
+    al = np.zeros((rows, units), complex)
+    xs = np.zeros(rows, complex)
+    Rb = np.ones((rows, units))
+    Gb = np.zeros((rows, units))
+    for q in range(units):
+        j0, j1 = 2 * first[q], 2 * first[q + 1]
+        M = j1 - j0
+        if M == 0:
+            continue
+        u = np.zeros(rows, complex)
+        A = np.zeros(rows, complex)
+        S = np.zeros(rows, complex)
+        for j in range(j0, j1):
+            u = u * r64 + x[:, j]
+            A = A * rinv + u
+            S = S + u
+            u0[:, j] = u
+        R = rl**M
+        tp[:, q] = u
+        al[:, q] = A * (rl**(M - 1)).astype(np.float64)
+        xs += S * (1.0 - r64) + r64 * u
+        Rb[:, q] = R.astype(np.float64)
+        Gb[:, q] = (rl * (1 - R * R) / (1 - rl * rl)).astype(np.float64)
+    # upwards over the blocks, cyclic closure, carries back down
+    lp = np.zeros(rows, complex)
+    AL = np.zeros(rows, complex)
+    rp = np.ones(rows)
+    for q in range(units):
+        z = lp * Gb[:, q] + al[:, q]
+        AL = AL + z * rp
+        rp = rp * Rb[:, q]
+        lp = lp * Rb[:, q] + tp[:, q]
+    RN = r**n
+    W = (1 / (1 - RN)).astype(np.float64)
+    GJ = (r * (1 - RN * RN) / (1 - r * r)).astype(np.float64)
+    cu0 = lp * W
+    cvd = (cu0 * GJ + AL) * W
+    cu = np.zeros((rows, units), complex)
+    acc = cu0
+    for q in range(units):
+        cu[:, q] = acc
+        acc = acc * Rb[:, q] + tp[:, q]
+    cv = np.zeros((rows, units), complex)
+    acc = cvd
+    for q in range(units - 1, -1, -1):
+        cv[:, q] = acc
+        acc = acc * Rb[:, q] + (cu[:, q] * Gb[:, q] + al[:, q])
+    dc = xs * q0.astype(np.float64)
+    kv = -2.0 * r64 / cc
+    out = np.empty_like(x)
+    for q in range(units):
+        j0, j1 = 2 * first[q], 2 * first[q + 1]
+        if j1 == j0:
+            continue
+        y = cv[:, q]
+        qq = cu[:, q] * Rb[:, q]
+        for j in range(j1 - 1, j0 - 1, -1):
+            y = y * r64 + (u0[:, j] + qq)
+            qq = qq * rinv
+            out[:, j] = y * kv + dc
+    return out
+
+
+def poisson_fused(n, dx, dy, f, K0=64, units=148):
+    ab, r, K, q0 = row_tables(n, dx, dy)
+    cc = 2 / dy**2
+    ck = np.cos(onp.wavenumbers(n))
+    X = np.fft.rfft(f, axis=0)  # [kx, j]
+    out = np.empty_like(X)
+    low = list(range(K0)) + [n // 2]
+    E = np.fft.fft(X[low, :], axis=1)
+    d = ab[low, None] + (cc * ck)[None, :]
+    E[0, 0] = 0
+    out[low, :] = np.fft.ifft(E / d, axis=1)
+    hi = np.arange(K0, n // 2)
+    out[hi, :] = solve_rows_fused(X[hi, :], r[hi], q0[hi], cc, units)
+    return np.fft.irfft(out, n=n, axis=0)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "fused":  # python tests/models/tri_model.py fused [n] [K0] [units]
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+        K0 = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+        units = int(sys.argv[4]) if len(sys.argv) > 4 else 148
+        dx = dy = 2 * np.pi / n
+        f = np.random.default_rng(3).standard_normal((n, n))
+        ref = onp.poisson(n, n, dx, dy, f)
+        got = poisson_fused(n, dx, dy, f, K0, units)
+        print(f"fused form: n={n} K0={K0} units={units}  white noise  rel-L2 = "
+              f"{np.linalg.norm(got - ref) / np.linalg.norm(ref):.3e}")
+        return
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     K0 = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 32

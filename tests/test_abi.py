@@ -70,3 +70,26 @@ def test_fails_loudly_without_gpu(lib):
     with pytest.raises(VmkError):
         Common(lib).fps(32, 32, .1, .1, None, None, None, None, np.zeros((32, 32), order="F"),
                         np.zeros((34, 34), order="F"))
+
+
+def test_fused_kernels_use_tensor_memory():
+    """the fused K1 / K3 (fps_mode 2) keep their per-slot state in tensor memory: their SASS holds tcgen05.ld / .st
+    (LDTM / STTM) and the allocation (UTCATOMSWS) -- and no tensor-core MMA; checked on the built library, no GPU needed"""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    import cfd_julia_b200
+    so = cfd_julia_b200.build()
+    txt = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for f in re.split(r"\n\s*Function : ", txt)[1:]:
+        name = f.split("\n", 1)[0]
+        if ("K1FBody" in name or "K3FBody" in name) and "FftCfgILi13" in name:
+            seen += 1
+            assert len(re.findall(r"\bLDTM\.", f)) >= 16 and len(re.findall(r"\bSTTM\.", f)) >= 32, name
+            assert "UTCATOMSWS" in f and "UTCMMA" not in f and "UTCHMMA" not in f, name
+        elif "Body" in name:
+            assert "LDTM" not in f or "FBody" in name, name  # no other kernel touches tensor memory
+    assert seen == 2
