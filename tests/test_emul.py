@@ -526,3 +526,26 @@ def test_fused_form_refused_where_it_does_not_apply(emul):
     with pytest.raises(Exception):
         p.set_option("fps_mode", 2)
     emul.clear_plans()
+
+
+@pytest.mark.parametrize("mode,ratio,grid_ctas", [(1, 1.7, 0), (2, 1.7, 0), (2, 0.4, 0), (2, 60.0, 0), (2, 60.0, 1)])
+def test_recurrence_forms_anisotropic_grid(emul, oracle_c, mode, ratio, grid_ctas):
+    """dy != dx: r, the block tables and (fused form) the range guard of the (1/r)^M Horner sum follow the grid; at
+    dy / dx = 60 with blocks of 130 rows ((1/r)^M = 1e540) the guard sends fps_mode 2 back to the separate kernels"""
+    n = 512
+    emul.clear_plans()
+    p = emul.plan(n, n)
+    p.set_option("fps_mode", mode)
+    if grid_ctas:
+        p.set_option("fz_grid", grid_ctas)
+    dx = 2 * np.pi / n
+    dy = ratio * dx
+    f = np.asfortranarray(np.random.default_rng(17).uniform(-1, 1, (n, n)))
+    s = np.zeros((n + 2, n + 2), order="F")
+    ref = np.zeros((n + 2, n + 2), order="F")
+    l0 = p.launch_count
+    emul.fps(n, n, dx, dy, None, None, None, None, f, s)
+    assert p.launch_count - l0 == (6 if mode == 1 or grid_ctas else 4)
+    oracle_c.fps(n, n, dx, dy, f, ref)
+    assert rel_l2(s[1:n + 1, 1:n + 1], ref[1:n + 1, 1:n + 1]) < 1e-12
+    emul.clear_plans()
