@@ -164,7 +164,8 @@ int vmk_profile_steps(vmk_plan* plan, double dx, double dy, double dt, double re
                       int64_t* launches);
 /* after vmk_profile_steps on a plan that solves along j by recurrences (option "fps_mode", csrc/vmk_tri.cuh): the part of
  * ms[1] / launches[1] spent in ms[0] chunk totals, ms[1] scan, ms[2] in-place solve (the rest of ms[1] is K2 on the rows
- * kx < K0) */
+ * kx < K0).  Fused form (fps_mode 2): totals and solve run inside K1 / K3 (classes 0 and 2 of vmk_profile_steps), so only
+ * the scan entry is non-zero */
 int vmk_profile_tri(vmk_plan* plan, double* ms, int64_t* launches);
 /* With the option "profile" set to 1, every kernel of the following calls on this plan (any solver) is bracketed by
  * CUDA events; vmk_profile_read sums them per class since the last read -- ms[0] row-forward transforms (K1), ms[1]
